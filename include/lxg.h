@@ -1,0 +1,150 @@
+/* lxg.h - C ABI of the B200 semantic-search hot path of lean-explore.
+ *
+ * This is the whole drop-in boundary: plain pointers and sizes, no torch / numpy / C++ types.
+ * Every entry point names the reference interface it replaces (paths relative to the
+ * reference repository justincasher/lean-explore @ 3a52d6b).  The reference delegates this
+ * arithmetic to the third-party wheels faiss-cpu (>=1.7) and sentence-transformers (>=2.2);
+ * the Python host side in lean_explore_b200/ binds these symbols with ctypes
+ * (INTEGRATION.md shows the stub a maintainer would add to the reference).
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative LXG_E* code otherwise, and never
+ *     aborts or exits (the MCP server maps start-up failures to sys.exit(1) itself,
+ *     src/lean_explore/mcp/server.py:153-181).  lxg_last_error() gives the message of the
+ *     last failure on the calling thread.
+ *   - nothing is ever printed to stdout (stdout is the MCP JSON-RPC channel,
+ *     src/lean_explore/mcp/server.py:33-38).
+ *   - device memory handed in (corpus, weights) stays owned by the caller (a torch.Tensor on
+ *     the Python side) and must outlive the handle.
+ *   - `stream` is a cudaStream_t passed as void*; NULL is the legacy default stream.
+ *   - handles may be used from any host thread; calls on one handle are serialised.
+ *   - there is no CPU fallback: without an sm_100 device lxg_init fails.
+ */
+#ifndef LXG_H_
+#define LXG_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LXG_OK 0
+#define LXG_EINVAL (-1)      /* bad argument */
+#define LXG_ECUDA (-2)       /* CUDA runtime / driver error */
+#define LXG_ENODEVICE (-3)   /* no sm_100 GPU */
+#define LXG_EUNSUPPORTED (-4)/* shape outside what the kernels cover */
+#define LXG_ETIES (-5)       /* > 16384 rows tie with the k-th score: exact result not representable */
+
+#define LXG_F32 0
+#define LXG_F16 1
+
+#define LXG_POOL_MEAN 0      /* sentence-transformers Pooling(mean) - all-MiniLM-L6-v2 */
+#define LXG_POOL_CLS 1       /* sentence-transformers Pooling(cls)  - bge-base-en-v1.5 */
+
+typedef struct lxg_index lxg_index;
+typedef struct lxg_encoder lxg_encoder;
+
+/* Library / device bring-up.  Selects `device`, checks it is compute capability 10.x and
+ * resolves the driver's tensor-map encoder.  Idempotent.  Replaces nothing in the reference
+ * (faiss-cpu needs no device); it is where "no CPU fallback" is enforced. */
+int lxg_init(int device);
+
+/* Message of the last failure on this thread ("" if none). */
+const char* lxg_last_error(void);
+
+/* ABI version, bumped on any signature change. */
+int lxg_abi_version(void);
+
+/* ---- flat inner-product index ------------------------------------------------------
+ * lxg_index_create replaces faiss.read_index()/IndexFlatIP.add() as used by
+ * SearchEngine._ensure_faiss_loaded (src/lean_explore/search/engine.py:151-161) on the matrix
+ * that extract/index.py:59-71 defines: `corpus_dev` is that [n, d] row-major matrix in device
+ * memory (fp32 as stored by the reference, or fp16), row i <-> faiss label i + row_offset.
+ * The rows are NOT normalised here (the reference does not either, extract/index.py:103-116).
+ * `row_offset` is the global row number of row 0 (row-sharded multi-GPU indexes). */
+int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t d, int dtype,
+                     int64_t row_offset);
+int lxg_index_destroy(lxg_index* index);
+int64_t lxg_index_ntotal(const lxg_index* index); /* faiss.Index.ntotal */
+int32_t lxg_index_d(const lxg_index* index);      /* faiss.Index.d */
+
+/* lxg_search replaces faiss.normalize_L2(x) + index.search(x, k)
+ * (src/lean_explore/search/engine.py:242 and :250) with IndexFlatIP semantics:
+ *   x        [nq, d] float32 queries, host or device memory (detected), NOT modified;
+ *   normalize != 0 applies faiss.normalize_L2 first (zero rows stay zero);
+ *   D_out    [nq, k] float32 inner products, best first; I_out [nq, k] int64 row ids;
+ *            host or device memory (detected); rows with fewer than k results are padded
+ *            with D = -FLT_MAX (-3.4028235e38), I = -1 exactly as FAISS does.
+ * Ties are ordered by ascending row id.  Ids are exact (certified against exact arithmetic),
+ * scores are the correctly rounded fp32 of the exact inner product.
+ * With host outputs the call returns after the results have landed; with device outputs it
+ * is asynchronous on `stream`. */
+int lxg_search(lxg_index* index, const float* x, int32_t nq, int32_t k, int normalize,
+               float* D_out, int64_t* I_out, void* stream);
+
+/* Same, plus optional exact fp64 scores D64_out [nq, k] (device memory) used to merge
+ * row-shards without losing the order of scores that collide in fp32. */
+int lxg_search_ex(lxg_index* index, const float* x, int32_t nq, int32_t k, int normalize,
+                  float* D_out, int64_t* I_out, double* D64_out, void* stream);
+
+/* In-place faiss.normalize_L2(x) on a device or host [nq, d] float32 matrix
+ * (src/lean_explore/search/engine.py:242) for callers that want the normalised queries. */
+int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream);
+
+/* Merge step of a row-sharded index: Dg/Ig are the all-gathered per-shard results
+ * [shards, nq, k] (exact fp64 scores, global ids, -1 padded; device memory); writes the global
+ * top-k to D_out/I_out (device).  No reference analogue (the reference is single-process);
+ * it is the exchange step of SURVEY.md section 8(e). */
+int lxg_merge_topk(const double* Dg, const int64_t* Ig, int32_t nq, int32_t k, int32_t shards,
+                   float* D_out, int64_t* I_out, void* stream);
+
+/* Counters of the last lxg_search on this handle (tests, bench.py). */
+typedef struct lxg_search_stats {
+  int32_t kernel_launches;   /* kernels launched by the call */
+  int32_t slices;            /* corpus slices per query block */
+  int32_t query_blocks;      /* blocks of 128 queries */
+  int32_t kp;                /* candidates kept per (slice, query) */
+  int32_t uncertified;       /* queries re-done by the exact path (-1 if not read back) */
+  int32_t tile_rows;         /* corpus rows per tcgen05 accumulator tile */
+} lxg_search_stats;
+int lxg_index_last_stats(const lxg_index* index, lxg_search_stats* out);
+
+/* Test hook: raw tensor-core scores of pass 1 (scores_dev [nq, n] float32, scaled by
+ * qscale_dev[q] * scan_scale) so the TMA/tcgen05 data path can be checked in isolation. */
+int lxg_debug_scores(lxg_index* index, const float* x_dev, int32_t nq, int normalize,
+                     float* scores_dev, float* qscale_dev, float* scan_scale_host, void* stream);
+
+/* ---- sentence encoder (BERT-class) --------------------------------------------------
+ * Replaces SentenceTransformer.encode inside EmbeddingClient.embed
+ * (src/lean_explore/util/embedding_client.py:88-101): transformer forward -> pooling ->
+ * L2 normalise.  Weights are fp16 device pointers laid out as HF BertModel stores them
+ * (nn.Linear weight [out, in] row-major), owned by the caller. */
+typedef struct lxg_bert_layer {
+  const void *wqkv, *bqkv;   /* [3H, H], [3H]  (query|key|value stacked) */
+  const void *wo, *bo;       /* [H, H], [H] */
+  const void *ln1_g, *ln1_b; /* attention.output.LayerNorm */
+  const void *w1, *b1;       /* intermediate.dense [F, H], [F] */
+  const void *w2, *b2;       /* output.dense [H, F], [H] */
+  const void *ln2_g, *ln2_b; /* output.LayerNorm */
+} lxg_bert_layer;
+
+typedef struct lxg_bert_weights {
+  int32_t hidden, layers, heads, ffn, vocab, max_pos;
+  float ln_eps;
+  const void *word_emb, *pos_emb, *type_emb; /* [vocab,H], [max_pos,H], [2,H] */
+  const void *emb_ln_g, *emb_ln_b;
+  const lxg_bert_layer* layer;               /* host array of `layers` entries */
+} lxg_bert_weights;
+
+int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w);
+int lxg_encoder_destroy(lxg_encoder* enc);
+/* ids/mask: [b, s] int32 token ids / attention mask (host or device); out: [b, H] float32
+ * unit vectors (host or device).  pool = LXG_POOL_MEAN | LXG_POOL_CLS. */
+int lxg_encode(lxg_encoder* enc, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,
+               int pool, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LXG_H_ */

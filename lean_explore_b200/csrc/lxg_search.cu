@@ -1,0 +1,595 @@
+// C-ABI entry points of the flat inner-product index (include/lxg.h).  Host logic only:
+// workspace sizing, slice/tile partitioning, tensor-map construction, launches.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lxg.h"
+#include "common.h"
+#include "rescore.cuh"
+#include "scan_topk.cuh"
+
+namespace lxg {
+
+thread_local std::string g_last_error;
+int set_error(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+
+static std::mutex g_init_mutex;
+static bool g_inited = false;
+static int g_device = -1;
+static int g_num_sms = 0;
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode_tiled = nullptr;
+
+int num_sms() { return g_num_sms; }
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// One growable device allocation.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    const size_t want = need + need / 4;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t reserve(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMallocHost(&p, need + need / 4);
+    if (e == cudaSuccess) bytes = need + need / 4;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+};
+
+}  // namespace lxg
+
+using namespace lxg;
+
+struct lxg_index {
+  CorpusView cv{};
+  __half* scan = nullptr;  // fp16 rows the tensor cores stream (== cv.rows when it can alias)
+  bool scan_owned = false;
+  int scan_pitch = 0;      // elements
+  int tile_rows = 0;       // N_T
+  int num_kc = 0;
+  CUtensorMap tmap{};
+  std::mutex mu;
+  DevBuf ws_cand, ws_small, ws_x, ws_out, ws_exact;
+  HostBuf h_stage;
+  lxg_search_stats stats{};
+};
+
+namespace {
+
+int build_tensor_map(lxg_index* ix) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ix->cv.d), static_cast<cuuint64_t>(ix->cv.n)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ix->scan_pitch) * sizeof(__half)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKC), static_cast<cuuint32_t>(ix->tile_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(&ix->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ix->scan, gdim, gstride,
+                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LXG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return LXG_OK;
+}
+
+int candidates_per_slice(int k) {
+  // kp = k plus a margin (so that the exactness certificate almost always holds), rounded to 32
+  const int margin = std::max(14, k / 4);
+  return ((k + margin + 31) / 32) * 32;
+}
+
+struct Plan {
+  int kp, cap, qblocks, slices, tiles_per_slice, num_tiles;
+};
+
+Plan make_plan(const lxg_index* ix, int nq, int k) {
+  Plan pl;
+  pl.kp = candidates_per_slice(k);
+  pl.cap = 2 * pl.kp;
+  pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
+  pl.num_tiles = static_cast<int>((ix->cv.n + ix->tile_rows - 1) / ix->tile_rows);
+  int s = std::max(1, g_num_sms / pl.qblocks);
+  s = std::min(s, std::max(1, 24576 / pl.kp));  // merge kernel keeps slices*kp keys in shared memory
+  s = std::min(s, 148);
+  s = std::min(s, std::max(1, pl.num_tiles));
+  pl.tiles_per_slice = (pl.num_tiles + s - 1) / s;
+  pl.slices = std::max(1, (pl.num_tiles + pl.tiles_per_slice - 1) / std::max(1, pl.tiles_per_slice));
+  return pl;
+}
+
+template <int N_T>
+cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int qblocks, cudaStream_t st) {
+  static bool attr_set = false;
+  const int smem = kStageRing + 1024;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<N_T>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid(sp.slices, qblocks, 1);
+  scan_topk_kernel<N_T><<<grid, kScanThreads, smem, st>>>(ix->tmap, sp);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+extern "C" {
+
+int lxg_abi_version(void) { return 1; }
+
+const char* lxg_last_error(void) { return g_last_error.c_str(); }
+
+int lxg_init(int device) {
+  std::lock_guard<std::mutex> lock(g_init_mutex);
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return set_error(LXG_ENODEVICE,
+                     std::string("no CUDA device visible (") + cudaGetErrorString(e) +
+                         "); the lxg kernels are sm_100a only and there is no CPU fallback");
+  }
+  if (device < 0 || device >= count) return set_error(LXG_EINVAL, "device index out of range");
+  cudaDeviceProp prop;
+  LXG_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(LXG_ENODEVICE, std::string("device is ") + prop.name + " (sm_" +
+                                        std::to_string(prop.major) + std::to_string(prop.minor) +
+                                        "); lxg needs sm_100 (B200)");
+  LXG_CUDA(cudaSetDevice(device));
+  LXG_CUDA(cudaFree(nullptr));
+  if (!g_encode_tiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    LXG_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess)
+      return set_error(LXG_ECUDA, "driver does not export cuTensorMapEncodeTiled");
+    g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  g_num_sms = prop.multiProcessorCount;
+  g_device = device;
+  g_inited = true;
+  return LXG_OK;
+}
+
+int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t d, int dtype,
+                     int64_t row_offset) {
+  if (!out) return set_error(LXG_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!g_inited) return set_error(LXG_EINVAL, "lxg_init has not been called");
+  if (n < 0 || d <= 0 || (dtype != LXG_F32 && dtype != LXG_F16))
+    return set_error(LXG_EINVAL, "bad n / d / dtype");
+  if (n >= (1ll << 31) - 256) return set_error(LXG_EUNSUPPORTED, "more than 2^31 rows per shard");
+  if (d > 768)
+    return set_error(LXG_EUNSUPPORTED,
+                     "d > 768: the fp16 query block must fit tensor memory next to two accumulators");
+  if (n > 0 && (!corpus_dev || !is_device_ptr(corpus_dev)))
+    return set_error(LXG_EINVAL, "corpus_dev must be device memory");
+  lxg_index* ix = new lxg_index();
+  ix->cv.rows = corpus_dev;
+  ix->cv.pitch = d;
+  ix->cv.dtype = dtype;
+  ix->cv.n = static_cast<int>(n);
+  ix->cv.d = d;
+  ix->cv.row_offset = row_offset;
+  ix->cv.max_row_norm = 0.f;
+  ix->cv.scan_scale = 1.f;
+  ix->num_kc = (d + kKC - 1) / kKC;
+  ix->tile_rows = (ix->num_kc * 32 + 256 <= 512) ? 128 : 64;
+  const float sqrt_d = std::sqrt(static_cast<float>(d));
+  const bool alias = dtype == LXG_F16 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(corpus_dev) % 16 == 0);
+  if (n > 0) {
+    // statistics for the certificate: max row norm, max |element|
+    const int blocks = std::min<int64_t>(4 * g_num_sms, (n + 7) / 8);
+    DevBuf tmp;
+    cudaError_t e = tmp.reserve(blocks * (sizeof(double) + sizeof(float)));
+    if (e != cudaSuccess) {
+      delete ix;
+      return set_error(LXG_ECUDA, cudaGetErrorString(e));
+    }
+    double* bn = reinterpret_cast<double*>(tmp.p);
+    float* ba = reinterpret_cast<float*>(bn + blocks);
+    corpus_stats_kernel<<<blocks, 256>>>(corpus_dev, d, dtype, n, d, bn, ba);
+    std::vector<double> hn(blocks);
+    std::vector<float> ha(blocks);
+    e = cudaMemcpy(hn.data(), bn, blocks * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(ha.data(), ba, blocks * sizeof(float), cudaMemcpyDeviceToHost);
+    tmp.release();
+    if (e != cudaSuccess) {
+      delete ix;
+      return set_error(LXG_ECUDA, std::string("corpus statistics: ") + cudaGetErrorString(e));
+    }
+    double n2 = 0;
+    float amax = 0;
+    for (int i = 0; i < blocks; ++i) {
+      n2 = std::max(n2, hn[i]);
+      amax = std::max(amax, ha[i]);
+    }
+    if (!std::isfinite(n2) || !std::isfinite(amax)) {
+      delete ix;
+      return set_error(LXG_EINVAL, "corpus contains non-finite values");
+    }
+    ix->cv.max_row_norm = static_cast<float>(std::sqrt(n2) * 1.000001);
+    if (alias) {
+      ix->scan = const_cast<__half*>(reinterpret_cast<const __half*>(corpus_dev));
+      ix->scan_pitch = d;
+      ix->cv.scan_scale = 1.f;
+    } else {
+      ix->scan_pitch = ((d + 7) / 8) * 8;
+      float scale = 1.f;
+      if (dtype == LXG_F32 && amax > 0.f) scale = std::ldexp(1.f, -std::ilogb(amax));
+      ix->cv.scan_scale = scale;
+      e = cudaMalloc(&ix->scan, static_cast<size_t>(n) * ix->scan_pitch * sizeof(__half));
+      if (e != cudaSuccess) {
+        delete ix;
+        return set_error(LXG_ECUDA, std::string("scan copy: ") + cudaGetErrorString(e));
+      }
+      ix->scan_owned = true;
+      make_scan_copy_kernel<<<8 * g_num_sms, 256>>>(corpus_dev, d, dtype, n, d, ix->scan,
+                                                    ix->scan_pitch, scale);
+      e = cudaDeviceSynchronize();
+      if (e != cudaSuccess) {
+        cudaFree(ix->scan);
+        delete ix;
+        return set_error(LXG_ECUDA, std::string("scan copy kernel: ") + cudaGetErrorString(e));
+      }
+    }
+    int rc = build_tensor_map(ix);
+    if (rc != LXG_OK) {
+      if (ix->scan_owned) cudaFree(ix->scan);
+      delete ix;
+      return rc;
+    }
+  }
+  // |tensor-core score - exact score| <= rel_err * ||row|| * ||query||  (certificate)
+  const float u16 = 1.0f / 2048.0f;  // fp16 round-to-nearest unit
+  float rel = u16 * 1.001f;          // query fp32 -> fp16
+  if (dtype == LXG_F32) rel += u16 * 1.001f;  // corpus fp32 -> fp16 scan copy
+  rel += 1.0f / 65536.0f;                     // fp32 accumulation inside the tensor core
+  rel += sqrt_d * (1.0f / 8388608.0f);        // fp16 subnormal flush of tiny elements
+  ix->cv.rel_err = rel;
+  *out = ix;
+  return LXG_OK;
+}
+
+int lxg_index_destroy(lxg_index* ix) {
+  if (!ix) return LXG_OK;
+  if (ix->scan_owned && ix->scan) cudaFree(ix->scan);
+  ix->ws_cand.release();
+  ix->ws_small.release();
+  ix->ws_x.release();
+  ix->ws_out.release();
+  ix->ws_exact.release();
+  ix->h_stage.release();
+  delete ix;
+  return LXG_OK;
+}
+
+int64_t lxg_index_ntotal(const lxg_index* ix) { return ix ? ix->cv.n : -1; }
+int32_t lxg_index_d(const lxg_index* ix) { return ix ? ix->cv.d : -1; }
+
+int lxg_index_last_stats(const lxg_index* ix, lxg_search_stats* out) {
+  if (!ix || !out) return set_error(LXG_EINVAL, "NULL argument");
+  *out = ix->stats;
+  return LXG_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Device-side search of up to 148*128 queries.  All pointers are device memory.
+int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, float* D, long long* I,
+                  double* D64, float* dbg_scores, float* dbg_qscale, cudaStream_t st, bool read_flags) {
+  const int d = ix->cv.d;
+  const Plan pl = make_plan(ix, nq, k);
+  const size_t lists = static_cast<size_t>(pl.slices) * nq;
+  LXG_CUDA(ix->ws_cand.reserve(lists * pl.cap * sizeof(uint2)));
+  // small arrays: cand_count, slice_thr [lists]; qscale, qnorm [nq]; flag_count(1)+overflow(1)+pad,
+  // flag_list [nq]; flag_theta [nq] (double)
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    const size_t o = off;
+    off += (bytes + 255) / 256 * 256;
+    return o;
+  };
+  const size_t o_count = take(lists * sizeof(int));
+  const size_t o_thr = take(lists * sizeof(float));
+  const size_t o_qscale = take(nq * sizeof(float));
+  const size_t o_qnorm = take(nq * sizeof(float));
+  const size_t o_flags = take(64);
+  const size_t o_flist = take(nq * sizeof(int));
+  const size_t o_theta = take(nq * sizeof(double));
+  LXG_CUDA(ix->ws_small.reserve(off));
+  LXG_CUDA(ix->ws_x.reserve(static_cast<size_t>(nq) * d * sizeof(float)));
+  uint8_t* sm = reinterpret_cast<uint8_t*>(ix->ws_small.p);
+  int* flag_count = reinterpret_cast<int*>(sm + o_flags);
+  int* overflow = flag_count + 1;
+
+  ScanParams sp{};
+  sp.x = x;
+  sp.xn = reinterpret_cast<float*>(ix->ws_x.p);
+  sp.qscale = dbg_qscale ? dbg_qscale : reinterpret_cast<float*>(sm + o_qscale);
+  sp.qnorm = reinterpret_cast<float*>(sm + o_qnorm);
+  sp.cand = reinterpret_cast<uint2*>(ix->ws_cand.p);
+  sp.cand_count = reinterpret_cast<int*>(sm + o_count);
+  sp.slice_thr = reinterpret_cast<float*>(sm + o_thr);
+  sp.dbg_scores = dbg_scores;
+  sp.nq = nq;
+  sp.d = d;
+  sp.num_kc = ix->num_kc;
+  sp.n = ix->cv.n;
+  sp.num_tiles = pl.num_tiles;
+  sp.slices = pl.slices;
+  sp.tiles_per_slice = pl.tiles_per_slice;
+  sp.kp = pl.kp;
+  sp.cap = pl.cap;
+  sp.normalize = normalize;
+
+  int launches = 0;
+  LXG_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
+  if (ix->tile_rows == 128)
+    LXG_CUDA(launch_scan<128>(ix, sp, pl.qblocks, st));
+  else
+    LXG_CUDA(launch_scan<64>(ix, sp, pl.qblocks, st));
+  ++launches;
+  ix->stats.slices = pl.slices;
+  ix->stats.query_blocks = pl.qblocks;
+  ix->stats.kp = pl.kp;
+  ix->stats.tile_rows = ix->tile_rows;
+  ix->stats.uncertified = -1;
+  if (dbg_scores) {
+    ix->stats.kernel_launches = launches;
+    return LXG_OK;
+  }
+
+  MergeParams mp{};
+  mp.cand = sp.cand;
+  mp.cand_count = sp.cand_count;
+  mp.slice_thr = sp.slice_thr;
+  mp.xn = sp.xn;
+  mp.qscale = sp.qscale;
+  mp.qnorm = sp.qnorm;
+  mp.out_d = D;
+  mp.out_i = I;
+  mp.out_d64 = D64;
+  mp.flag_count = flag_count;
+  mp.flag_list = reinterpret_cast<int*>(sm + o_flist);
+  mp.flag_theta = reinterpret_cast<double*>(sm + o_theta);
+  mp.nq = nq;
+  mp.k = k;
+  mp.kp = pl.kp;
+  mp.cap = pl.cap;
+  mp.slices = pl.slices;
+  const size_t msmem = static_cast<size_t>(pl.slices) * pl.kp * 8 + static_cast<size_t>(pl.kp) * 12 +
+                       static_cast<size_t>(d) * 4 + 64;
+  static size_t merge_attr = 0;
+  if (msmem > merge_attr) {
+    LXG_CUDA(cudaFuncSetAttribute(merge_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(msmem)));
+    merge_attr = msmem;
+  }
+  merge_rescore_kernel<<<nq, kMergeThreads, msmem, st>>>(mp, ix->cv);
+  LXG_CUDA(cudaGetLastError());
+  ++launches;
+
+  // exact path for uncertified queries (normally zero of them: both kernels exit at once)
+  const int nflag_max = std::min(nq, 256);
+  const size_t ex_bytes = static_cast<size_t>(nflag_max) * kExactListCap * (sizeof(double) + sizeof(unsigned)) +
+                          static_cast<size_t>(nflag_max) * sizeof(int) + 256;
+  LXG_CUDA(ix->ws_exact.reserve(ex_bytes));
+  ExactParams ep{};
+  ep.xn = sp.xn;
+  ep.flag_count = flag_count;
+  ep.flag_list = mp.flag_list;
+  ep.flag_theta = mp.flag_theta;
+  ep.list_score = reinterpret_cast<double*>(ix->ws_exact.p);
+  ep.list_row = reinterpret_cast<unsigned*>(ep.list_score + static_cast<size_t>(nflag_max) * kExactListCap);
+  ep.list_count = reinterpret_cast<int*>(ep.list_row + static_cast<size_t>(nflag_max) * kExactListCap);
+  ep.out_d = D;
+  ep.out_i = I;
+  ep.out_d64 = D64;
+  ep.overflow = overflow;
+  ep.nq = nq;
+  ep.k = k;
+  ep.nflag_max = nflag_max;
+  LXG_CUDA(cudaMemsetAsync(ep.list_count, 0, nflag_max * sizeof(int), st));
+  exact_collect_kernel<<<2 * g_num_sms, 256, d * sizeof(float), st>>>(ep, ix->cv);
+  LXG_CUDA(cudaGetLastError());
+  exact_finalize_kernel<<<nflag_max, 256, 0, st>>>(ep, ix->cv);
+  LXG_CUDA(cudaGetLastError());
+  launches += 2;
+  ix->stats.kernel_launches = launches;
+
+  if (read_flags) {
+    int h[2] = {0, 0};
+    LXG_CUDA(cudaMemcpyAsync(h, flag_count, sizeof(h), cudaMemcpyDeviceToHost, st));
+    LXG_CUDA(cudaStreamSynchronize(st));
+    ix->stats.uncertified = h[0];
+    if (h[0] > nflag_max)
+      return set_error(LXG_ETIES, "more than 256 queries of one batch needed the exact path");
+    if (h[1])
+      return set_error(LXG_ETIES, "more than 16384 corpus rows tie with the k-th best score of a query");
+  }
+  return LXG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int normalize, float* D_out,
+                  int64_t* I_out, double* D64_out, void* stream) {
+  if (!ix || !D_out || !I_out) return set_error(LXG_EINVAL, "NULL argument");
+  if (nq < 0 || k <= 0) return set_error(LXG_EINVAL, "nq must be >= 0 and k >= 1");
+  if (k > 2048) return set_error(LXG_EUNSUPPORTED, "k > 2048");
+  if (nq == 0) return LXG_OK;
+  if (!x) return set_error(LXG_EINVAL, "x is NULL");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int d = ix->cv.d;
+  const bool x_dev = is_device_ptr(x);
+  const bool out_dev = is_device_ptr(D_out);
+  if (out_dev != is_device_ptr(I_out))
+    return set_error(LXG_EINVAL, "D_out and I_out must both be host or both be device memory");
+  if (D64_out && !is_device_ptr(D64_out)) return set_error(LXG_EINVAL, "D64_out must be device memory");
+  ix->stats = lxg_search_stats{};
+
+  const size_t out_elems = static_cast<size_t>(nq) * k;
+  if (ix->cv.n == 0) {  // empty index: FAISS returns all -1 / -FLT_MAX
+    std::vector<float> hd(out_elems, -FLT_MAX);
+    std::vector<long long> hi(out_elems, -1);
+    if (out_dev) {
+      LXG_CUDA(cudaMemcpyAsync(D_out, hd.data(), out_elems * 4, cudaMemcpyHostToDevice, st));
+      LXG_CUDA(cudaMemcpyAsync(I_out, hi.data(), out_elems * 8, cudaMemcpyHostToDevice, st));
+      LXG_CUDA(cudaStreamSynchronize(st));
+    } else {
+      std::memcpy(D_out, hd.data(), out_elems * 4);
+      std::memcpy(I_out, hi.data(), out_elems * 8);
+    }
+    return LXG_OK;
+  }
+
+  // device staging for host-side arguments
+  const size_t x_bytes = static_cast<size_t>(nq) * d * sizeof(float);
+  const size_t stage_bytes = (x_dev ? 0 : x_bytes) + (out_dev ? 0 : out_elems * 12) + 256;
+  LXG_CUDA(ix->ws_out.reserve(stage_bytes));
+  uint8_t* stg = reinterpret_cast<uint8_t*>(ix->ws_out.p);
+  const float* xd = x;
+  if (!x_dev) {
+    LXG_CUDA(ix->h_stage.reserve(std::max(x_bytes, out_elems * 12)));
+    std::memcpy(ix->h_stage.p, x, x_bytes);
+    LXG_CUDA(cudaMemcpyAsync(stg, ix->h_stage.p, x_bytes, cudaMemcpyHostToDevice, st));
+    xd = reinterpret_cast<const float*>(stg);
+    stg += (x_bytes + 255) / 256 * 256;
+  }
+  float* Dd = D_out;
+  long long* Id = reinterpret_cast<long long*>(I_out);
+  if (!out_dev) {
+    Id = reinterpret_cast<long long*>(stg);
+    Dd = reinterpret_cast<float*>(stg + out_elems * 8);
+  }
+  // at most 148 query blocks per launch
+  const int max_q = 148 * kQueryBlock;
+  int total_launches = 0, total_flag = 0;
+  for (int q0 = 0; q0 < nq; q0 += max_q) {
+    const int nb = std::min(max_q, nq - q0);
+    int rc = search_device(ix, xd + static_cast<size_t>(q0) * d, nb, k, normalize,
+                           Dd + static_cast<size_t>(q0) * k, Id + static_cast<size_t>(q0) * k,
+                           D64_out ? D64_out + static_cast<size_t>(q0) * k : nullptr, nullptr, nullptr, st,
+                           /*read_flags=*/!out_dev || nq > max_q);
+    if (rc != LXG_OK) return rc;
+    total_launches += ix->stats.kernel_launches;
+    if (ix->stats.uncertified > 0) total_flag += ix->stats.uncertified;
+  }
+  ix->stats.kernel_launches = total_launches;
+  if (!out_dev) {
+    ix->stats.uncertified = total_flag;
+    LXG_CUDA(ix->h_stage.reserve(out_elems * 12));
+    LXG_CUDA(cudaMemcpyAsync(ix->h_stage.p, Id, out_elems * 12, cudaMemcpyDeviceToHost, st));
+    LXG_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(I_out, ix->h_stage.p, out_elems * 8);
+    std::memcpy(D_out, reinterpret_cast<uint8_t*>(ix->h_stage.p) + out_elems * 8, out_elems * 4);
+  }
+  return LXG_OK;
+}
+
+int lxg_search(lxg_index* ix, const float* x, int32_t nq, int32_t k, int normalize, float* D_out,
+               int64_t* I_out, void* stream) {
+  return lxg_search_ex(ix, x, nq, k, normalize, D_out, I_out, nullptr, stream);
+}
+
+int lxg_debug_scores(lxg_index* ix, const float* x_dev, int32_t nq, int normalize, float* scores_dev,
+                     float* qscale_dev, float* scan_scale_host, void* stream) {
+  if (!ix || !x_dev || !scores_dev || !qscale_dev) return set_error(LXG_EINVAL, "NULL argument");
+  if (nq <= 0 || nq > 148 * kQueryBlock) return set_error(LXG_EINVAL, "nq out of range");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  if (scan_scale_host) *scan_scale_host = ix->cv.scan_scale;
+  return search_device(ix, x_dev, nq, 1, normalize, nullptr, nullptr, nullptr, scores_dev, qscale_dev,
+                       reinterpret_cast<cudaStream_t>(stream), false);
+}
+
+int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream) {
+  if (!x || nq < 0 || d <= 0) return set_error(LXG_EINVAL, "bad argument");
+  if (nq == 0) return LXG_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const size_t bytes = static_cast<size_t>(nq) * d * sizeof(float);
+  if (is_device_ptr(x)) {
+    normalize_l2_kernel<<<(nq + 127) / 128, 128, 0, st>>>(x, nq, d);
+    LXG_CUDA(cudaGetLastError());
+    return LXG_OK;
+  }
+  float* tmp = nullptr;
+  LXG_CUDA(cudaMalloc(&tmp, bytes));
+  cudaError_t e = cudaMemcpyAsync(tmp, x, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    normalize_l2_kernel<<<(nq + 127) / 128, 128, 0, st>>>(tmp, nq, d);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(x, tmp, bytes, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(tmp);
+  LXG_CUDA(e);
+  return LXG_OK;
+}
+
+int lxg_merge_topk(const double* Dg, const int64_t* Ig, int32_t nq, int32_t k, int32_t shards, float* D_out,
+                   int64_t* I_out, void* stream) {
+  if (!Dg || !Ig || !D_out || !I_out) return set_error(LXG_EINVAL, "NULL argument");
+  if (nq < 0 || k <= 0 || shards <= 0) return set_error(LXG_EINVAL, "bad nq / k / shards");
+  if (nq == 0) return LXG_OK;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const int warps = 8;
+  merge_shards_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, st>>>(
+      Dg, reinterpret_cast<const long long*>(Ig), nq, k, shards, D_out, reinterpret_cast<long long*>(I_out));
+  LXG_CUDA(cudaGetLastError());
+  return LXG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,421 @@
+// Pass 2 of the flat inner-product search: per query, merge the per-slice candidate lists of
+// pass 1, re-score the best kp exactly (fp64 accumulation of exact fp32 x fp16/fp32 products),
+// order them (score desc, row asc - the tie rule of FAISS' CMin heap, see oracle/faiss_flat.py),
+// write the (D float32[nq,k], I int64[nq,k]) result that faiss.Index.search returns
+// (reference call site src/lean_explore/search/engine.py:250) and CERTIFY it: the result is
+// provably the exact top-k iff the k-th exact score beats every possible score of a dropped
+// row (a_min + eps).  Uncertified queries (near-duplicate rows around rank k) are re-done by
+// the exact collectors at the end of this file, so ids are exact in every case.
+#pragma once
+#include <cfloat>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "scan_topk.cuh"
+
+namespace lxg {
+
+constexpr int kMergeThreads = 256;
+constexpr int kExactListCap = 16384;  // rows an uncertified query may collect before we give up
+
+struct CorpusView {
+  const void* rows;   // original corpus rows (fp32 or fp16), used for exact scores
+  long long pitch;    // elements between rows
+  int dtype;          // 0 = fp32, 1 = fp16
+  int n, d;
+  long long row_offset;  // added to every output id (row-sharded indexes)
+  float max_row_norm;    // upper bound of ||row||_2 over the corpus
+  float scan_scale;      // power-of-two scale baked into the fp16 scan copy
+  float rel_err;         // relative bound of |tensor-core score - exact score| / (||c|| ||q||)
+};
+
+struct MergeParams {
+  const uint2* cand;
+  const int* cand_count;
+  const float* slice_thr;
+  const float* xn;
+  const float* qscale;
+  const float* qnorm;
+  float* out_d;        // [nq, k]
+  long long* out_i;    // [nq, k]
+  double* out_d64;     // optional [nq, k] exact scores (sharded merge), else nullptr
+  int* flag_count;     // number of uncertified queries
+  int* flag_list;      // [nq] their ids
+  double* flag_theta;  // [nq] lower bound of the true k-th best exact score
+  int nq, k, kp, cap, slices;
+};
+
+// Exact inner product of one corpus row with a query held in shared memory, computed by a
+// full warp.  Products of an fp32 by an fp16/fp32 value are exact in fp64; the summation order
+// is fixed (lane-strided, then xor tree), so the value is identical wherever it is computed.
+__device__ __forceinline__ double warp_exact_dot(const CorpusView& cv, long long row,
+                                                 const float* __restrict__ xq, int lane) {
+  double acc = 0.0;
+  if (cv.dtype == 1) {
+    const __half* r = reinterpret_cast<const __half*>(cv.rows) + row * cv.pitch;
+    for (int i = lane; i < cv.d; i += 32)
+      acc = fma(static_cast<double>(__half2float(r[i])), static_cast<double>(xq[i]), acc);
+  } else {
+    const float* r = reinterpret_cast<const float*>(cv.rows) + row * cv.pitch;
+    for (int i = lane; i < cv.d; i += 32)
+      acc = fma(static_cast<double>(r[i]), static_cast<double>(xq[i]), acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  return acc;
+}
+
+__device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsigned ib) {
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+// One CTA per query.  Dynamic shared memory: slices*kp 64-bit keys, then kp (double,uint) pairs,
+// then d floats.
+__global__ void __launch_bounds__(kMergeThreads)
+merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int max_items = p.slices * p.kp;
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(msm);
+  double* sel_score = reinterpret_cast<double*>(keys + max_items);
+  unsigned* sel_row = reinterpret_cast<unsigned*>(sel_score + p.kp);
+  float* xq = reinterpret_cast<float*>(sel_row + p.kp);
+  __shared__ int s_off[160];
+  __shared__ int s_cnt, s_sel;
+  __shared__ float s_t0;
+  __shared__ double s_kth;
+
+  for (int i = tid; i < cv.d; i += kMergeThreads) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
+  if (tid == 0) {
+    int off = 0;
+    float t0 = -CUDART_INF_F;
+    for (int s = 0; s < p.slices; ++s) {
+      s_off[s] = off;
+      off += p.cand_count[static_cast<size_t>(s) * p.nq + q];
+      t0 = fmaxf(t0, p.slice_thr[static_cast<size_t>(s) * p.nq + q]);
+    }
+    s_off[p.slices] = off;
+    s_t0 = t0;
+    s_sel = 0;
+    s_kth = 0.0;
+  }
+  __syncthreads();
+  const int m = s_off[p.slices];
+  // composite key: higher score first, then lower row
+  for (int s = warp; s < p.slices; s += kMergeThreads / 32) {
+    const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
+    const int c = s_off[s + 1] - s_off[s];
+    for (int i = lane; i < c; i += 32) {
+      const uint2 e = __ldcg(lst + i);
+      keys[s_off[s] + i] =
+          (static_cast<unsigned long long>(float_to_key(e.x)) << 32) | (0xFFFFFFFFu - e.y);
+    }
+  }
+  __syncthreads();
+
+  // kp-th largest composite key (keys are distinct: rows are distinct)
+  unsigned long long prefix = 0;
+  float a_min = s_t0;  // approx score no dropped row can exceed (scaled units)
+  if (m > p.kp) {
+    for (int bit = 63; bit >= 0; --bit) {
+      const unsigned long long cnd = prefix | (1ull << bit);
+      int mine = 0;
+      for (int i = tid; i < m; i += kMergeThreads) mine += (keys[i] >= cnd) ? 1 : 0;
+      if (tid == 0) s_cnt = 0;
+      __syncthreads();
+      mine = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
+      __syncthreads();
+      if (s_cnt >= p.kp) prefix = cnd;
+      __syncthreads();
+    }
+    a_min = fmaxf(a_min, __uint_as_float(key_to_float_bits(static_cast<uint32_t>(prefix >> 32))));
+  }
+  // gather the selected rows
+  for (int i = tid; i < m; i += kMergeThreads) {
+    if (keys[i] >= prefix) {
+      const int slot = atomicAdd(&s_sel, 1);
+      sel_row[slot] = 0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xFFFFFFFFu);
+    }
+  }
+  __syncthreads();
+  const int nsel = s_sel;  // == min(m, kp)
+  // exact re-score
+  for (int j = warp; j < nsel; j += kMergeThreads / 32) {
+    const double s = warp_exact_dot(cv, sel_row[j], xq, lane);
+    if (lane == 0) sel_score[j] = s;
+  }
+  __syncthreads();
+  // rank by counting, emit the top k
+  const int k = p.k;
+  for (int j = tid; j < nsel; j += kMergeThreads) {
+    const double s = sel_score[j];
+    const unsigned r = sel_row[j];
+    int rank = 0;
+    for (int u = 0; u < nsel; ++u) rank += better(sel_score[u], sel_row[u], s, r) ? 1 : 0;
+    if (rank < k) {
+      p.out_d[static_cast<size_t>(q) * k + rank] = static_cast<float>(s);
+      p.out_i[static_cast<size_t>(q) * k + rank] = static_cast<long long>(r) + cv.row_offset;
+      if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + rank] = s;
+      if (rank == k - 1) s_kth = s;
+    }
+  }
+  for (int r = nsel + tid; r < k; r += kMergeThreads) {  // fewer than k rows: FAISS pads -FLT_MAX / -1
+    p.out_d[static_cast<size_t>(q) * k + r] = -FLT_MAX;
+    p.out_i[static_cast<size_t>(q) * k + r] = -1;
+    if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + r] = -static_cast<double>(FLT_MAX);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    bool certified;
+    double theta = 0.0;
+    if (a_min == -CUDART_INF_F) {
+      certified = true;  // nothing was ever dropped: every row of the corpus was re-scored
+    } else if (p.qnorm[q] == 0.0f) {
+      certified = true;  // all-zero query: every score is exactly 0 and ties are ordered exactly
+    } else {
+      const double unscale = 1.0 / (static_cast<double>(p.qscale[q]) * cv.scan_scale);
+      const double eps = static_cast<double>(cv.max_row_norm) * p.qnorm[q] * cv.rel_err;
+      const double bound = static_cast<double>(a_min) * unscale + eps;  // >= any dropped row's exact score
+      if (nsel >= k) {
+        certified = s_kth > bound;
+        theta = s_kth;
+      } else {
+        certified = false;
+        theta = static_cast<double>(a_min) * unscale - eps;
+      }
+    }
+    if (!certified) {
+      const int slot = atomicAdd(p.flag_count, 1);
+      p.flag_list[slot] = q;
+      p.flag_theta[slot] = theta;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Exact path for uncertified queries: collect every row whose exact score is >= theta (theta
+// is a proven lower bound of the true k-th best), then order that short list.
+struct ExactParams {
+  const float* xn;
+  const int* flag_count;
+  const int* flag_list;
+  const double* flag_theta;
+  double* list_score;  // [nflag_max, kExactListCap]
+  unsigned* list_row;  // [nflag_max, kExactListCap]
+  int* list_count;     // [nflag_max]
+  float* out_d;
+  long long* out_i;
+  double* out_d64;
+  int* overflow;       // set to 1 if some list overflowed (result would be wrong -> error)
+  int nq, k;
+  int nflag_max;       // lists allocated; queries flagged beyond this are reported as an error
+};
+
+__global__ void __launch_bounds__(256) exact_collect_kernel(const ExactParams p, const CorpusView cv) {
+  const int nflag = min(*p.flag_count, p.nflag_max);
+  if (nflag == 0) return;
+  extern __shared__ __align__(16) float xq_s[];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long gwarp = static_cast<long long>(blockIdx.x) * warps_per_block + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * warps_per_block;
+  for (int f = 0; f < nflag; ++f) {
+    const int q = p.flag_list[f];
+    const double theta = p.flag_theta[f];
+    __syncthreads();
+    for (int i = threadIdx.x; i < cv.d; i += blockDim.x) xq_s[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
+    __syncthreads();
+    for (long long row = gwarp; row < cv.n; row += nwarps) {
+      const double s = warp_exact_dot(cv, row, xq_s, lane);
+      if (lane == 0 && s >= theta) {
+        const int slot = atomicAdd(&p.list_count[f], 1);
+        if (slot < kExactListCap) {
+          p.list_score[static_cast<size_t>(f) * kExactListCap + slot] = s;
+          p.list_row[static_cast<size_t>(f) * kExactListCap + slot] = static_cast<unsigned>(row);
+        } else {
+          *p.overflow = 1;
+        }
+      }
+    }
+  }
+}
+
+// One CTA per uncertified query: k rounds of block-wide arg-best over the collected list.
+__global__ void __launch_bounds__(256) exact_finalize_kernel(const ExactParams p, const CorpusView cv) {
+  const int nflag = min(*p.flag_count, p.nflag_max);
+  const int f = blockIdx.x;
+  if (f >= nflag) return;
+  const int q = p.flag_list[f];
+  const int cnt = min(p.list_count[f], kExactListCap);
+  double* sc = p.list_score + static_cast<size_t>(f) * kExactListCap;
+  unsigned* rw = p.list_row + static_cast<size_t>(f) * kExactListCap;
+  __shared__ double w_s[8];
+  __shared__ unsigned w_r[8];
+  __shared__ int w_i[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int r = 0; r < p.k; ++r) {
+    double bs = -CUDART_INF;
+    unsigned br = 0xFFFFFFFFu;
+    int bi = -1;
+    for (int i = tid; i < cnt; i += 256) {
+      const unsigned row = rw[i];
+      if (row == 0xFFFFFFFFu) continue;  // already emitted
+      if (bi < 0 || better(sc[i], row, bs, br)) {
+        bs = sc[i];
+        br = row;
+        bi = i;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double os = __shfl_xor_sync(0xffffffffu, bs, o);
+      const unsigned orr = __shfl_xor_sync(0xffffffffu, br, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oi >= 0 && (bi < 0 || better(os, orr, bs, br))) {
+        bs = os;
+        br = orr;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      w_s[warp] = bs;
+      w_r[warp] = br;
+      w_i[warp] = bi;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w)
+        if (w_i[w] >= 0 && (w_i[0] < 0 || better(w_s[w], w_r[w], w_s[0], w_r[0]))) {
+          w_s[0] = w_s[w];
+          w_r[0] = w_r[w];
+          w_i[0] = w_i[w];
+        }
+      const size_t o = static_cast<size_t>(q) * p.k + r;
+      if (w_i[0] >= 0) {
+        p.out_d[o] = static_cast<float>(w_s[0]);
+        p.out_i[o] = static_cast<long long>(w_r[0]) + cv.row_offset;
+        if (p.out_d64) p.out_d64[o] = w_s[0];
+        rw[w_i[0]] = 0xFFFFFFFFu;
+      } else {
+        p.out_d[o] = -FLT_MAX;
+        p.out_i[o] = -1;
+        if (p.out_d64) p.out_d64[o] = -static_cast<double>(FLT_MAX);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Row-sharded indexes: merge `shards` per-shard results ([shards, nq, k], exact fp64 scores +
+// global int64 ids, as all-gathered over NCCL) into the global top-k.  One warp per query.
+__global__ void __launch_bounds__(256)
+merge_shards_kernel(const double* __restrict__ dg, const long long* __restrict__ ig, int nq, int k,
+                    int shards, float* __restrict__ out_d, long long* __restrict__ out_i) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq) return;
+  const int total = shards * k;
+  for (int j = lane; j < total; j += 32) {
+    const int s = j / k, r = j % k;
+    const size_t src = (static_cast<size_t>(s) * nq + q) * k + r;
+    const long long id = ig[src];
+    if (id < 0) continue;
+    const double sc = dg[src];
+    int rank = 0;
+    for (int u = 0; u < total; ++u) {
+      const size_t us = (static_cast<size_t>(u / k) * nq + q) * k + (u % k);
+      const long long uid = ig[us];
+      if (uid < 0) continue;
+      const double usc = dg[us];
+      rank += (usc > sc || (usc == sc && uid < id)) ? 1 : 0;
+    }
+    if (rank < k) {
+      out_d[static_cast<size_t>(q) * k + rank] = static_cast<float>(sc);
+      out_i[static_cast<size_t>(q) * k + rank] = id;
+    }
+  }
+  // padding: count valid entries
+  int valid = 0;
+  for (int j = lane; j < total; j += 32)
+    valid += (ig[(static_cast<size_t>(j / k) * nq + q) * k + (j % k)] >= 0) ? 1 : 0;
+  valid = __reduce_add_sync(0xffffffffu, valid);
+  for (int r = valid + lane; r < k; r += 32) {
+    out_d[static_cast<size_t>(q) * k + r] = -FLT_MAX;
+    out_i[static_cast<size_t>(q) * k + r] = -1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// Index preparation (what faiss.Index.add does for a flat index: store the rows; here also the
+// fp16 scan copy and the statistics the certificate needs).
+// Per-block partial max of row L2 norm^2 (fp64) and of |element|.
+__global__ void __launch_bounds__(256)
+corpus_stats_kernel(const void* rows, long long pitch, int dtype, long long n, int d,
+                    double* __restrict__ blk_norm2, float* __restrict__ blk_amax) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long gwarp = static_cast<long long>(blockIdx.x) * 8 + warp;
+  const long long nwarps = static_cast<long long>(gridDim.x) * 8;
+  double best = 0.0;
+  float amax = 0.0f;
+  for (long long row = gwarp; row < n; row += nwarps) {
+    double acc = 0.0;
+    if (dtype == 1) {
+      const __half* r = reinterpret_cast<const __half*>(rows) + row * pitch;
+      for (int i = lane; i < d; i += 32) {
+        const float v = __half2float(r[i]);
+        acc = fma(static_cast<double>(v), static_cast<double>(v), acc);
+        amax = fmaxf(amax, fabsf(v));
+      }
+    } else {
+      const float* r = reinterpret_cast<const float*>(rows) + row * pitch;
+      for (int i = lane; i < d; i += 32) {
+        const float v = r[i];
+        acc = fma(static_cast<double>(v), static_cast<double>(v), acc);
+        amax = fmaxf(amax, fabsf(v));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    best = fmax(best, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  __shared__ double sb[8];
+  __shared__ float sa[8];
+  if (lane == 0) {
+    sb[warp] = best;
+    sa[warp] = amax;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) {
+      sb[0] = fmax(sb[0], sb[w]);
+      sa[0] = fmaxf(sa[0], sa[w]);
+    }
+    blk_norm2[blockIdx.x] = sb[0];
+    blk_amax[blockIdx.x] = sa[0];
+  }
+}
+
+// fp32/fp16 rows -> fp16 scan copy with a 16-byte-multiple pitch, scaled by a power of two.
+__global__ void __launch_bounds__(256)
+make_scan_copy_kernel(const void* rows, long long pitch, int dtype, long long n, int d,
+                      __half* __restrict__ out, int out_pitch, float scale) {
+  const long long total = n * out_pitch;
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / out_pitch;
+    const int col = static_cast<int>(i - row * out_pitch);
+    float v = 0.0f;
+    if (col < d) {
+      v = dtype == 1 ? __half2float(reinterpret_cast<const __half*>(rows)[row * pitch + col])
+                     : reinterpret_cast<const float*>(rows)[row * pitch + col];
+    }
+    out[i] = __float2half_rn(v * scale);
+  }
+}
+
+}  // namespace lxg

@@ -1,0 +1,414 @@
+// Pass 1 of the flat inner-product search (replaces faiss.normalize_L2 + Index.search,
+// reference call sites: src/lean_explore/search/engine.py:242 and :250).
+//
+// One persistent CTA per (corpus slice, block of 128 queries):
+//   * epilogue warps 0-3: thread t owns query t of the block.  Prologue = the fused
+//     L2-normalise (FAISS fvec_renorm_L2 semantics, engine.py:242): read the fp32 query row,
+//     normalise, scale by a power of two, convert to fp16 and park it in TENSOR MEMORY as the
+//     A operand (lane t, d/2 columns).  The queries never touch shared memory.
+//   * warp 4: TMA producer. Streams the slice of the fp16 corpus ("scan copy") through a
+//     ring of 128B-swizzled shared-memory stages (N_T rows x 64 dims each) - all ~192 KB of
+//     shared memory is corpus pipeline.
+//   * warp 5: one elected thread issues tcgen05.mma (M=128 queries, N=N_T corpus rows, K=16),
+//     A from TMEM, B from the swizzled stage, fp32 accumulators in TMEM, double buffered.
+//   * epilogue: tcgen05.ld 32 scores per thread at a time (lane = query, column = corpus
+//     row), compare against the thread's private threshold; survivors are appended to the
+//     query's candidate list (global memory, L2 resident).  When a list fills up the warp
+//     compacts it cooperatively to the best kp entries (exact k-th-largest by bit bisection)
+//     and raises the threshold.
+// The output is, per (slice, query), the exact top-kp of the slice *by fp16-input score*.
+// Pass 2 (rescore.cuh) merges slices, re-scores the survivors exactly and certifies that the
+// answer equals the exact top-k.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "ptx.cuh"
+
+namespace lxg {
+
+constexpr int kEpiThreads = 128;   // warps 0..3
+constexpr int kScanThreads = 192;  // + warp 4 (TMA) + warp 5 (MMA)
+constexpr int kKC = 64;            // fp16 elements per 128-byte swizzled row
+constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline
+constexpr int kQueryBlock = 128;   // queries per CTA == UMMA M
+
+struct ScanParams {
+  const float* x;     // [nq, d] fp32 queries as given by the caller
+  float* xn;          // [nq, d] fp32 queries after normalize_L2 (written by slice 0)
+  float* qscale;      // [nq] power-of-two scale applied before the fp16 conversion
+  float* qnorm;       // [nq] ||xn||_2
+  uint2* cand;        // [slices, nq, cap] (score bits, row)
+  int* cand_count;    // [slices, nq]
+  float* slice_thr;   // [slices, nq] kp-th best of the slice (scaled units) or -inf if nothing dropped
+  float* dbg_scores;  // optional [nq, n] raw tensor-core scores (tests only), else nullptr
+  int nq, d, num_kc;
+  int n;
+  int num_tiles, slices, tiles_per_slice;
+  int kp, cap;
+  int normalize;
+};
+
+__device__ __forceinline__ uint32_t float_to_key(uint32_t b) {
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ uint32_t key_to_float_bits(uint32_t k) {
+  return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+}
+
+// ||x||^2 of one fp32 row, accumulated in fp64 in a fixed order (four interleaved partial sums),
+// rounded once to fp32: the `nr` of FAISS' fvec_renorm_L2.  Shared by the fused prologue of the
+// scan kernel and by normalize_l2_kernel so both produce bit-identical normalised queries.
+__device__ __forceinline__ float row_norm_sq(const float* xr, int d) {
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  int i = 0;
+  for (; i + 3 < d; i += 4) {
+    const double a = xr[i], b = xr[i + 1], c = xr[i + 2], e = xr[i + 3];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+    s2 = fma(c, c, s2);
+    s3 = fma(e, e, s3);
+  }
+  for (; i < d; ++i) {
+    const double a = xr[i];
+    s0 = fma(a, a, s0);
+  }
+  return static_cast<float>((s0 + s1) + (s2 + s3));
+}
+// inv_nr = 1.0 / sqrtf(nr) evaluated in double and rounded to float, as FAISS writes it.
+__device__ __forceinline__ float inv_norm(float nr) {
+  return nr > 0.0f ? static_cast<float>(1.0 / static_cast<double>(sqrtf(nr))) : 1.0f;
+}
+
+// In-place faiss.normalize_L2 (engine.py:242): one thread per row.
+__global__ void __launch_bounds__(128) normalize_l2_kernel(float* __restrict__ x, int nq, int d) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= nq) return;
+  float* xr = x + static_cast<size_t>(q) * d;
+  const float inv = inv_norm(row_norm_sq(xr, d));
+  for (int i = 0; i < d; ++i) xr[i] = xr[i] * inv;
+}
+
+// Warp-cooperative compaction of one candidate list: keep the kp largest scores (ties: first
+// in list order == lowest row), return the kp-th largest score.  c > kp on entry.
+__device__ float warp_compact(uint2* __restrict__ buf, int c, int kp, int lane) {
+  __syncwarp();
+  const uint32_t lt_mask = (1u << lane) - 1u;
+  uint32_t prefix = 0;
+  if (c <= 128) {
+    uint2 e[4];
+    uint32_t key[4];
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const int i = m * 32 + lane;
+      if (i < c) {
+        e[m] = __ldcg(buf + i);
+        key[m] = float_to_key(e[m].x);
+      } else {
+        e[m] = make_uint2(0, 0);
+        key[m] = 0;
+      }
+    }
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cnd = prefix | (1u << bit);
+      int mine = 0;
+#pragma unroll
+      for (int m = 0; m < 4; ++m) mine += (key[m] >= cnd) ? 1 : 0;
+      if (__reduce_add_sync(0xffffffffu, mine) >= kp) prefix = cnd;
+    }
+    int gt = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) gt += (key[m] > prefix) ? 1 : 0;
+    const int need_eq = kp - __reduce_add_sync(0xffffffffu, gt);
+    int w = 0, eq_seen = 0;
+#pragma unroll
+    for (int m = 0; m < 4; ++m) {
+      const bool is_eq = (key[m] == prefix) && (m * 32 + lane < c);
+      const uint32_t be = __ballot_sync(0xffffffffu, is_eq);
+      const bool keep = (key[m] > prefix) || (is_eq && (eq_seen + __popc(be & lt_mask) < need_eq));
+      const uint32_t bk = __ballot_sync(0xffffffffu, keep);
+      if (keep) __stcg(buf + w + __popc(bk & lt_mask), e[m]);
+      w += __popc(bk);
+      eq_seen += __popc(be);
+    }
+  } else {
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cnd = prefix | (1u << bit);
+      int mine = 0;
+      for (int i = lane; i < c; i += 32) mine += (float_to_key(__ldcg(buf + i).x) >= cnd) ? 1 : 0;
+      if (__reduce_add_sync(0xffffffffu, mine) >= kp) prefix = cnd;
+    }
+    int gt = 0;
+    for (int i = lane; i < c; i += 32) gt += (float_to_key(__ldcg(buf + i).x) > prefix) ? 1 : 0;
+    const int need_eq = kp - __reduce_add_sync(0xffffffffu, gt);
+    int w = 0, eq_seen = 0;
+    for (int base = 0; base < c; base += 32) {
+      const int i = base + lane;
+      uint2 e = make_uint2(0, 0);
+      uint32_t key = 0;
+      if (i < c) {
+        e = __ldcg(buf + i);
+        key = float_to_key(e.x);
+      }
+      const bool is_eq = (i < c) && (key == prefix);
+      const uint32_t be = __ballot_sync(0xffffffffu, is_eq);
+      const bool keep = (key > prefix) || (is_eq && (eq_seen + __popc(be & lt_mask) < need_eq));
+      const uint32_t bk = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();  // every lane has read chunk `base` before anyone overwrites [w, w+32) <= base+32
+      if (keep) __stcg(buf + w + __popc(bk & lt_mask), e);
+      w += __popc(bk);
+      eq_seen += __popc(be);
+      __syncwarp();
+    }
+  }
+  __syncwarp();
+  return __uint_as_float(key_to_float_bits(prefix));
+}
+
+// N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
+// columns (d <= 512), 64 when they need up to 384 (d <= 768): A + 2 accumulators <= 512 columns.
+template <int N_T>
+__global__ void __launch_bounds__(kScanThreads, 1)
+scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  constexpr int kStageBytes = N_T * 128;
+  constexpr int kStages = kStageRing / kStageBytes;
+  constexpr int kChunksPerTile = N_T / 32;
+  constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(128, N_T);
+
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ __align__(8) uint64_t empty_bar[kStages];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t a_ready_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int slice = blockIdx.x;
+  const int qblock = blockIdx.y;
+
+  // 1024-byte aligned stage ring (SWIZZLE_128B atoms are 1024 bytes).
+  const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring = smem_raw + (ring_u32 - ptx::smem_u32(smem_raw));
+
+  const int tile_begin = slice * p.tiles_per_slice;
+  const int tile_end = min(p.num_tiles, tile_begin + p.tiles_per_slice);
+  const int my_tiles = max(0, tile_end - tile_begin);
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tmem_full_bar[a], 1);
+      ptx::mbar_init(&tmem_empty_bar[a], kEpiThreads);
+    }
+    ptx::mbar_init(&a_ready_bar, kEpiThreads);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) ptx::prefetch_tensormap(&tmap);
+    ptx::tmem_alloc(&tmem_base_holder, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 4) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        for (int kc = 0; kc < p.num_kc; ++kc) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          ptx::tma_load_2d(ring + stage * kStageBytes, &tmap, kc * kKC, t * N_T, &full_bar[stage],
+                           ptx::kEvictNormal);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      ptx::mbar_wait(&a_ready_bar, 0);
+      ptx::tc_fence_after();
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t acc = it & 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_T;
+        for (int kc = 0; kc < p.num_kc; ++kc) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ring_u32 + stage * kStageBytes);
+          const uint32_t a_tmem = tmem_base + kACol0 + kc * 32;
+#pragma unroll
+          for (int k4 = 0; k4 < 4; ++k4) {
+            // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
+            // 8 TMEM columns in A.
+            ptx::mma_f16_ts(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc,
+                            (kc | k4) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit(&empty_bar[stage]);  // stage reusable once these MMAs retire
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        ptx::tc_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------- epilogue warps: one query per thread
+    const int t = threadIdx.x;  // TMEM lane
+    const int q = qblock * kQueryBlock + t;
+    const bool live = q < p.nq;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    const int d = p.d;
+
+    // ---- fused normalize_L2 (FAISS fvec_renorm_L2: nr = ||x||^2; if nr > 0: x *= 1/sqrt(nr))
+    float inv = 1.0f, sq = 1.0f, nrm = 0.0f;
+    const float* xr = p.x + static_cast<size_t>(live ? q : 0) * d;
+    if (live) {
+      if (p.normalize) inv = inv_norm(row_norm_sq(xr, d));
+      float amax = 0.0f;
+      double n2 = 0;
+      for (int j = 0; j < d; ++j) {
+        const float v = __ldg(xr + j) * inv;
+        amax = fmaxf(amax, fabsf(v));
+        n2 = fma(static_cast<double>(v), static_cast<double>(v), n2);
+      }
+      nrm = static_cast<float>(sqrt(n2)) * 1.0000002f;  // rounded up: used only in the error bound
+      // power-of-two scale so that max|x| lands in [1,2): exact, keeps fp16 out of the subnormals
+      if (amax > 0.0f && amax < CUDART_INF_F) sq = ldexpf(1.0f, -ilogbf(amax));
+      if (slice == 0) {
+        p.qscale[q] = sq;
+        p.qnorm[q] = nrm;
+      }
+    }
+    for (int kc = 0; kc < p.num_kc; ++kc) {
+      uint32_t r[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int i0 = kc * kKC + 2 * j;
+        float v0 = 0.0f, v1 = 0.0f;
+        if (live) {
+          if (i0 < d) v0 = __ldg(xr + i0) * inv;
+          if (i0 + 1 < d) v1 = __ldg(xr + i0 + 1) * inv;
+          if (slice == 0) {
+            if (i0 < d) p.xn[static_cast<size_t>(q) * d + i0] = v0;
+            if (i0 + 1 < d) p.xn[static_cast<size_t>(q) * d + i0 + 1] = v1;
+          }
+        }
+        const __half2 h = __floats2half2_rn(v0 * sq, v1 * sq);  // .x (low half) = even k
+        r[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      ptx::tmem_st_32x32b_x32(tmem_base + lane_base + kACol0 + kc * 32, r);
+    }
+    ptx::tc_wait_st();
+    ptx::tc_fence_before();
+    ptx::mbar_arrive(&a_ready_bar);
+
+    // ---- threshold scan
+    const size_t list = static_cast<size_t>(slice) * p.nq + (live ? q : 0);
+    uint2* buf = p.cand + list * p.cap;
+    float thr = live ? -CUDART_INF_F : CUDART_INF_F;
+    int cnt = 0;
+    const int kp = p.kp, cap = p.cap, n = p.n;
+
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const int row0 = (tile_begin + it) * N_T;
+#pragma unroll 1
+      for (int c = 0; c < kChunksPerTile; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * N_T + c * 32, r);
+        ptx::tc_wait_ld();
+        const int base_row = row0 + c * 32;
+        if (base_row >= n) break;  // warp-uniform: rest of the tile is TMA zero fill
+        const int valid = min(32, n - base_row);
+        if (p.dbg_scores != nullptr && live) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (j < valid)
+              p.dbg_scores[static_cast<size_t>(q) * n + base_row + j] = __uint_as_float(r[j]);
+        }
+        bool hit = false;
+        if (valid == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) > thr);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) hit |= (j < valid) && (__uint_as_float(r[j]) > thr);
+        }
+        if (__any_sync(0xffffffffu, hit)) {
+          if (hit) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (j < valid && __uint_as_float(r[j]) > thr) {
+                __stcg(buf + cnt, make_uint2(r[j], static_cast<uint32_t>(base_row + j)));
+                ++cnt;
+              }
+            }
+          }
+          uint32_t need = __ballot_sync(0xffffffffu, cnt > cap - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            uint2* b = reinterpret_cast<uint2*>(
+                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src));
+            const int bc = __shfl_sync(0xffffffffu, cnt, src);
+            const float tnew = warp_compact(b, bc, kp, lane);
+            if (lane == src) {
+              thr = tnew;
+              cnt = kp;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive(&tmem_empty_bar[acc]);
+    }
+    // ---- final compaction to exactly the slice's top-kp
+    {
+      uint32_t need = __ballot_sync(0xffffffffu, cnt > kp);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        uint2* b = reinterpret_cast<uint2*>(
+            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src));
+        const int bc = __shfl_sync(0xffffffffu, cnt, src);
+        const float tnew = warp_compact(b, bc, kp, lane);
+        if (lane == src) {
+          thr = tnew;
+          cnt = kp;
+        }
+      }
+    }
+    if (live) {
+      p.cand_count[list] = cnt;
+      p.slice_thr[list] = thr;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace lxg
