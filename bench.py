@@ -1,0 +1,461 @@
+#!/usr/bin/env python
+"""Benchmark of the semantic-search hot path: queries/sec for exact top-k over an N x d corpus.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1|cfg4]
+                  [--queries Q] [--impl b200|reference]
+
+A "step" is one batch of Q synthetic queries searched against the whole corpus (fused
+normalise + fp16 tensor-core scan + exact re-score + top-k).  Prints ONE JSON line (rank 0).
+
+  value     QPS with the query batch already resident in HBM (CUDA events, max over ranks)
+  e2e       QPS through the public host API (numpy in / numpy out, copies inside the timing)
+  roofline  the scan kernel's achieved TFLOP/s (or GB/s) against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference: the FAISS restatement (numpy sgemm + FAISS-style heaps,
+            oracle/) on this box's host cores.
+
+Workloads (BASELINE.json configs): cfg1 50k x 384 fp32 top-10 (Q=1000); cfg2 500k x 384 fp16
+top-50 (default; Q=1024); cfg3 2M x 768 fp16 top-50; cfg4 16M x 768 fp16 row-sharded over the
+ranks with an NCCL all-gather of per-shard candidates (strong scaling).
+With --gpus N > 1 the default workload runs as N query-parallel replicas (each rank holds the
+whole corpus and searches its own batches; no collective; weak scaling) - the corpus fits one
+GPU, and the north star shards rows only when it does not.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    "cfg1": dict(n=50_000, d=384, dtype="float32", k=10, q=1000,
+                 name="cfg1: 1k-query batch, 50k x 384 fp32 corpus, top-10"),
+    "cfg2": dict(n=500_000, d=384, dtype="float16", k=50, q=1024,
+                 name="cfg2: Mathlib-scale 500k x 384 fp16 corpus, top-50"),
+    "cfg3": dict(n=2_000_000, d=768, dtype="float16", k=50, q=1024,
+                 name="cfg3: 2M x 768 fp16 corpus, top-50"),
+    "cfg4": dict(n=16_000_000, d=768, dtype="float16", k=50, q=1024,
+                 name="cfg4: 16M x 768 fp16 corpus row-sharded, top-50"),
+}
+
+
+def load_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        j = json.loads(p.read_text())
+        return dict(hbm_gbs=j["hbm_gbs"], tflops=j["bf16_tflops"],
+                    tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
+    return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+# --------------------------------------------------------------------------- synthetic data
+def make_corpus_gpu(n, d, dtype, device, row0=0, seed=0):
+    """BASELINE.md synthetic corpus: N(0,1) rows, L2-normalised in fp32, cast to `dtype`.
+    Generated on the GPU in 64Ki-row chunks seeded by (seed, chunk) so any row range is
+    reproducible on any rank."""
+    import torch
+
+    tdt = torch.float16 if dtype == "float16" else torch.float32
+    out = torch.empty((n, d), dtype=tdt, device=device)
+    chunk = 65536
+    first = row0 // chunk
+    last = (row0 + n + chunk - 1) // chunk
+    for c in range(first, last):
+        g = torch.Generator(device=device)
+        g.manual_seed(seed * 1_000_003 + c)
+        blk = torch.randn((chunk, d), generator=g, device=device, dtype=torch.float32)
+        blk /= blk.norm(dim=1, keepdim=True)
+        lo = max(row0, c * chunk)
+        hi = min(row0 + n, (c + 1) * chunk)
+        out[lo - row0 : hi - row0] = blk[lo - c * chunk : hi - c * chunk].to(tdt)
+    return out
+
+
+def make_queries_gpu(q, d, device, seed):
+    import torch
+
+    g = torch.Generator(device=device)
+    g.manual_seed(1_000_000_007 + seed)
+    return torch.randn((q, d), generator=g, device=device, dtype=torch.float32)
+
+
+# --------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+               0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU reference
+class CpuFlatIP:
+    """The reference's CPU path for this hot path, restated (oracle/): faiss.normalize_L2 +
+    IndexFlatIP.search = blocked sgemm (numpy/OpenBLAS, all cores) + FAISS-style per-query
+    heaps (oracle/flat_ip.c, OpenMP, all cores).  bench.py is one of the three places allowed
+    to execute oracle/ code, and only as the baseline being reported."""
+
+    def __init__(self, corpus32: np.ndarray):
+        import ctypes
+
+        self.c = corpus32
+        so = ROOT / "oracle" / "liblxoracle.so"
+        if not so.exists():
+            import subprocess
+
+            subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True)
+        self.lib = ctypes.CDLL(str(so))
+        vp, sz, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64
+        self.lib.lxo_renorm_l2.argtypes = [sz, sz, vp]
+        self.lib.lxo_heap_init.argtypes = [sz, sz, vp, vp]
+        self.lib.lxo_heap_add_block.argtypes = [sz, sz, vp, vp, vp, sz, i64]
+        self.lib.lxo_heap_finish.argtypes = [sz, sz, vp, vp]
+        self.threads = int(self.lib.lxo_num_threads())
+
+    def search(self, x: np.ndarray, k: int, block: int = 16384):
+        x = np.ascontiguousarray(x, dtype=np.float32).copy()
+        nq, d = x.shape
+        self.lib.lxo_renorm_l2(d, nq, x.ctypes.data)
+        D = np.empty((nq, k), dtype=np.float32)
+        I = np.empty((nq, k), dtype=np.int64)
+        self.lib.lxo_heap_init(nq, k, D.ctypes.data, I.ctypes.data)
+        for j0 in range(0, self.c.shape[0], block):
+            s = x @ self.c[j0 : j0 + block].T
+            s = np.ascontiguousarray(s)
+            self.lib.lxo_heap_add_block(nq, k, D.ctypes.data, I.ctypes.data, s.ctypes.data, s.shape[1], j0)
+        self.lib.lxo_heap_finish(nq, k, D.ctypes.data, I.ctypes.data)
+        return D, I
+
+
+def time_cpu(cpu: CpuFlatIP, x: np.ndarray, k: int, budget_s: float):
+    """QPS of the CPU path on a bounded sample: grow the query sample until ~budget_s."""
+    nq = min(16, x.shape[0])
+    cpu.search(x[:nq], k)  # warm-up (BLAS thread pool, page-in)
+    while True:
+        t0 = time.perf_counter()
+        cpu.search(x[:nq], k)
+        dt = time.perf_counter() - t0
+        if dt > budget_s / 3 or nq >= x.shape[0]:
+            return nq / dt, nq, dt
+        nq = min(x.shape[0], max(nq * 2, int(nq * budget_s / 2 / max(dt, 1e-3))))
+
+
+# --------------------------------------------------------------------------- main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--queries", type=int, default=None)
+    ap.add_argument("--k", type=int, default=None)
+    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary cfg3 / sweep numbers")
+    args = ap.parse_args()
+
+    wl = dict(WORKLOADS[args.workload])
+    if args.queries:
+        wl["q"] = args.queries
+    if args.k:
+        wl["k"] = args.k
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        args.gpus = world
+
+    if args.impl == "reference":
+        return run_reference(args, wl, rank)
+
+    import torch
+    import torch.distributed as dist
+
+    from lean_explore_b200 import GpuIndexFlatIP
+
+    assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    sharded = args.workload == "cfg4"
+    n, d, k, q = wl["n"], wl["d"], wl["k"], wl["q"]
+    peaks = load_peaks()
+
+    if sharded:
+        from lean_explore_b200.sharded import ShardedFlatIP, shard_rows
+
+        lo, hi = shard_rows(n, world, rank)
+        corpus = make_corpus_gpu(hi - lo, d, wl["dtype"], dev, row0=lo)
+        index = GpuIndexFlatIP.from_tensor(corpus, row_offset=lo)
+        engine = ShardedFlatIP(index, world, rank)
+        batches = [make_queries_gpu(q, d, dev, seed=s) for s in range(4)]  # same queries on every rank
+        rows_local = hi - lo
+    else:
+        corpus = make_corpus_gpu(n, d, wl["dtype"], dev)
+        index = GpuIndexFlatIP.from_tensor(corpus)
+        engine = None
+        batches = [make_queries_gpu(q, d, dev, seed=rank * 16 + s) for s in range(4)]
+        rows_local = n
+    D = torch.empty((q, k), dtype=torch.float32, device=dev)
+    I = torch.empty((q, k), dtype=torch.int64, device=dev)
+
+    def step(i):
+        x = batches[i % len(batches)]
+        if sharded:
+            return engine.search_torch(x, k, normalize=True)
+        return index.search_torch(x, k, normalize=True, out=(D, I))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+
+    sampler = ClockSampler(local_rank)
+    index.set_timing(True)
+    index.get_timing()
+    with sampler:
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(args.steps):
+            step(i)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        tm = index.get_timing()
+        index.set_timing(False)
+        launches = index.last_stats()["kernel_launches"] * args.steps + (args.steps if sharded else 0)
+
+        # end to end through the public host API: numpy in, numpy out, copies inside the timing
+        e2e = None
+        if not sharded:
+            xh = [b.cpu().numpy() for b in batches]
+            index.search(xh[0], k, normalize=True)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                index.search(xh[i % len(xh)], k, normalize=True)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+        else:
+            xh = [b.cpu().numpy() for b in batches]
+            engine.search(xh[0], k, normalize=True)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                engine.search(xh[i % len(xh)], k, normalize=True)
+            torch.cuda.synchronize()
+            e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, e2e_s = float(t[0]), float(t[1]) / 1e3
+    units = q * args.steps * (1 if sharded else world)
+    value = units / (ms / 1e3)
+    e2e_value = units / e2e_s
+
+    # roofline of the dominant kernel (pass-1 scan), per launch, from CUDA events on its stream
+    scan_ms = tm["scan_ms"] / max(1, tm["calls"])
+    flops = 2.0 * q * rows_local * d
+    bytes_alg = rows_local * d * 2 + q * d * 4 + q * k * 12
+    tf = flops / (scan_ms / 1e3) / 1e12
+    gbs = bytes_alg / (scan_ms / 1e3) / 1e9
+    tensor_frac, hbm_frac = tf / peaks["tflops"], gbs / peaks["hbm_gbs"]
+    ridge_q = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)  # fp16: flop/byte == Q
+    if q >= ridge_q:
+        roof = dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tflops"], unit="TFLOP/s",
+                    frac=round(tensor_frac, 4), traffic=None)
+    else:
+        roof = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s",
+                    frac=round(hbm_frac, 4), traffic=None)
+    roof.update(kernel="scan_topk_kernel", ms_per_launch=round(scan_ms, 4), peak_source=peaks["source"],
+                other_bound_frac=round(hbm_frac if roof["bound"] == "tensor" else tensor_frac, 4),
+                merge_ms_per_launch=round(tm["merge_ms"] / max(1, tm["calls"]), 4),
+                exact_ms_per_launch=round(tm["exact_ms"] / max(1, tm["calls"]), 4))
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists():
+        roof["traffic"] = json.loads(traffic_file.read_text()).get(args.workload)
+
+    out = {
+        "metric": "queries/sec top-50 over Nxd corpus" if k == 50 else f"queries/sec top-{k} over Nxd corpus",
+        "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f16xf16->f32 scan, f64 re-score",
+        "data": "synthetic",
+        "config": {"workload": wl["name"], "corpus_rows": n, "d": d, "corpus_dtype": wl["dtype"], "k": k,
+                   "queries_per_step": q, "normalize": True,
+                   "parallelism": ("row-sharded x%d + NCCL all-gather of per-shard top-k" % world) if sharded
+                   else ("query-parallel replicas x%d" % world if world > 1 else "single GPU"),
+                   "l2_policy": "corpus (%.0f MB) larger than L2; 4 rotating query batches" % (n * d * 2 / 1e6)
+                   if n * d * 2 > 126e6 else "inputs fit L2 (config as specified by BASELINE.json)"},
+        "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": q * d * 4,
+                "d2h_bytes_per_step": q * k * 12, "api": "GpuIndexFlatIP.search(numpy) -> lxg_search"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "clocks": sampler.summary(),
+    }
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c32 = corpus.float().cpu().numpy()
+        cpu = CpuFlatIP(c32)
+        xs = torch.cat(batches).cpu().numpy()
+        qps, nq_s, dt = time_cpu(cpu, xs, k, args.cpu_budget)
+        out["cpu_baseline"] = {"value": round(qps, 1), "unit": "queries/s", "cores": cpu.threads, "kind": "port",
+                               "sample": "%d queries x full %d x %d corpus (fp32), %.1f s; numpy sgemm + FAISS-style heaps"
+                               % (nq_s, n, d, dt), "host_cpus": os.cpu_count()}
+        # parity spot check of what was just timed
+        Dg, Ig = index.search(xs[:nq_s], k, normalize=True)
+        Dc, Ic = cpu.search(xs[:nq_s], k)
+        out["cpu_baseline"]["ids_equal_frac"] = round(float((Ig == Ic).mean()), 6)
+        del c32, cpu
+
+    if rank == 0 and world == 1 and not args.no_extra and args.workload == "cfg2":
+        out["extra"] = extra_numbers(index, d, k, dev, peaks)
+
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+def extra_numbers(index, d, k, dev, peaks):
+    """Query-batch sweep on the same corpus (Q in {1,8,64,256,1024,4096})."""
+    import torch
+
+    res = {}
+    n = index.ntotal
+    for q in (1, 8, 64, 256, 4096):
+        xs = [make_queries_gpu(q, d, dev, seed=100 + s) for s in range(4)]
+        for i in range(3):
+            index.search_torch(xs[i], k, normalize=True)
+        torch.cuda.synchronize()
+        steps = 50
+        index.set_timing(True)
+        index.get_timing()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            index.search_torch(xs[i % 4], k, normalize=True)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        tm = index.get_timing()
+        index.set_timing(False)
+        scan = tm["scan_ms"] / steps
+        res[f"Q={q}"] = {"qps": round(q / (ms / 1e3), 1), "ms_per_step": round(ms, 4), "scan_ms": round(scan, 4),
+                         "hbm_frac": round(n * d * 2 / (scan / 1e3) / 1e9 / peaks["hbm_gbs"], 4),
+                         "tensor_frac": round(2.0 * q * n * d / (scan / 1e3) / 1e12 / peaks["tflops"], 4)}
+    return res
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the reference's CPU path for this hot path (FAISS restatement from
+    oracle/) on the host cores, same config/metric; rank 0 only."""
+    if rank != 0:
+        return
+    n, d, k, q = wl["n"], wl["d"], wl["k"], wl["q"]
+    if args.workload == "cfg4":
+        n = 2_000_000  # 16M x 768 fp32 does not fit host RAM: time a 2M slice, scale x1/8 below
+    rng = np.random.default_rng(0)
+    c32 = np.empty((n, d), dtype=np.float32)
+    for j0 in range(0, n, 65536):
+        blk = rng.standard_normal((min(65536, n - j0), d), dtype=np.float32)
+        blk /= np.linalg.norm(blk, axis=1, keepdims=True)
+        c32[j0 : j0 + blk.shape[0]] = blk.astype(np.float16).astype(np.float32) if wl["dtype"] == "float16" else blk
+    cpu = CpuFlatIP(c32)
+    xs = np.random.default_rng(1).standard_normal((q, d), dtype=np.float32)
+    # bounded sample per step: as many queries as keep one step near 1 s
+    qps0, nq_s, dt0 = time_cpu(cpu, xs, k, 3.0)
+    nq_step = int(min(q, max(1, qps0 * 1.0)))
+    for _ in range(min(args.warmup, 3)):
+        cpu.search(xs[:nq_step], k)
+    steps = max(1, min(args.steps, int(120.0 / max(nq_step / qps0, 1e-3))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu.search(xs[:nq_step], k)
+    dt = time.perf_counter() - t0
+    value = nq_step * steps / dt
+    if args.workload == "cfg4":
+        value /= 8.0
+    out = {
+        "impl": "reference", "metric": "queries/sec top-50 over Nxd corpus" if k == 50 else f"queries/sec top-{k} over Nxd corpus",
+        "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
+        "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "corpus_rows": wl["n"], "d": d, "corpus_dtype": wl["dtype"], "k": k,
+                   "queries_per_step": nq_step, "normalize": True, "parallelism": "host CPU, all cores"},
+        "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cpu.threads, "kind": "port",
+                         "sample": "%d queries/step x %d steps over %d x %d fp32 rows%s; faiss-cpu is not installable "
+                                   "offline, so this is its restatement (numpy/OpenBLAS sgemm + FAISS-style heaps)"
+                                   % (nq_step, steps, n, d, " (2M-row slice, QPS scaled 1/8)" if args.workload == "cfg4" else ""),
+                         "host_cpus": os.cpu_count()},
+        "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

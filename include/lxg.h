@@ -110,6 +110,18 @@ typedef struct lxg_search_stats {
 } lxg_search_stats;
 int lxg_index_last_stats(const lxg_index* index, lxg_search_stats* out);
 
+/* Optional per-kernel device timing (bench.py's roofline numbers).  While enabled, every
+ * lxg_search records CUDA events around its kernels on the stream it launches on;
+ * lxg_index_get_timing synchronises them, returns the sums since the last get and resets. */
+typedef struct lxg_timing {
+  int32_t calls;
+  float scan_ms;   /* pass 1: fused normalise + tcgen05 GEMM + threshold top-k' */
+  float merge_ms;  /* pass 2: merge + exact re-score + certificate */
+  float exact_ms;  /* exact collectors for uncertified queries */
+} lxg_timing;
+int lxg_index_set_timing(lxg_index* index, int enable);
+int lxg_index_get_timing(lxg_index* index, lxg_timing* out);
+
 /* Test hook: raw tensor-core scores of pass 1 (scores_dev [nq, n] float32, scaled by
  * qscale_dev[q] * scan_scale) so the TMA/tcgen05 data path can be checked in isolation. */
 int lxg_debug_scores(lxg_index* index, const float* x_dev, int32_t nq, int normalize,

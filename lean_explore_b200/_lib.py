@@ -36,6 +36,10 @@ class SearchStats(ctypes.Structure):
     ]
 
 
+class Timing(ctypes.Structure):
+    _fields_ = [("calls", c_int32), ("scan_ms", c_float), ("merge_ms", c_float), ("exact_ms", c_float)]
+
+
 class BertLayer(ctypes.Structure):
     _fields_ = [(n, c_void_p) for n in (
         "wqkv", "bqkv", "wo", "bo", "ln1_g", "ln1_b", "w1", "b1", "w2", "b2", "ln2_g", "ln2_b")]
@@ -67,6 +71,8 @@ SIGNATURES = {
     "lxg_merge_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                c_void_p]),
     "lxg_index_last_stats": (c_int, [c_void_p, POINTER(SearchStats)]),
+    "lxg_index_set_timing": (c_int, [c_void_p, c_int]),
+    "lxg_index_get_timing": (c_int, [c_void_p, POINTER(Timing)]),
     "lxg_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p,
                                  POINTER(c_float), c_void_p]),
     "lxg_encoder_create": (c_int, [POINTER(c_void_p), POINTER(BertWeights)]),

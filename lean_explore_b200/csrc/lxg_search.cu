@@ -100,6 +100,9 @@ struct lxg_index {
   DevBuf ws_cand, ws_small, ws_x, ws_out, ws_exact;
   HostBuf h_stage;
   lxg_search_stats stats{};
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_pool;   // 4 events per timed call
+  size_t ev_used = 0;
 };
 
 namespace {
@@ -301,6 +304,7 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
 int lxg_index_destroy(lxg_index* ix) {
   if (!ix) return LXG_OK;
   if (ix->scan_owned && ix->scan) cudaFree(ix->scan);
+  for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
   ix->ws_cand.release();
   ix->ws_small.release();
   ix->ws_x.release();
@@ -313,6 +317,33 @@ int lxg_index_destroy(lxg_index* ix) {
 
 int64_t lxg_index_ntotal(const lxg_index* ix) { return ix ? ix->cv.n : -1; }
 int32_t lxg_index_d(const lxg_index* ix) { return ix ? ix->cv.d : -1; }
+
+int lxg_index_set_timing(lxg_index* ix, int enable) {
+  if (!ix) return set_error(LXG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  ix->timing = enable != 0;
+  ix->ev_used = 0;
+  return LXG_OK;
+}
+
+int lxg_index_get_timing(lxg_index* ix, lxg_timing* out) {
+  if (!ix || !out) return set_error(LXG_EINVAL, "NULL argument");
+  std::lock_guard<std::mutex> lock(ix->mu);
+  *out = lxg_timing{};
+  for (size_t i = 0; i + 4 <= ix->ev_used; i += 4) {
+    LXG_CUDA(cudaEventSynchronize(ix->ev_pool[i + 3]));
+    float a = 0, b = 0, c = 0;
+    LXG_CUDA(cudaEventElapsedTime(&a, ix->ev_pool[i], ix->ev_pool[i + 1]));
+    LXG_CUDA(cudaEventElapsedTime(&b, ix->ev_pool[i + 1], ix->ev_pool[i + 2]));
+    LXG_CUDA(cudaEventElapsedTime(&c, ix->ev_pool[i + 2], ix->ev_pool[i + 3]));
+    out->scan_ms += a;
+    out->merge_ms += b;
+    out->exact_ms += c;
+    out->calls += 1;
+  }
+  ix->ev_used = 0;
+  return LXG_OK;
+}
 
 int lxg_index_last_stats(const lxg_index* ix, lxg_search_stats* out) {
   if (!ix || !out) return set_error(LXG_EINVAL, "NULL argument");
@@ -373,12 +404,26 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.normalize = normalize;
 
   int launches = 0;
+  cudaEvent_t* ev = nullptr;
+  if (ix->timing && !dbg_scores) {
+    if (ix->ev_used + 4 > ix->ev_pool.size()) {
+      for (int i = 0; i < 4; ++i) {
+        cudaEvent_t e;
+        LXG_CUDA(cudaEventCreate(&e));
+        ix->ev_pool.push_back(e);
+      }
+    }
+    ev = &ix->ev_pool[ix->ev_used];
+    ix->ev_used += 4;
+  }
   LXG_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
+  if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
   if (ix->tile_rows == 128)
     LXG_CUDA(launch_scan<128>(ix, sp, pl.qblocks, st));
   else
     LXG_CUDA(launch_scan<64>(ix, sp, pl.qblocks, st));
   ++launches;
+  if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
   ix->stats.slices = pl.slices;
   ix->stats.query_blocks = pl.qblocks;
   ix->stats.kp = pl.kp;
@@ -418,6 +463,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   merge_rescore_kernel<<<nq, kMergeThreads, msmem, st>>>(mp, ix->cv);
   LXG_CUDA(cudaGetLastError());
   ++launches;
+  if (ev) LXG_CUDA(cudaEventRecord(ev[2], st));
 
   // exact path for uncertified queries (normally zero of them: both kernels exit at once)
   const int nflag_max = std::min(nq, 256);
@@ -445,6 +491,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   exact_finalize_kernel<<<nflag_max, 256, 0, st>>>(ep, ix->cv);
   LXG_CUDA(cudaGetLastError());
   launches += 2;
+  if (ev) LXG_CUDA(cudaEventRecord(ev[3], st));
   ix->stats.kernel_launches = launches;
 
   if (read_flags) {

@@ -158,6 +158,17 @@ class GpuIndexFlatIP:
         _lib.check(self._lib.lxg_index_last_stats(self._handle, ctypes.byref(st)))
         return {name: getattr(st, name) for name, _ in st._fields_}
 
+    def set_timing(self, enable: bool) -> None:
+        """Record CUDA events around the kernels of every search (bench.py's roofline)."""
+        self._materialise()
+        _lib.check(self._lib.lxg_index_set_timing(self._handle, int(enable)))
+
+    def get_timing(self) -> dict:
+        """Sum of per-kernel device times (ms) since the last call; synchronises."""
+        t = _lib.Timing()
+        _lib.check(self._lib.lxg_index_get_timing(self._handle, ctypes.byref(t)))
+        return {name: getattr(t, name) for name, _ in t._fields_}
+
     def debug_scores(self, x: torch.Tensor, normalize: bool = False):
         """Test hook: raw tensor-core scores of pass 1, un-scaled back to true units."""
         self._materialise()
