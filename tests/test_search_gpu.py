@@ -39,7 +39,7 @@ def _check(corpus_np, x, k, normalize=True):
         # fp32 sgemm noise scales with ||q|| * ||c||: only there may two fp32 FAISS builds disagree
         scale = float(np.linalg.norm(xn, axis=1).max() * np.linalg.norm(corpus_np.astype(np.float32), axis=1).max())
         assert ff.ambiguous_positions(D64, tol=4e-6 * scale)[differ].all(), "differs from fp32 oracle away from a near-tie"
-        assert differ.mean() < 1e-3
+        assert differ.sum() <= max(4, 1e-3 * differ.size)  # a swapped near-tie pair costs 2 positions
     return ix
 
 
