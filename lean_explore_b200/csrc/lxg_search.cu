@@ -127,13 +127,17 @@ int candidates_per_slice(int k) {
 }
 
 struct Plan {
-  int kp, cap, qblocks, slices, tiles_per_slice, num_tiles;
+  int kp, cap, keep_max, qblocks, slices, tiles_per_slice, num_tiles;
 };
 
 Plan make_plan(const lxg_index* ix, int nq, int k) {
   Plan pl;
   pl.kp = candidates_per_slice(k);
-  pl.cap = 2 * pl.kp;
+  // list capacity: room for many appends between two compactions (each one costs a warp ~1-2k
+  // cycles); a mid-scan compaction may keep up to keep_max entries (cheaper inexact cut)
+  pl.cap = pl.kp <= 64 ? 4 * pl.kp : 2 * pl.kp;
+  pl.keep_max = pl.kp + std::max(16, pl.kp / 2);
+  if (pl.keep_max > pl.cap - 64) pl.keep_max = pl.kp;
   pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
   pl.num_tiles = static_cast<int>((ix->cv.n + ix->tile_rows - 1) / ix->tile_rows);
   int s = std::max(1, g_num_sms / pl.qblocks);
@@ -401,6 +405,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.tiles_per_slice = pl.tiles_per_slice;
   sp.kp = pl.kp;
   sp.cap = pl.cap;
+  sp.keep_max = pl.keep_max;
   sp.normalize = normalize;
 
   int launches = 0;

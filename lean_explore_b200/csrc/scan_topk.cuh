@@ -31,6 +31,7 @@ constexpr int kEpiThreads = 128;   // warps 0..3
 constexpr int kScanThreads = 192;  // + warp 4 (TMA) + warp 5 (MMA)
 constexpr int kKC = 64;            // fp16 elements per 128-byte swizzled row
 constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline
+constexpr int kStageBytes = 32768; // one pipeline stage: N_T rows x (32768 / (128 N_T)) k-chunks
 constexpr int kQueryBlock = 128;   // queries per CTA == UMMA M
 
 struct ScanParams {
@@ -45,7 +46,7 @@ struct ScanParams {
   int nq, d, num_kc;
   int n;
   int num_tiles, slices, tiles_per_slice;
-  int kp, cap;
+  int kp, cap, keep_max;
   int normalize;
 };
 
@@ -89,49 +90,86 @@ __global__ void __launch_bounds__(128) normalize_l2_kernel(float* __restrict__ x
   for (int i = 0; i < d; ++i) xr[i] = xr[i] * inv;
 }
 
-// Warp-cooperative compaction of one candidate list: keep the kp largest scores (ties: first
-// in list order == lowest row), return the kp-th largest score.  c > kp on entry.
-__device__ float warp_compact(uint2* __restrict__ buf, int c, int kp, int lane) {
-  __syncwarp();
+// Warp-cooperative compaction of one candidate list (c > kp entries on entry).
+// Finds a cut key by bit bisection, starting at the highest bit in which the keys differ.
+//   keep_max == kp : exact - keeps the kp largest scores (ties: first in list order == lowest
+//                    row) and returns the kp-th largest score;
+//   keep_max >  kp : the bisection stops as soon as kp <= #(key >= cut) <= keep_max and keeps all
+//                    of those (cheaper: no tie handling, ~3x fewer steps).
+// Returns the cut score (every dropped entry scores <= it); *kept = entries left in the list.
+template <int PER_LANE>
+__device__ __forceinline__ float warp_compact_regs(uint2* __restrict__ buf, int c, int kp, int keep_max,
+                                                   int lane, int* kept) {
   const uint32_t lt_mask = (1u << lane) - 1u;
-  uint32_t prefix = 0;
-  if (c <= 128) {
-    uint2 e[4];
-    uint32_t key[4];
+  uint2 e[PER_LANE];
+  uint32_t key[PER_LANE];
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const int i = m * 32 + lane;
-      if (i < c) {
-        e[m] = __ldcg(buf + i);
-        key[m] = float_to_key(e[m].x);
-      } else {
-        e[m] = make_uint2(0, 0);
-        key[m] = 0;
-      }
+  for (int m = 0; m < PER_LANE; ++m) {
+    const int i = m * 32 + lane;
+    if (i < c) {
+      e[m] = __ldcg(buf + i);
+      key[m] = float_to_key(e[m].x);
+      kmin = min(kmin, key[m]);
+      kmax = max(kmax, key[m]);
+    } else {
+      e[m] = make_uint2(0, 0);
+      key[m] = 0;  // below every real key (float_to_key never returns 0 for a finite score)
     }
-    for (int bit = 31; bit >= 0; --bit) {
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  uint32_t prefix = kmax;
+  bool exact = true;  // prefix is the exact kp-th largest key (tie handling needed)
+  if (kmin != kmax) {
+    const int hb = 31 - __clz(kmin ^ kmax);
+    prefix = (hb == 31) ? 0u : (kmax & ~((2u << hb) - 1u));
+    for (int bit = hb; bit >= 0; --bit) {
       const uint32_t cnd = prefix | (1u << bit);
       int mine = 0;
 #pragma unroll
-      for (int m = 0; m < 4; ++m) mine += (key[m] >= cnd) ? 1 : 0;
-      if (__reduce_add_sync(0xffffffffu, mine) >= kp) prefix = cnd;
+      for (int m = 0; m < PER_LANE; ++m) mine += (key[m] >= cnd) ? 1 : 0;
+      const int ge = __reduce_add_sync(0xffffffffu, mine);
+      if (ge >= kp) {
+        prefix = cnd;
+        if (ge <= keep_max && keep_max > kp) {
+          exact = false;
+          break;
+        }
+      }
     }
-    int gt = 0;
+  }
+  int gt = 0;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) gt += (key[m] > prefix) ? 1 : 0;
-    const int need_eq = kp - __reduce_add_sync(0xffffffffu, gt);
-    int w = 0, eq_seen = 0;
+  for (int m = 0; m < PER_LANE; ++m) gt += (key[m] > prefix) ? 1 : 0;
+  const int need_eq = exact ? kp - __reduce_add_sync(0xffffffffu, gt) : 0x7fffffff;
+  int w = 0, eq_seen = 0;
 #pragma unroll
-    for (int m = 0; m < 4; ++m) {
-      const bool is_eq = (key[m] == prefix) && (m * 32 + lane < c);
-      const uint32_t be = __ballot_sync(0xffffffffu, is_eq);
-      const bool keep = (key[m] > prefix) || (is_eq && (eq_seen + __popc(be & lt_mask) < need_eq));
-      const uint32_t bk = __ballot_sync(0xffffffffu, keep);
-      if (keep) __stcg(buf + w + __popc(bk & lt_mask), e[m]);
-      w += __popc(bk);
-      eq_seen += __popc(be);
-    }
+  for (int m = 0; m < PER_LANE; ++m) {
+    const bool is_eq = (key[m] == prefix) && (m * 32 + lane < c);
+    const uint32_t be = __ballot_sync(0xffffffffu, is_eq);
+    const bool keep = (key[m] > prefix) || (is_eq && (eq_seen + __popc(be & lt_mask) < need_eq));
+    const uint32_t bk = __ballot_sync(0xffffffffu, keep);
+    if (keep) __stcg(buf + w + __popc(bk & lt_mask), e[m]);
+    w += __popc(bk);
+    eq_seen += __popc(be);
+  }
+  *kept = w;
+  return __uint_as_float(key_to_float_bits(prefix));
+}
+
+__device__ __noinline__ float warp_compact(uint2* __restrict__ buf, int c, int kp, int keep_max, int lane,
+                                           int* kept) {
+  __syncwarp();
+  float r;
+  if (c <= 128) {
+    r = warp_compact_regs<4>(buf, c, kp, keep_max, lane, kept);
+  } else if (c <= 256) {
+    r = warp_compact_regs<8>(buf, c, kp, keep_max, lane, kept);
   } else {
+    // large k: keys stay in memory, always exact
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t prefix = 0;
     for (int bit = 31; bit >= 0; --bit) {
       const uint32_t cnd = prefix | (1u << bit);
       int mine = 0;
@@ -160,9 +198,61 @@ __device__ float warp_compact(uint2* __restrict__ buf, int c, int kp, int lane) 
       eq_seen += __popc(be);
       __syncwarp();
     }
+    *kept = w;
+    r = __uint_as_float(key_to_float_bits(prefix));
   }
   __syncwarp();
-  return __uint_as_float(key_to_float_bits(prefix));
+  return r;
+}
+
+// State of one epilogue thread's candidate list.
+struct ListState {
+  uint2* buf;
+  float thr;  // scores <= thr are dropped
+  int cnt;
+};
+
+// Compacts the lists of every lane whose list is fuller than `limit` (warp-cooperative).
+__device__ __forceinline__ void compact_full_lists(ListState& ls, int limit, int kp, int keep_max, int lane) {
+  uint32_t need = __ballot_sync(0xffffffffu, ls.cnt > limit);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    uint2* b = reinterpret_cast<uint2*>(
+        __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ls.buf), src));
+    const int bc = __shfl_sync(0xffffffffu, ls.cnt, src);
+    int kept;
+    const float tnew = warp_compact(b, bc, kp, keep_max, lane, &kept);
+    if (lane == src) {
+      ls.thr = tnew;
+      ls.cnt = kept;
+    }
+  }
+}
+
+// Cold path of the epilogue: (re)load one 32-column chunk of the accumulator from TMEM, append
+// the scores above the thread's threshold to its list, compact lists that filled up.
+__device__ __noinline__ void append_chunk(uint32_t taddr, ListState& ls, int base_row, int valid, int kp,
+                                          int keep_max, int cap, int lane, float* __restrict__ dbg_row) {
+  uint32_t r[32];
+  ptx::tmem_ld_32x32b_x32(taddr, r);
+  ptx::tc_wait_ld();
+  if (dbg_row != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (j < valid) dbg_row[base_row + j] = __uint_as_float(r[j]);
+  }
+  const float thr = ls.thr;
+  int cnt = ls.cnt;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    if (j < valid && __uint_as_float(r[j]) > thr) {
+      __stcg(ls.buf + cnt, make_uint2(r[j], static_cast<uint32_t>(base_row + j)));
+      ++cnt;
+    }
+  }
+  ls.cnt = cnt;
+  compact_full_lists(ls, cap - 32, kp, keep_max, lane);
 }
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
@@ -170,7 +260,8 @@ __device__ float warp_compact(uint2* __restrict__ buf, int c, int kp, int lane) 
 template <int N_T>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-  constexpr int kStageBytes = N_T * 128;
+  constexpr int kBoxBytes = N_T * 128;                  // one TMA box: N_T rows x 64 fp16
+  constexpr int kKcPerStage = kStageBytes / kBoxBytes;  // k-chunks (boxes) per pipeline stage
   constexpr int kStages = kStageRing / kStageBytes;
   constexpr int kChunksPerTile = N_T / 32;
   constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
@@ -221,51 +312,66 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int t = tile_begin; t < tile_end; ++t) {
-        for (int kc = 0; kc < p.num_kc; ++kc) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          ptx::tma_load_2d(ring + stage * kStageBytes, &tmap, kc * kKC, t * N_T, &full_bar[stage],
-                           ptx::kEvictNormal);
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+    // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
+    uint32_t stage = 0, phase = 0;
+    for (int t = tile_begin; t < tile_end; ++t) {
+      for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
+        const int nb = min(kKcPerStage, p.num_kc - kc0);
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+        if (ptx::elect_one()) {
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], nb * kBoxBytes);
+          uint8_t* dst = ring + stage * kStageBytes;
+#pragma unroll
+          for (int b = 0; b < kKcPerStage; ++b)
+            if (b < nb)
+              ptx::tma_load_2d(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, t * N_T, &full_bar[stage],
+                               ptx::kEvictNormal);
+        }
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
         }
       }
     }
   } else if (warp == 5) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      ptx::mbar_wait(&a_ready_bar, 0);
+    ptx::mbar_wait(&a_ready_bar, 0);
+    ptx::tc_fence_after();
+    uint32_t stage = 0, phase = 0;
+    for (int it = 0; it < my_tiles; ++it) {
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);
       ptx::tc_fence_after();
-      uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t acc = it & 1;
-        ptx::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);
+      const uint32_t d_tmem = tmem_base + acc * N_T;
+      for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
+        const int nb = min(kKcPerStage, p.num_kc - kc0);
+        ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_T;
-        for (int kc = 0; kc < p.num_kc; ++kc) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t bdesc = ptx::make_kmajor_sw128_desc(ring_u32 + stage * kStageBytes);
-          const uint32_t a_tmem = tmem_base + kACol0 + kc * 32;
+        if (ptx::elect_one()) {
+          const uint32_t stage_addr = ring_u32 + stage * kStageBytes;
 #pragma unroll
-          for (int k4 = 0; k4 < 4; ++k4) {
-            // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
-            // 8 TMEM columns in A.
-            ptx::mma_f16_ts(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc,
-                            (kc | k4) != 0 ? 1u : 0u);
+          for (int b = 0; b < kKcPerStage; ++b) {
+            if (b < nb) {
+              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(stage_addr + b * kBoxBytes);
+              const uint32_t a_tmem = tmem_base + kACol0 + (kc0 + b) * 32;
+#pragma unroll
+              for (int k4 = 0; k4 < 4; ++k4) {
+                // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
+                // 8 TMEM columns in A.
+                ptx::mma_f16_ts(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc,
+                                (kc0 | b | k4) != 0 ? 1u : 0u);
+              }
+            }
           }
           ptx::tc_commit(&empty_bar[stage]);  // stage reusable once these MMAs retire
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1u;
-          }
+          if (kc0 + kKcPerStage >= p.num_kc) ptx::tc_commit(&tmem_full_bar[acc]);
         }
-        ptx::tc_commit(&tmem_full_bar[acc]);
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else {
@@ -321,60 +427,36 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
     // ---- threshold scan
     const size_t list = static_cast<size_t>(slice) * p.nq + (live ? q : 0);
-    uint2* buf = p.cand + list * p.cap;
-    float thr = live ? -CUDART_INF_F : CUDART_INF_F;
-    int cnt = 0;
-    const int kp = p.kp, cap = p.cap, n = p.n;
+    ListState ls;
+    ls.buf = p.cand + list * p.cap;
+    ls.thr = live ? -CUDART_INF_F : CUDART_INF_F;
+    ls.cnt = 0;
+    const int kp = p.kp, cap = p.cap, keep_max = p.keep_max, n = p.n;
+    float* dbg_row = (p.dbg_scores != nullptr && live) ? p.dbg_scores + static_cast<size_t>(q) * n : nullptr;
+    const bool dbg = p.dbg_scores != nullptr;
 
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
       ptx::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
       ptx::tc_fence_after();
       const int row0 = (tile_begin + it) * N_T;
-#pragma unroll 1
+      const uint32_t tile_addr = tmem_base + lane_base + acc * N_T;
+      // software pipeline over the tile's 32-column chunks: chunk c+1 is in flight while c is compared
+      uint32_t r[2][32];
+      ptx::tmem_ld_32x32b_x32(tile_addr, r[0]);
+#pragma unroll
       for (int c = 0; c < kChunksPerTile; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * N_T + c * 32, r);
         ptx::tc_wait_ld();
+        if (c + 1 < kChunksPerTile) ptx::tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, r[(c + 1) & 1]);
         const int base_row = row0 + c * 32;
-        if (base_row >= n) break;  // warp-uniform: rest of the tile is TMA zero fill
-        const int valid = min(32, n - base_row);
-        if (p.dbg_scores != nullptr && live) {
+        if (base_row < n) {  // warp-uniform: otherwise the chunk is TMA zero fill only
+          const int valid = min(32, n - base_row);
+          bool hit = false;
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (j < valid)
-              p.dbg_scores[static_cast<size_t>(q) * n + base_row + j] = __uint_as_float(r[j]);
-        }
-        bool hit = false;
-        if (valid == 32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[j]) > thr);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hit |= (j < valid) && (__uint_as_float(r[j]) > thr);
-        }
-        if (__any_sync(0xffffffffu, hit)) {
-          if (hit) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (j < valid && __uint_as_float(r[j]) > thr) {
-                __stcg(buf + cnt, make_uint2(r[j], static_cast<uint32_t>(base_row + j)));
-                ++cnt;
-              }
-            }
-          }
-          uint32_t need = __ballot_sync(0xffffffffu, cnt > cap - 32);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            uint2* b = reinterpret_cast<uint2*>(
-                __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src));
-            const int bc = __shfl_sync(0xffffffffu, cnt, src);
-            const float tnew = warp_compact(b, bc, kp, lane);
-            if (lane == src) {
-              thr = tnew;
-              cnt = kp;
-            }
+          for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[c & 1][j]) > ls.thr);
+          if (valid < 32 || dbg || __any_sync(0xffffffffu, hit)) {
+            ptx::tc_wait_ld();  // settle the prefetched chunk before the call (registers may be saved)
+            append_chunk(tile_addr + c * 32, ls, base_row, valid, kp, keep_max, cap, lane, dbg_row);
           }
         }
       }
@@ -382,24 +464,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       ptx::mbar_arrive(&tmem_empty_bar[acc]);
     }
     // ---- final compaction to exactly the slice's top-kp
-    {
-      uint32_t need = __ballot_sync(0xffffffffu, cnt > kp);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        uint2* b = reinterpret_cast<uint2*>(
-            __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(buf), src));
-        const int bc = __shfl_sync(0xffffffffu, cnt, src);
-        const float tnew = warp_compact(b, bc, kp, lane);
-        if (lane == src) {
-          thr = tnew;
-          cnt = kp;
-        }
-      }
-    }
+    compact_full_lists(ls, kp, kp, kp, lane);
     if (live) {
-      p.cand_count[list] = cnt;
-      p.slice_thr[list] = thr;
+      p.cand_count[list] = ls.cnt;
+      p.slice_thr[list] = ls.thr;
     }
   }
 

@@ -1,0 +1,62 @@
+"""ctypes binding of ``oracle/liblxoracle.so`` (the C restatement in ``flat_ip.c``).
+
+CPU ORACLE - test infrastructure, not product code (see ``faiss_flat.py`` for who may import it).
+"""
+
+from __future__ import annotations
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SO = HERE / "liblxoracle.so"
+
+
+def load() -> ctypes.CDLL:
+    if not SO.exists() or SO.stat().st_mtime < (HERE / "flat_ip.c").stat().st_mtime:
+        subprocess.run(["make", "-C", str(HERE)], check=True, capture_output=True)
+    lib = ctypes.CDLL(str(SO))
+    vp, sz, i64 = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int64
+    lib.lxo_renorm_l2.argtypes = [sz, sz, vp]
+    lib.lxo_heap_init.argtypes = [sz, sz, vp, vp]
+    lib.lxo_heap_add_block.argtypes = [sz, sz, vp, vp, vp, sz, i64]
+    lib.lxo_heap_finish.argtypes = [sz, sz, vp, vp]
+    lib.lxo_knn_inner_product_seq.argtypes = [vp, vp, sz, sz, sz, sz, vp, vp]
+    lib.lxo_num_threads.restype = ctypes.c_int
+    return lib
+
+
+def renorm_l2(x: np.ndarray) -> None:
+    """faiss fvec_renorm_L2 with fp32 SIMD-order accumulation (in place)."""
+    assert x.dtype == np.float32 and x.flags.c_contiguous
+    load().lxo_renorm_l2(x.shape[1], x.shape[0], x.ctypes.data)
+
+
+def knn_inner_product_seq(x: np.ndarray, y: np.ndarray, k: int):
+    """FAISS' nq < 20 path: per-pair fp32 dot products + CMin heap."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    D = np.empty((x.shape[0], k), dtype=np.float32)
+    I = np.empty((x.shape[0], k), dtype=np.int64)
+    load().lxo_knn_inner_product_seq(x.ctypes.data, y.ctypes.data, x.shape[1], x.shape[0], y.shape[0], k,
+                                     D.ctypes.data, I.ctypes.data)
+    return D, I
+
+
+def knn_inner_product_blas(x: np.ndarray, y: np.ndarray, k: int, block: int = 1024):
+    """FAISS' nq >= 20 path: blocked sgemm (numpy/OpenBLAS) + HeapBlockResultHandler."""
+    lib = load()
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32)
+    nq = x.shape[0]
+    D = np.empty((nq, k), dtype=np.float32)
+    I = np.empty((nq, k), dtype=np.int64)
+    lib.lxo_heap_init(nq, k, D.ctypes.data, I.ctypes.data)
+    for j0 in range(0, y.shape[0], block):
+        s = np.ascontiguousarray(x @ y[j0 : j0 + block].T)
+        lib.lxo_heap_add_block(nq, k, D.ctypes.data, I.ctypes.data, s.ctypes.data, s.shape[1], j0)
+    lib.lxo_heap_finish(nq, k, D.ctypes.data, I.ctypes.data)
+    return D, I
