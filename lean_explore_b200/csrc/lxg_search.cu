@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -28,6 +29,7 @@ static std::mutex g_init_mutex;
 static bool g_inited = false;
 static int g_device = -1;
 static int g_num_sms = 0;
+static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -95,7 +97,8 @@ struct lxg_index {
   int scan_pitch = 0;      // elements
   int tile_rows = 0;       // N_T
   int num_kc = 0;
-  CUtensorMap tmap{};
+  CUtensorMap tmap{};       // box = tile_rows rows   (one CTA per query block)
+  CUtensorMap tmap_pair{};  // box = tile_rows/2 rows (CTA pairs, tcgen05 cta_group::2)
   std::mutex mu;
   DevBuf ws_cand, ws_small, ws_x, ws_out, ws_exact;
   HostBuf h_stage;
@@ -110,13 +113,16 @@ namespace {
 int build_tensor_map(lxg_index* ix) {
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ix->cv.d), static_cast<cuuint64_t>(ix->cv.n)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ix->scan_pitch) * sizeof(__half)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kKC), static_cast<cuuint32_t>(ix->tile_rows)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode_tiled(&ix->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ix->scan, gdim, gstride,
-                              box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS)
-    return set_error(LXG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  for (int pair = 0; pair < 2; ++pair) {
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(kKC), static_cast<cuuint32_t>(ix->tile_rows >> pair)};
+    CUresult r = g_encode_tiled(pair ? &ix->tmap_pair : &ix->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, ix->scan,
+                                gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+      return set_error(LXG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  }
   return LXG_OK;
 }
 
@@ -128,6 +134,8 @@ int candidates_per_slice(int k) {
 
 struct Plan {
   int kp, cap, keep_max, qblocks, slices, tiles_per_slice, num_tiles;
+  bool pair;    // CTA pairs (cta_group::2) when there are at least two query blocks
+  int grid_x;   // query blocks launched (padded to even in pair mode)
 };
 
 Plan make_plan(const lxg_index* ix, int nq, int k) {
@@ -140,7 +148,9 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
   if (pl.keep_max > pl.cap - 64) pl.keep_max = pl.kp;
   pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
   pl.num_tiles = static_cast<int>((ix->cv.n + ix->tile_rows - 1) / ix->tile_rows);
-  int s = std::max(1, g_num_sms / pl.qblocks);
+  pl.pair = pl.qblocks >= 2 && !g_force_single;
+  pl.grid_x = pl.pair ? (pl.qblocks + 1) / 2 * 2 : pl.qblocks;
+  int s = std::max(1, g_num_sms / pl.grid_x);
   s = std::min(s, std::max(1, 24576 / pl.kp));  // merge kernel keeps slices*kp keys in shared memory
   s = std::min(s, 148);
   s = std::min(s, std::max(1, pl.num_tiles));
@@ -149,19 +159,29 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
   return pl;
 }
 
-template <int N_T>
-cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int qblocks, cudaStream_t st) {
+template <int N_T, bool kPair>
+cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, cudaStream_t st) {
   static bool attr_set = false;
   const int smem = kStageRing + 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<N_T>,
+    cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<N_T, kPair>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid(sp.slices, qblocks, 1);
-  scan_topk_kernel<N_T><<<grid, kScanThreads, smem, st>>>(ix->tmap, sp);
-  return cudaGetLastError();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid_x, sp.slices, 1);
+  cfg.blockDim = dim3(kScanThreads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, scan_topk_kernel<N_T, kPair>, kPair ? ix->tmap_pair : ix->tmap, sp);
 }
 
 }  // namespace
@@ -200,6 +220,8 @@ int lxg_init(int device) {
     g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   }
   g_num_sms = prop.multiProcessorCount;
+  const char* fs = std::getenv("LXG_SCAN_SINGLE");
+  g_force_single = fs && fs[0] == '1';
   g_device = device;
   g_inited = true;
   return LXG_OK;
@@ -423,10 +445,13 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   }
   LXG_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
-  if (ix->tile_rows == 128)
-    LXG_CUDA(launch_scan<128>(ix, sp, pl.qblocks, st));
-  else
-    LXG_CUDA(launch_scan<64>(ix, sp, pl.qblocks, st));
+  if (ix->tile_rows == 128) {
+    if (pl.pair) LXG_CUDA((launch_scan<128, true>(ix, sp, pl.grid_x, st)));
+    else LXG_CUDA((launch_scan<128, false>(ix, sp, pl.grid_x, st)));
+  } else {
+    if (pl.pair) LXG_CUDA((launch_scan<64, true>(ix, sp, pl.grid_x, st)));
+    else LXG_CUDA((launch_scan<64, false>(ix, sp, pl.grid_x, st)));
+  }
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
   ix->stats.slices = pl.slices;

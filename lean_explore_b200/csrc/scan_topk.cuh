@@ -257,15 +257,21 @@ __device__ __noinline__ void append_chunk(uint32_t taddr, ListState& ls, int bas
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
 // columns (d <= 512), 64 when they need up to 384 (d <= 768): A + 2 accumulators <= 512 columns.
-template <int N_T>
+// kPair: two CTAs of a cluster (two adjacent blocks of 128 queries) run ONE tcgen05.mma
+// cta_group::2 stream (M = 256): each CTA stages only N_T/2 rows of every corpus tile, so a corpus
+// byte crosses L2 -> SM once per 256 queries instead of once per 128.
+template <int N_T, bool kPair>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
-  constexpr int kBoxBytes = N_T * 128;                  // one TMA box: N_T rows x 64 fp16
-  constexpr int kKcPerStage = kStageBytes / kBoxBytes;  // k-chunks (boxes) per pipeline stage
-  constexpr int kStages = kStageRing / kStageBytes;
+  constexpr int kBoxRows = kPair ? N_T / 2 : N_T;       // corpus rows this CTA stages per tile
+  constexpr int kBoxBytes = kBoxRows * 128;             // one TMA box: kBoxRows rows x 64 fp16
+  constexpr int kStageBytesT = kPair ? kStageBytes / 2 : kStageBytes;
+  constexpr int kKcPerStage = kStageBytesT / kBoxBytes;  // k-chunks (boxes) per pipeline stage
+  constexpr int kStages = kStageRing / kStageBytesT;
   constexpr int kChunksPerTile = N_T / 32;
   constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
-  constexpr uint32_t kIdesc = ptx::make_idesc_f16(128, N_T);
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, N_T);
+  constexpr uint32_t kArrivals = kPair ? 2 * kEpiThreads : kEpiThreads;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -277,8 +283,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int slice = blockIdx.x;
-  const int qblock = blockIdx.y;
+  const int qblock = blockIdx.x;
+  const int slice = blockIdx.y;
+  const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;  // position in the CTA pair
 
   // 1024-byte aligned stage ring (SWIZZLE_128B atoms are 1024 bytes).
   const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -295,37 +302,51 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], kEpiThreads);
+      ptx::mbar_init(&tmem_empty_bar[a], kArrivals);
     }
-    ptx::mbar_init(&a_ready_bar, kEpiThreads);
+    ptx::mbar_init(&a_ready_bar, kArrivals);
     ptx::fence_barrier_init();
   }
   if (warp == 4) {
     if (lane == 0) ptx::prefetch_tensormap(&tmap);
-    ptx::tmem_alloc(&tmem_base_holder, 512);
-    ptx::tmem_relinquish();
+    if constexpr (kPair) {
+      ptx::tmem_alloc_pair(&tmem_base_holder, 512);
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(&tmem_base_holder, 512);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
   if (warp == 4) {
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
+    // Pair mode: both CTAs load their half of the tile; the bytes of both halves are counted on
+    // the even CTA's full barrier (it issues the MMAs), which therefore expects 2x the bytes.
     uint32_t stage = 0, phase = 0;
     for (int t = tile_begin; t < tile_end; ++t) {
+      const int row = t * N_T + static_cast<int>(rank) * kBoxRows;
       for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
         const int nb = min(kKcPerStage, p.num_kc - kc0);
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
         if (ptx::elect_one()) {
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], nb * kBoxBytes);
-          uint8_t* dst = ring + stage * kStageBytes;
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], nb * kBoxBytes * (kPair ? 2 : 1));
+          uint8_t* dst = ring + stage * kStageBytesT;
 #pragma unroll
-          for (int b = 0; b < kKcPerStage; ++b)
-            if (b < nb)
-              ptx::tma_load_2d(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, t * N_T, &full_bar[stage],
-                               ptx::kEvictNormal);
+          for (int b = 0; b < kKcPerStage; ++b) {
+            if (b < nb) {
+              if constexpr (kPair)
+                ptx::tma_load_2d_pair(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, row, &full_bar[stage],
+                                      ptx::kEvictNormal);
+              else
+                ptx::tma_load_2d(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, row, &full_bar[stage],
+                                 ptx::kEvictNormal);
+            }
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -336,41 +357,54 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
   } else if (warp == 5) {
     // -------------------------------------------------------------- MMA issuer
-    ptx::mbar_wait(&a_ready_bar, 0);
-    ptx::tc_fence_after();
-    uint32_t stage = 0, phase = 0;
-    for (int it = 0; it < my_tiles; ++it) {
-      const uint32_t acc = it & 1;
-      ptx::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);
+    if (rank == 0) {
+      ptx::mbar_wait(&a_ready_bar, 0);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * N_T;
-      for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
-        const int nb = min(kKcPerStage, p.num_kc - kc0);
-        ptx::mbar_wait(&full_bar[stage], phase);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t acc = it & 1;
+        ptx::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t stage_addr = ring_u32 + stage * kStageBytes;
+        const uint32_t d_tmem = tmem_base + acc * N_T;
+        for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
+          const int nb = min(kKcPerStage, p.num_kc - kc0);
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t stage_addr = ring_u32 + stage * kStageBytesT;
 #pragma unroll
-          for (int b = 0; b < kKcPerStage; ++b) {
-            if (b < nb) {
-              const uint64_t bdesc = ptx::make_kmajor_sw128_desc(stage_addr + b * kBoxBytes);
-              const uint32_t a_tmem = tmem_base + kACol0 + (kc0 + b) * 32;
+            for (int b = 0; b < kKcPerStage; ++b) {
+              if (b < nb) {
+                const uint64_t bdesc = ptx::make_kmajor_sw128_desc(stage_addr + b * kBoxBytes);
+                const uint32_t a_tmem = tmem_base + kACol0 + (kc0 + b) * 32;
 #pragma unroll
-              for (int k4 = 0; k4 < 4; ++k4) {
-                // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
-                // 8 TMEM columns in A.
-                ptx::mma_f16_ts(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc,
-                                (kc0 | b | k4) != 0 ? 1u : 0u);
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
+                  // 8 TMEM columns in A.
+                  const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
+                  if constexpr (kPair)
+                    ptx::mma_f16_ts_pair(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc,
+                                         accum);
+                  else
+                    ptx::mma_f16_ts(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc, accum);
+                }
               }
             }
+            // stage reusable (in both CTAs) once these MMAs retire
+            const bool last = kc0 + kKcPerStage >= p.num_kc;
+            if constexpr (kPair) {
+              ptx::tc_commit_pair(&empty_bar[stage], 3);
+              if (last) ptx::tc_commit_pair(&tmem_full_bar[acc], 3);
+            } else {
+              ptx::tc_commit(&empty_bar[stage]);
+              if (last) ptx::tc_commit(&tmem_full_bar[acc]);
+            }
           }
-          ptx::tc_commit(&empty_bar[stage]);  // stage reusable once these MMAs retire
-          if (kc0 + kKcPerStage >= p.num_kc) ptx::tc_commit(&tmem_full_bar[acc]);
-        }
-        __syncwarp();
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1u;
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
       }
     }
@@ -423,7 +457,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
     ptx::tc_wait_st();
     ptx::tc_fence_before();
-    ptx::mbar_arrive(&a_ready_bar);
+    if constexpr (kPair) ptx::mbar_arrive_cluster(&a_ready_bar, 0); else ptx::mbar_arrive(&a_ready_bar);
 
     // ---- threshold scan
     const size_t list = static_cast<size_t>(slice) * p.nq + (live ? q : 0);
@@ -461,7 +495,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
     }
     // ---- final compaction to exactly the slice's top-kp
     compact_full_lists(ls, kp, kp, kp, lane);
@@ -472,10 +506,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) ptx::cluster_sync(); else __syncthreads();
   if (warp == 4) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 512);
+    if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }
 }
 

@@ -80,8 +80,9 @@ class ShardedFlatIP:
         if self.world == 1:
             return self._merge(d64.unsqueeze(0).contiguous(), ids.unsqueeze(0).contiguous(), k)
         packed = torch.stack([d64.contiguous().view(torch.int64), ids], dim=0).contiguous()  # [2, nq, k]
-        gathered = torch.empty((self.world, 2, nq, k), dtype=torch.int64, device=packed.device)
+        gathered = torch.empty((self.world * 2, nq, k), dtype=torch.int64, device=packed.device)
         dist.all_gather_into_tensor(gathered, packed, group=self.group)  # the single exchange step
+        gathered = gathered.view(self.world, 2, nq, k)
         dg = gathered[:, 0].contiguous().view(torch.float64)
         ig = gathered[:, 1].contiguous()
         return self._merge(dg, ig, k)
