@@ -1,0 +1,418 @@
+// Kernels of the BERT-class sentence encoder (replaces SentenceTransformer.encode inside
+// EmbeddingClient.embed, reference src/lean_explore/util/embedding_client.py:88-101):
+//   embeddings + LayerNorm -> L x [ QKV GEMM, attention, out-proj GEMM (+residual), LayerNorm,
+//   FFN GEMM + GELU, FFN GEMM (+residual), LayerNorm ] -> pooling (mean / CLS) -> L2 normalise.
+// Post-LN BERT exactly as transformers.BertModel computes it (erf GELU, learned absolute
+// positions, token type 0, additive -inf key mask).  Activations are fp16 between kernels,
+// every accumulation / LayerNorm / softmax is fp32.
+//
+// The GEMMs run on tcgen05 tensor cores: TMA (128B swizzle) stages A[128 x 64] and W[BN x 64]
+// tiles into a shared-memory ring, one elected thread issues tcgen05.mma (M=128, N=BN, K=16) into
+// a TMEM accumulator, four epilogue warps read it back with tcgen05.ld and apply
+// bias / GELU / residual in registers.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "ptx.cuh"
+
+namespace lxg {
+
+// ------------------------------------------------------------------ embeddings + LayerNorm
+// One warp per token.  out = LN(word[id] + pos[s] + type[0]) * g + b   (fp16)
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const int* __restrict__ ids, int tokens, int seq, int hidden, int vocab,
+                const __half* __restrict__ word, const __half* __restrict__ pos,
+                const __half* __restrict__ type0, const float* __restrict__ g,
+                const float* __restrict__ b, float eps, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  int id = ids[t];
+  id = min(max(id, 0), vocab - 1);
+  const int s = t % seq;
+  const __half2* w2 = reinterpret_cast<const __half2*>(word + static_cast<size_t>(id) * hidden);
+  const __half2* p2 = reinterpret_cast<const __half2*>(pos + static_cast<size_t>(s) * hidden);
+  const __half2* t2 = reinterpret_cast<const __half2*>(type0);
+  constexpr int kMax = 16;  // hidden <= 1024
+  float2 v[kMax];
+  float sum = 0.f;
+  const int n2 = hidden >> 1;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    v[i] = make_float2(0.f, 0.f);
+    if (j < n2) {
+      const float2 a = __half22float2(w2[j]), c = __half22float2(p2[j]), e = __half22float2(t2[j]);
+      v[i] = make_float2(a.x + c.x + e.x, a.y + c.y + e.y);
+      sum += v[i].x + v[i].y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / hidden;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n2) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean;
+      var += dx * dx + dy * dy;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / hidden + eps);
+  __half2* o2 = reinterpret_cast<__half2*>(out + static_cast<size_t>(t) * hidden);
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n2) {
+      const float2 gg = reinterpret_cast<const float2*>(g)[j], bb = reinterpret_cast<const float2*>(b)[j];
+      o2[j] = __floats2half2_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ LayerNorm (fp32 in, fp16 out)
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const float* __restrict__ x, int tokens, int hidden, const float* __restrict__ g,
+                 const float* __restrict__ b, float eps, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  const float2* x2 = reinterpret_cast<const float2*>(x + static_cast<size_t>(t) * hidden);
+  constexpr int kMax = 16;
+  float2 v[kMax];
+  float sum = 0.f;
+  const int n2 = hidden >> 1;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    v[i] = make_float2(0.f, 0.f);
+    if (j < n2) {
+      v[i] = x2[j];
+      sum += v[i].x + v[i].y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum / hidden;
+  float var = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n2) {
+      const float dx = v[i].x - mean, dy = v[i].y - mean;
+      var += dx * dx + dy * dy;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = rsqrtf(var / hidden + eps);
+  __half2* o2 = reinterpret_cast<__half2*>(out + static_cast<size_t>(t) * hidden);
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n2) {
+      const float2 gg = reinterpret_cast<const float2*>(g)[j], bb = reinterpret_cast<const float2*>(b)[j];
+      o2[j] = __floats2half2_rn((v[i].x - mean) * rstd * gg.x + bb.x, (v[i].y - mean) * rstd * gg.y + bb.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ tcgen05 GEMM
+// C[M, N] = epi(A[M, K] . W[N, K]^T + bias[N])
+//   kEpiStore : fp16 out                     (QKV projection)
+//   kEpiGelu  : erf-GELU, fp16 out           (intermediate.dense)
+//   kEpiResid : + residual fp16 [M, N], fp32 out   (attention.output.dense / output.dense, pre-LN)
+enum GemmEpilogue { kEpiStore = 0, kEpiGelu = 1, kEpiResid = 2 };
+
+constexpr int kGemmBM = 128;
+constexpr int kGemmBN = 128;
+constexpr int kGemmBK = 64;
+constexpr int kGemmStages = 4;
+constexpr int kGemmStageBytes = (kGemmBM + kGemmBN) * kGemmBK * 2;  // 32 KB
+constexpr int kGemmThreads = 192;                                   // 4 epilogue warps + TMA + MMA
+constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024;
+
+struct GemmParams {
+  const float* bias;       // [N]
+  const __half* residual;  // [M, N] (kEpiResid)
+  void* out;               // fp16 [M, N] or fp32 [M, N]
+  int m, n, k;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(kGemmThreads)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+               const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kGemmStages];
+  __shared__ __align__(8) uint64_t empty_bar[kGemmStages];
+  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kGemmBM;
+  const int n0 = blockIdx.y * kGemmBN;
+  const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
+  const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* ring = smem_raw + (ring_u32 - ptx::smem_u32(smem_raw));
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kGemmBM, kGemmBN);
+
+  if (warp == 5 && lane == 0) {
+    for (int s = 0; s < kGemmStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(&acc_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tmap_a);
+      ptx::prefetch_tensormap(&tmap_w);
+    }
+    ptx::tmem_alloc(&tmem_base_holder, kGemmBN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == 4) {
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
+      if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
+        uint8_t* dst = ring + stage * kGemmStageBytes;
+        ptx::tma_load_2d(dst, &tmap_a, kb * kGemmBK, m0, &full_bar[stage], ptx::kEvictFirst);
+        ptx::tma_load_2d(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, &full_bar[stage],
+                         ptx::kEvictLast);
+      }
+      __syncwarp();
+      if (++stage == kGemmStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else if (warp == 5) {
+    uint32_t stage = 0, phase = 0;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      ptx::mbar_wait(&full_bar[stage], phase);
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
+        const uint32_t a_addr = ring_u32 + stage * kGemmStageBytes;
+        const uint64_t adesc = ptx::make_kmajor_sw128_desc(a_addr);
+        const uint64_t bdesc = ptx::make_kmajor_sw128_desc(a_addr + kGemmBM * kGemmBK * 2);
+#pragma unroll
+        for (int k4 = 0; k4 < 4; ++k4)
+          ptx::mma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2),
+                          kIdesc, (kb | k4) != 0 ? 1u : 0u);
+        ptx::tc_commit(&empty_bar[stage]);
+        if (kb == num_kb - 1) ptx::tc_commit(&acc_bar);
+      }
+      __syncwarp();
+      if (++stage == kGemmStages) {
+        stage = 0;
+        phase ^= 1u;
+      }
+    }
+  } else {
+    // epilogue: thread = output row of the tile
+    const int row = m0 + threadIdx.x;
+    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+    ptx::mbar_wait(&acc_bar, 0);
+    ptx::tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < kGemmBN / 32; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
+      ptx::tc_wait_ld();
+      const int col0 = n0 + c * 32;
+      if (row < p.m && col0 < p.n) {
+        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 bb = __ldg(b4 + j);
+          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
+          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+        }
+        if constexpr (EPI == kEpiGelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+        }
+        if constexpr (EPI == kEpiResid) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
+          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rr = __ldg(r4 + j);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+            const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
+            const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
+            o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
+            o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
+          }
+        } else {
+          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            __half2 h;
+            h = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
+            o.x = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+            o.y = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+            o.z = *reinterpret_cast<uint32_t*>(&h);
+            h = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+            o.w = *reinterpret_cast<uint32_t*>(&h);
+            o4[j] = o;
+          }
+        }
+      }
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, kGemmBN);
+  }
+}
+
+// ------------------------------------------------------------------ attention
+// One CTA per (sequence, head); K and V of the head live in shared memory (fp16), one warp per
+// query row at a time: scores over keys (lane = key), fp32 softmax with the additive -inf key
+// mask of BertModel, then context (lane = feature).  CUDA-core kernel: at the query path's
+// S <= 64 attention is < 2 % of the encoder's FLOPs.
+constexpr int kAttnThreads = 256;
+
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int hidden,
+                 int heads, __half* __restrict__ ctx) {
+  extern __shared__ __align__(16) uint8_t asm_raw[];
+  const int dh = hidden / heads;
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int kpitch = dh + 2;  // fp16 elements; odd word pitch -> conflict-free key-strided reads
+  __half* ks = reinterpret_cast<__half*>(asm_raw);
+  __half* vs = ks + static_cast<size_t>(seq) * kpitch;
+  float* bias = reinterpret_cast<float*>(vs + static_cast<size_t>(seq) * kpitch);
+  float* probs = bias + seq;  // [warps, seq]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const size_t row_stride = static_cast<size_t>(3) * hidden;
+  const __half* base = qkv + static_cast<size_t>(b) * seq * row_stride;
+  for (int i = threadIdx.x; i < seq * (dh / 2); i += blockDim.x) {
+    const int j = i / (dh / 2), c = i % (dh / 2);
+    const __half2 kk = *reinterpret_cast<const __half2*>(base + j * row_stride + hidden + h * dh + 2 * c);
+    const __half2 vv = *reinterpret_cast<const __half2*>(base + j * row_stride + 2 * hidden + h * dh + 2 * c);
+    *reinterpret_cast<__half2*>(ks + j * kpitch + 2 * c) = kk;
+    *reinterpret_cast<__half2*>(vs + j * kpitch + 2 * c) = vv;
+  }
+  for (int j = threadIdx.x; j < seq; j += blockDim.x)
+    bias[j] = mask[b * seq + j] != 0 ? 0.f : -CUDART_INF_F;
+  __syncthreads();
+  const float scale = rsqrtf(static_cast<float>(dh));
+  float* pw = probs + warp * seq;
+  for (int i = warp; i < seq; i += nwarps) {
+    // q row in registers: lane holds features 2*lane, 2*lane+1 (dh <= 64)
+    const __half* qp = base + i * row_stride + h * dh;
+    float2 qv = make_float2(0.f, 0.f);
+    if (2 * lane < dh) qv = __half22float2(*reinterpret_cast<const __half2*>(qp + 2 * lane));
+    float mx = -CUDART_INF_F;
+    for (int j0 = 0; j0 < seq; j0 += 32) {
+      const int j = j0 + lane;
+      float s = 0.f;
+      for (int c = 0; c < dh / 2; ++c) {
+        const float qx = __shfl_sync(0xffffffffu, qv.x, c), qy = __shfl_sync(0xffffffffu, qv.y, c);
+        if (j < seq) {
+          const float2 kk = __half22float2(*reinterpret_cast<const __half2*>(ks + j * kpitch + 2 * c));
+          s = fmaf(qx, kk.x, s);
+          s = fmaf(qy, kk.y, s);
+        }
+      }
+      if (j < seq) {
+        s = s * scale + bias[j];
+        pw[j] = s;
+        mx = fmaxf(mx, s);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (mx == -CUDART_INF_F) mx = 0.f;  // every key masked: BertModel yields a uniform row; value unused
+    float sum = 0.f;
+    __syncwarp();
+    for (int j = lane; j < seq; j += 32) {
+      const float e = __expf(pw[j] - mx);
+      pw[j] = e;
+      sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = sum > 0.f ? 1.f / sum : 0.f;
+    __syncwarp();
+    float2 acc = make_float2(0.f, 0.f);
+    if (2 * lane < dh) {
+      for (int j = 0; j < seq; ++j) {
+        const float pj = pw[j];
+        const float2 vv = __half22float2(*reinterpret_cast<const __half2*>(vs + j * kpitch + 2 * lane));
+        acc.x = fmaf(pj, vv.x, acc.x);
+        acc.y = fmaf(pj, vv.y, acc.y);
+      }
+      *reinterpret_cast<__half2*>(ctx + (static_cast<size_t>(b) * seq + i) * hidden + h * dh + 2 * lane) =
+          __floats2half2_rn(acc.x * inv, acc.y * inv);
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------ pooling + L2 normalise
+// sentence-transformers Pooling (mean over unmasked tokens, clamp(sum_mask, 1e-9) / CLS) followed
+// by Normalize (x / max(||x||_2, 1e-12)).  One CTA per sequence, fp32 output.
+__global__ void __launch_bounds__(256)
+pool_normalize_kernel(const __half* __restrict__ hs, const int* __restrict__ mask, int seq, int hidden,
+                      int pool_cls, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  __shared__ float red[8];
+  __shared__ float s_cnt;
+  extern __shared__ float pooled[];
+  if (threadIdx.x == 0) {
+    float c = 0.f;
+    for (int j = 0; j < seq; ++j) c += mask[b * seq + j] != 0 ? 1.f : 0.f;
+    s_cnt = fmaxf(c, 1e-9f);
+  }
+  __syncthreads();
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+    float v;
+    if (pool_cls) {
+      v = __half2float(hs[static_cast<size_t>(b) * seq * hidden + c]);
+    } else {
+      float acc = 0.f;
+      for (int j = 0; j < seq; ++j)
+        if (mask[b * seq + j] != 0) acc += __half2float(hs[(static_cast<size_t>(b) * seq + j) * hidden + c]);
+      v = acc / s_cnt;
+    }
+    pooled[c] = v;
+    ss += v * v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) tot += red[w];
+  const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
+  for (int c = threadIdx.x; c < hidden; c += blockDim.x) out[static_cast<size_t>(b) * hidden + c] = pooled[c] * inv;
+}
+
+}  // namespace lxg

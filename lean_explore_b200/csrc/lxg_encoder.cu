@@ -1,16 +1,245 @@
-// Sentence-encoder entry points (include/lxg.h).  Placeholder until the BERT kernels land.
+// Sentence-encoder entry points of the C ABI (include/lxg.h): host logic only - workspace,
+// tensor maps, launch sequence.  Replaces SentenceTransformer.encode as called by
+// EmbeddingClient.embed (reference src/lean_explore/util/embedding_client.py:88-101).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/lxg.h"
 #include "common.h"
+#include "encoder_kernels.cuh"
+
+using namespace lxg;
+
+struct lxg_encoder {
+  lxg_bert_weights w{};
+  std::vector<lxg_bert_layer> layers;
+  std::mutex mu;
+  int cap_tokens = 0;  // workspace capacity (tokens)
+  __half *h = nullptr, *qkv = nullptr, *ctx = nullptr, *ffn = nullptr;
+  float* pre = nullptr;
+  int *ids = nullptr, *mask = nullptr;
+  CUtensorMap map_h{}, map_ctx{}, map_ffn{};  // A operands (activations)
+  std::vector<CUtensorMap> map_wqkv, map_wo, map_w1, map_w2;
+  int launches = 0;
+};
+
+namespace {
+
+int make_map(CUtensorMap* m, const void* base, int rows, int cols) {
+  // row-major fp16 [rows, cols]; box = 64 columns x 128 rows, 128-byte swizzle
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * sizeof(__half)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(kGemmBM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = lxg::encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LXG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return LXG_OK;
+}
+
+void free_ws(lxg_encoder* e) {
+  cudaFree(e->h);
+  cudaFree(e->qkv);
+  cudaFree(e->ctx);
+  cudaFree(e->ffn);
+  cudaFree(e->pre);
+  cudaFree(e->ids);
+  cudaFree(e->mask);
+  e->h = e->qkv = e->ctx = e->ffn = nullptr;
+  e->pre = nullptr;
+  e->ids = e->mask = nullptr;
+  e->cap_tokens = 0;
+}
+
+int reserve_ws(lxg_encoder* e, int tokens) {
+  if (tokens <= e->cap_tokens) return LXG_OK;
+  free_ws(e);
+  const int cap = (std::max(tokens, 256) + 127) / 128 * 128;
+  const size_t H = e->w.hidden, F = e->w.ffn;
+  LXG_CUDA(cudaMalloc(&e->h, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->qkv, cap * 3 * H * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->ctx, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->ffn, cap * F * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->pre, cap * H * sizeof(float)));
+  LXG_CUDA(cudaMalloc(&e->ids, cap * sizeof(int)));
+  LXG_CUDA(cudaMalloc(&e->mask, cap * sizeof(int)));
+  // rows beyond the live tokens are read by TMA (never stored): keep them finite
+  LXG_CUDA(cudaMemset(e->h, 0, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMemset(e->ctx, 0, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMemset(e->ffn, 0, cap * F * sizeof(__half)));
+  int rc;
+  if ((rc = make_map(&e->map_h, e->h, cap, static_cast<int>(H))) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_ctx, e->ctx, cap, static_cast<int>(H))) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_ffn, e->ffn, cap, static_cast<int>(F))) != LXG_OK) return rc;
+  e->cap_tokens = cap;
+  return LXG_OK;
+}
+
+template <int EPI>
+cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((gp.m + kGemmBM - 1) / kGemmBM, gp.n / kGemmBN, 1);
+  gemm_tc_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, st>>>(a, w, gp);
+  return cudaGetLastError();
+}
+
+}  // namespace
 
 extern "C" {
-int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights*) {
-  if (out) *out = nullptr;
-  return lxg::set_error(LXG_EUNSUPPORTED, "encoder kernels not built yet");
+
+int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w) {
+  if (!out) return set_error(LXG_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!w || !w->layer) return set_error(LXG_EINVAL, "weights are NULL");
+  if (!lxg::encode_tensor_map_ready()) return set_error(LXG_EINVAL, "lxg_init has not been called");
+  if (w->hidden <= 0 || w->hidden > 1024 || w->hidden % kGemmBN != 0 || w->ffn % kGemmBN != 0 || w->layers <= 0 ||
+      w->heads <= 0 || w->hidden % w->heads != 0)
+    return set_error(LXG_EUNSUPPORTED, "encoder geometry: hidden and ffn must be multiples of 128, hidden <= 1024");
+  const int dh = w->hidden / w->heads;
+  if (dh > 64 || dh % 2 != 0) return set_error(LXG_EUNSUPPORTED, "encoder geometry: head size must be even and <= 64");
+  if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b)
+    return set_error(LXG_EINVAL, "embedding weights are NULL");
+  lxg_encoder* e = new lxg_encoder();
+  e->w = *w;
+  e->layers.assign(w->layer, w->layer + w->layers);
+  e->w.layer = e->layers.data();
+  const int H = w->hidden, F = w->ffn;
+  e->map_wqkv.resize(w->layers);
+  e->map_wo.resize(w->layers);
+  e->map_w1.resize(w->layers);
+  e->map_w2.resize(w->layers);
+  for (int l = 0; l < w->layers; ++l) {
+    const lxg_bert_layer& L = e->layers[l];
+    const void* ptrs[] = {L.wqkv, L.bqkv, L.wo, L.bo, L.ln1_g, L.ln1_b, L.w1, L.b1, L.w2, L.b2, L.ln2_g, L.ln2_b};
+    for (const void* p : ptrs)
+      if (!p || !is_device_ptr(p)) {
+        delete e;
+        return set_error(LXG_EINVAL, "layer " + std::to_string(l) + ": weight pointer is not device memory");
+      }
+    int rc;
+    if ((rc = make_map(&e->map_wqkv[l], L.wqkv, 3 * H, H)) != LXG_OK || (rc = make_map(&e->map_wo[l], L.wo, H, H)) != LXG_OK ||
+        (rc = make_map(&e->map_w1[l], L.w1, F, H)) != LXG_OK || (rc = make_map(&e->map_w2[l], L.w2, H, F)) != LXG_OK) {
+      delete e;
+      return rc;
+    }
+  }
+  *out = e;
+  return LXG_OK;
 }
-int lxg_encoder_destroy(lxg_encoder*) { return LXG_OK; }
-int lxg_encode(lxg_encoder*, const int32_t*, const int32_t*, int32_t, int32_t, int, float*, void*) {
-  return lxg::set_error(LXG_EUNSUPPORTED, "encoder kernels not built yet");
+
+int lxg_encoder_destroy(lxg_encoder* e) {
+  if (!e) return LXG_OK;
+  free_ws(e);
+  delete e;
+  return LXG_OK;
 }
+
+int lxg_encoder_last_launches(const lxg_encoder* e) { return e ? e->launches : -1; }
+
+int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, int pool, float* out,
+               void* stream) {
+  if (!e || !ids || !mask || !out) return set_error(LXG_EINVAL, "NULL argument");
+  if (b < 0 || s <= 0) return set_error(LXG_EINVAL, "b must be >= 0 and s >= 1");
+  if (s > e->w.max_pos) return set_error(LXG_EINVAL, "sequence longer than the position table");
+  if (pool != LXG_POOL_MEAN && pool != LXG_POOL_CLS) return set_error(LXG_EINVAL, "bad pooling mode");
+  if (b == 0) return LXG_OK;
+  std::lock_guard<std::mutex> lock(e->mu);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  const long long tokens_ll = static_cast<long long>(b) * s;
+  if (tokens_ll > (1 << 22)) return set_error(LXG_EUNSUPPORTED, "more than 4M tokens per call");
+  const int tokens = static_cast<int>(tokens_ll);
+  int rc = reserve_ws(e, tokens);
+  if (rc != LXG_OK) return rc;
+  const int H = e->w.hidden, F = e->w.ffn, heads = e->w.heads, dh = H / heads;
+  const bool ids_dev = is_device_ptr(ids), mask_dev = is_device_ptr(mask), out_dev = is_device_ptr(out);
+  LXG_CUDA(cudaMemcpyAsync(e->ids, ids, tokens * sizeof(int), ids_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  LXG_CUDA(cudaMemcpyAsync(e->mask, mask, tokens * sizeof(int), mask_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  int launches = 0;
+  const int warps_per_block = 8;
+  const int row_blocks = (tokens + warps_per_block - 1) / warps_per_block;
+  embed_ln_kernel<<<row_blocks, 256, 0, st>>>(e->ids, tokens, s, H, e->w.vocab, reinterpret_cast<const __half*>(e->w.word_emb),
+                                              reinterpret_cast<const __half*>(e->w.pos_emb),
+                                              reinterpret_cast<const __half*>(e->w.type_emb),
+                                              reinterpret_cast<const float*>(e->w.emb_ln_g),
+                                              reinterpret_cast<const float*>(e->w.emb_ln_b), e->w.ln_eps, e->h);
+  LXG_CUDA(cudaGetLastError());
+  ++launches;
+  const int kpitch = dh + 2;
+  const size_t attn_smem = static_cast<size_t>(2) * s * kpitch * sizeof(__half) + static_cast<size_t>(s) * sizeof(float) +
+                           static_cast<size_t>(kAttnThreads / 32) * s * sizeof(float);
+  static size_t attn_attr = 48 * 1024;
+  if (attn_smem > attn_attr) {
+    LXG_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
+    attn_attr = attn_smem;
+  }
+  for (int l = 0; l < e->w.layers; ++l) {
+    const lxg_bert_layer& L = e->layers[l];
+    GemmParams gp{};
+    // QKV projection
+    gp.bias = reinterpret_cast<const float*>(L.bqkv);
+    gp.out = e->qkv;
+    gp.m = tokens;
+    gp.n = 3 * H;
+    gp.k = H;
+    LXG_CUDA(launch_gemm<kEpiStore>(e->map_h, e->map_wqkv[l], gp, st));
+    attention_kernel<<<b * heads, kAttnThreads, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
+    LXG_CUDA(cudaGetLastError());
+    // attention.output.dense + residual -> LayerNorm
+    gp.bias = reinterpret_cast<const float*>(L.bo);
+    gp.residual = e->h;
+    gp.out = e->pre;
+    gp.n = H;
+    gp.k = H;
+    LXG_CUDA(launch_gemm<kEpiResid>(e->map_ctx, e->map_wo[l], gp, st));
+    layernorm_kernel<<<row_blocks, 256, 0, st>>>(e->pre, tokens, H, reinterpret_cast<const float*>(L.ln1_g),
+                                                 reinterpret_cast<const float*>(L.ln1_b), e->w.ln_eps, e->h);
+    LXG_CUDA(cudaGetLastError());
+    // intermediate.dense + GELU
+    gp.bias = reinterpret_cast<const float*>(L.b1);
+    gp.residual = nullptr;
+    gp.out = e->ffn;
+    gp.n = F;
+    gp.k = H;
+    LXG_CUDA(launch_gemm<kEpiGelu>(e->map_h, e->map_w1[l], gp, st));
+    // output.dense + residual -> LayerNorm
+    gp.bias = reinterpret_cast<const float*>(L.b2);
+    gp.residual = e->h;
+    gp.out = e->pre;
+    gp.n = H;
+    gp.k = F;
+    LXG_CUDA(launch_gemm<kEpiResid>(e->map_ffn, e->map_w2[l], gp, st));
+    layernorm_kernel<<<row_blocks, 256, 0, st>>>(e->pre, tokens, H, reinterpret_cast<const float*>(L.ln2_g),
+                                                 reinterpret_cast<const float*>(L.ln2_b), e->w.ln_eps, e->h);
+    LXG_CUDA(cudaGetLastError());
+    launches += 7;
+  }
+  float* out_d = out;
+  float* staged = nullptr;
+  if (!out_dev) {
+    staged = e->pre;  // fp32 [cap, H] scratch is free again after the last LayerNorm
+    out_d = staged;
+  }
+  pool_normalize_kernel<<<b, 256, H * sizeof(float), st>>>(e->h, e->mask, s, H, pool == LXG_POOL_CLS ? 1 : 0, out_d);
+  LXG_CUDA(cudaGetLastError());
+  ++launches;
+  e->launches = launches;
+  if (!out_dev) {
+    LXG_CUDA(cudaMemcpyAsync(out, staged, static_cast<size_t>(b) * H * sizeof(float), cudaMemcpyDeviceToHost, st));
+    LXG_CUDA(cudaStreamSynchronize(st));
+  }
+  return LXG_OK;
 }
+
+}  // extern "C"

@@ -144,8 +144,9 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
   // list capacity: room for many appends between two compactions (each one costs a warp ~1-2k
   // cycles); a mid-scan compaction may keep up to keep_max entries (cheaper inexact cut)
   pl.cap = pl.kp <= 64 ? 4 * pl.kp : 2 * pl.kp;
+  pl.cap = std::max(pl.cap, pl.kp + 2 * ix->tile_rows);  // a whole tile is appended between compactions
   pl.keep_max = pl.kp + std::max(16, pl.kp / 2);
-  if (pl.keep_max > pl.cap - 64) pl.keep_max = pl.kp;
+  if (pl.keep_max > pl.cap - ix->tile_rows - 32) pl.keep_max = pl.kp;
   pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
   pl.num_tiles = static_cast<int>((ix->cv.n + ix->tile_rows - 1) / ix->tile_rows);
   pl.pair = pl.qblocks >= 2 && !g_force_single;

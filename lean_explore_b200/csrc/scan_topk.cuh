@@ -166,6 +166,8 @@ __device__ __noinline__ float warp_compact(uint2* __restrict__ buf, int c, int k
     r = warp_compact_regs<4>(buf, c, kp, keep_max, lane, kept);
   } else if (c <= 256) {
     r = warp_compact_regs<8>(buf, c, kp, keep_max, lane, kept);
+  } else if (c <= 384) {
+    r = warp_compact_regs<12>(buf, c, kp, keep_max, lane, kept);
   } else {
     // large k: keys stay in memory, always exact
     const uint32_t lt_mask = (1u << lane) - 1u;
@@ -230,10 +232,11 @@ __device__ __forceinline__ void compact_full_lists(ListState& ls, int limit, int
   }
 }
 
-// Cold path of the epilogue: (re)load one 32-column chunk of the accumulator from TMEM, append
-// the scores above the thread's threshold to its list, compact lists that filled up.
-__device__ __noinline__ void append_chunk(uint32_t taddr, ListState& ls, int base_row, int valid, int kp,
-                                          int keep_max, int cap, int lane, float* __restrict__ dbg_row) {
+// Cold path of the epilogue: (re)load one 32-column chunk of the accumulator from TMEM and append
+// the scores above the thread's threshold to its list.  Lists are compacted once per tile, AFTER
+// the accumulator has been handed back to the MMA warp, so a compaction overlaps the next MMAs.
+__device__ __noinline__ void append_chunk(uint32_t taddr, ListState& ls, int base_row, int valid,
+                                          float* __restrict__ dbg_row) {
   uint32_t r[32];
   ptx::tmem_ld_32x32b_x32(taddr, r);
   ptx::tc_wait_ld();
@@ -252,7 +255,6 @@ __device__ __noinline__ void append_chunk(uint32_t taddr, ListState& ls, int bas
     }
   }
   ls.cnt = cnt;
-  compact_full_lists(ls, cap - 32, kp, keep_max, lane);
 }
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
@@ -271,7 +273,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr int kChunksPerTile = N_T / 32;
   constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, N_T);
-  constexpr uint32_t kArrivals = kPair ? 2 * kEpiThreads : kEpiThreads;
+  constexpr uint32_t kArrivals = (kPair ? 2 : 1) * (kEpiThreads / 32);  // one arrival per epilogue warp
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -457,7 +459,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
     ptx::tc_wait_st();
     ptx::tc_fence_before();
-    if constexpr (kPair) ptx::mbar_arrive_cluster(&a_ready_bar, 0); else ptx::mbar_arrive(&a_ready_bar);
+    __syncwarp();
+    if (lane == 0) {
+      if constexpr (kPair) ptx::mbar_arrive_cluster(&a_ready_bar, 0); else ptx::mbar_arrive(&a_ready_bar);
+    }
 
     // ---- threshold scan
     const size_t list = static_cast<size_t>(slice) * p.nq + (live ? q : 0);
@@ -490,12 +495,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[c & 1][j]) > ls.thr);
           if (valid < 32 || dbg || __any_sync(0xffffffffu, hit)) {
             ptx::tc_wait_ld();  // settle the prefetched chunk before the call (registers may be saved)
-            append_chunk(tile_addr + c * 32, ls, base_row, valid, kp, keep_max, cap, lane, dbg_row);
+            append_chunk(tile_addr + c * 32, ls, base_row, valid, dbg_row);
           }
         }
       }
       ptx::tc_fence_before();
-      if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {  // one arrival per warp (in pair mode the odd CTA's arrivals are remote)
+        if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      // a tile appends at most N_T entries per list: keep that much room for the next one
+      compact_full_lists(ls, cap - N_T, kp, keep_max, lane);
     }
     // ---- final compaction to exactly the slice's top-kp
     compact_full_lists(ls, kp, kp, kp, lane);
