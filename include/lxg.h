@@ -130,8 +130,9 @@ int lxg_debug_scores(lxg_index* index, const float* x_dev, int32_t nq, int norma
 /* ---- sentence encoder (BERT-class) --------------------------------------------------
  * Replaces SentenceTransformer.encode inside EmbeddingClient.embed
  * (src/lean_explore/util/embedding_client.py:88-101): transformer forward -> pooling ->
- * L2 normalise.  Weights are fp16 device pointers laid out as HF BertModel stores them
- * (nn.Linear weight [out, in] row-major), owned by the caller. */
+ * L2 normalise.  Device pointers owned by the caller: matrices (nn.Linear weights [out, in]
+ * row-major as HF BertModel stores them, embedding tables) are fp16; vectors (biases, LayerNorm
+ * gamma / beta) are fp32.  hidden and ffn must be multiples of 128, head size even and <= 64. */
 typedef struct lxg_bert_layer {
   const void *wqkv, *bqkv;   /* [3H, H], [3H]  (query|key|value stacked) */
   const void *wo, *bo;       /* [H, H], [H] */
@@ -151,6 +152,7 @@ typedef struct lxg_bert_weights {
 
 int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w);
 int lxg_encoder_destroy(lxg_encoder* enc);
+int lxg_encoder_last_launches(const lxg_encoder* enc); /* kernels launched by the last lxg_encode */
 /* ids/mask: [b, s] int32 token ids / attention mask (host or device); out: [b, H] float32
  * unit vectors (host or device).  pool = LXG_POOL_MEAN | LXG_POOL_CLS. */
 int lxg_encode(lxg_encoder* enc, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,

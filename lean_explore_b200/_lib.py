@@ -77,6 +77,7 @@ SIGNATURES = {
                                  POINTER(c_float), c_void_p]),
     "lxg_encoder_create": (c_int, [POINTER(c_void_p), POINTER(BertWeights)]),
     "lxg_encoder_destroy": (c_int, [c_void_p]),
+    "lxg_encoder_last_launches": (c_int, [c_void_p]),
     "lxg_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int, c_void_p, c_void_p]),
 }
 

@@ -1,5 +1,6 @@
 // Shared host-side helpers of the lxg C-ABI implementation.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <string>
@@ -9,6 +10,12 @@ namespace lxg {
 int set_error(int code, const std::string& msg);
 bool is_device_ptr(const void* p);
 int num_sms();
+// cuTensorMapEncodeTiled resolved through the runtime by lxg_init (no link-time libcuda dependency).
+bool encode_tensor_map_ready();
+CUresult encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base,
+                           const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box,
+                           const cuuint32_t* estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw,
+                           CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob);
 }  // namespace lxg
 
 #define LXG_CUDA(call)                                                                          \

@@ -29,6 +29,7 @@ static std::mutex g_init_mutex;
 static bool g_inited = false;
 static int g_device = -1;
 static int g_num_sms = 0;
+static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
 static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -37,6 +38,13 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 static EncodeTiledFn g_encode_tiled = nullptr;
 
 int num_sms() { return g_num_sms; }
+bool encode_tensor_map_ready() { return g_encode_tiled != nullptr; }
+CUresult encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base,
+                           const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box,
+                           const cuuint32_t* estr, CUtensorMapInterleave il, CUtensorMapSwizzle sw,
+                           CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob) {
+  return g_encode_tiled(map, dt, rank, base, gdim, gstride, box, estr, il, sw, l2, oob);
+}
 
 bool is_device_ptr(const void* p) {
   cudaPointerAttributes a;
@@ -223,6 +231,8 @@ int lxg_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   const char* fs = std::getenv("LXG_SCAN_SINGLE");
   g_force_single = fs && fs[0] == '1';
+  const char* nl = std::getenv("LXG_SCAN_NOLEVEL");
+  g_no_level = nl && nl[0] == '1';
   g_device = device;
   g_inited = true;
   return LXG_OK;
@@ -404,6 +414,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   const size_t o_flags = take(64);
   const size_t o_flist = take(nq * sizeof(int));
   const size_t o_theta = take(nq * sizeof(double));
+  const size_t o_lvl = take(lists * sizeof(uint32_t));
   LXG_CUDA(ix->ws_small.reserve(off));
   LXG_CUDA(ix->ws_x.reserve(static_cast<size_t>(nq) * d * sizeof(float)));
   uint8_t* sm = reinterpret_cast<uint8_t*>(ix->ws_small.p);
@@ -429,6 +440,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.kp = pl.kp;
   sp.cap = pl.cap;
   sp.keep_max = pl.keep_max;
+  sp.lvl = reinterpret_cast<uint32_t*>(sm + o_lvl);
+  sp.lvl_r = (pl.kp + pl.slices - 1) / pl.slices;
+  if (pl.slices < 2 || sp.lvl_r > 8 || g_no_level) sp.lvl_r = 0;
+  if (sp.lvl_r > 0) LXG_CUDA(cudaMemsetAsync(sp.lvl, 0, lists * sizeof(uint32_t), st));
   sp.normalize = normalize;
 
   int launches = 0;

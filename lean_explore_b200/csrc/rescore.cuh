@@ -69,82 +69,176 @@ __device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsign
   return sa > sb || (sa == sb && ia < ib);
 }
 
-// One CTA per query.  Dynamic shared memory: slices*kp 64-bit keys, then kp (double,uint) pairs,
-// then d floats.
+// One CTA per query.  Dynamic shared memory: slices*kp (score key, row) pairs, then kp
+// (double,uint) pairs, then d floats.
 __global__ void __launch_bounds__(kMergeThreads)
 merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   extern __shared__ __align__(16) uint8_t msm[];
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int max_items = p.slices * p.kp;
-  unsigned long long* keys = reinterpret_cast<unsigned long long*>(msm);
-  double* sel_score = reinterpret_cast<double*>(keys + max_items);
+  uint2* items = reinterpret_cast<uint2*>(msm);  // .x = ordered score key, .y = row
+  double* sel_score = reinterpret_cast<double*>(items + max_items);
   unsigned* sel_row = reinterpret_cast<unsigned*>(sel_score + p.kp);
   float* xq = reinterpret_cast<float*>(sel_row + p.kp);
   __shared__ int s_off[160];
-  __shared__ int s_cnt, s_sel;
+  __shared__ int s_wsum[kMergeThreads / 32];
+  __shared__ int s_cnt[3], s_sel;
+  __shared__ uint32_t s_kmin, s_kmax;
   __shared__ float s_t0;
   __shared__ double s_kth;
 
   for (int i = tid; i < cv.d; i += kMergeThreads) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
-  if (tid == 0) {
-    int off = 0;
-    float t0 = -CUDART_INF_F;
-    for (int s = 0; s < p.slices; ++s) {
-      s_off[s] = off;
-      off += p.cand_count[static_cast<size_t>(s) * p.nq + q];
-      t0 = fmaxf(t0, p.slice_thr[static_cast<size_t>(s) * p.nq + q]);
+  // offsets of the slice lists (exclusive scan of their lengths) and the largest slice threshold
+  {
+    int c = 0;
+    float t = -CUDART_INF_F;
+    if (tid < p.slices) {  // slices <= 148 < kMergeThreads
+      c = p.cand_count[static_cast<size_t>(tid) * p.nq + q];
+      t = p.slice_thr[static_cast<size_t>(tid) * p.nq + q];
     }
-    s_off[p.slices] = off;
-    s_t0 = t0;
-    s_sel = 0;
-    s_kth = 0.0;
+    int incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
+    if (lane == 31) s_wsum[warp] = incl;
+    if (tid == 0) {
+      s_t0 = -CUDART_INF_F;
+      s_sel = 0;
+      s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+      s_kth = 0.0;
+      s_kmin = 0xFFFFFFFFu;
+      s_kmax = 0u;
+    }
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; ++w) base += s_wsum[w];
+    if (tid < p.slices) s_off[tid] = base + incl - c;
+    if (tid == p.slices - 1) s_off[p.slices] = base + incl;
+    // largest slice threshold (ordered-key atomic max, decoded below)
+    if (lane == 0) atomicMax(&s_kmax, float_to_key(__float_as_uint(t)));
+    __syncthreads();
+    if (tid == 0) {
+      s_t0 = __uint_as_float(key_to_float_bits(s_kmax));
+      s_kmax = 0u;
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const int m = s_off[p.slices];
-  // composite key: higher score first, then lower row
+  uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
   for (int s = warp; s < p.slices; s += kMergeThreads / 32) {
     const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
     const int c = s_off[s + 1] - s_off[s];
     for (int i = lane; i < c; i += 32) {
       const uint2 e = __ldcg(lst + i);
-      keys[s_off[s] + i] =
-          (static_cast<unsigned long long>(float_to_key(e.x)) << 32) | (0xFFFFFFFFu - e.y);
+      const uint32_t key = float_to_key(e.x);
+      items[s_off[s] + i] = make_uint2(key, e.y);
+      kmin = min(kmin, key);
+      kmax = max(kmax, key);
     }
+  }
+  kmin = __reduce_min_sync(0xffffffffu, kmin);
+  kmax = __reduce_max_sync(0xffffffffu, kmax);
+  if (lane == 0) {
+    atomicMin(&s_kmin, kmin);
+    atomicMax(&s_kmax, kmax);
   }
   __syncthreads();
 
-  // kp-th largest composite key (keys are distinct: rows are distinct)
-  unsigned long long prefix = 0;
+  // cut = kp-th largest score key (bisection from the highest bit in which the keys differ);
+  // entries above the cut are selected, ties with the cut by ascending row
+  uint32_t cut = 0;
+  int need_eq = 0x7fffffff;
   float a_min = s_t0;  // approx score no dropped row can exceed (scaled units)
   if (m > p.kp) {
-    for (int bit = 63; bit >= 0; --bit) {
-      const unsigned long long cnd = prefix | (1ull << bit);
-      int mine = 0;
-      for (int i = tid; i < m; i += kMergeThreads) mine += (keys[i] >= cnd) ? 1 : 0;
-      if (tid == 0) s_cnt = 0;
-      __syncthreads();
-      mine = __reduce_add_sync(0xffffffffu, mine);
-      if (lane == 0 && mine) atomicAdd(&s_cnt, mine);
-      __syncthreads();
-      if (s_cnt >= p.kp) prefix = cnd;
-      __syncthreads();
+    kmin = s_kmin;
+    kmax = s_kmax;
+    cut = kmax;
+    if (kmin != kmax) {
+      const int hb = 31 - __clz(kmin ^ kmax);
+      cut = (hb == 31) ? 0u : (kmax & ~((2u << hb) - 1u));
+      int cur = 0;  // three rotating counters: one barrier per step instead of three
+      for (int bit = hb; bit >= 0; --bit) {
+        const uint32_t cnd = cut | (1u << bit);
+        int mine = 0;
+        for (int i = tid; i < m; i += kMergeThreads) mine += (items[i].x >= cnd) ? 1 : 0;
+        mine = __reduce_add_sync(0xffffffffu, mine);
+        if (lane == 0 && mine) atomicAdd(&s_cnt[cur], mine);
+        __syncthreads();
+        if (s_cnt[cur] >= p.kp) cut = cnd;
+        // counter cur+2 was last read before this barrier and is next written after the following one
+        if (tid == 0) s_cnt[(cur + 2) % 3] = 0;
+        cur = (cur + 1) % 3;
+      }
     }
-    a_min = fmaxf(a_min, __uint_as_float(key_to_float_bits(static_cast<uint32_t>(prefix >> 32))));
+    __syncthreads();
+    if (tid == 0) s_cnt[0] = s_cnt[1] = 0;
+    __syncthreads();
+    int gt = 0, eq = 0;
+    for (int i = tid; i < m; i += kMergeThreads) {
+      gt += (items[i].x > cut) ? 1 : 0;
+      eq += (items[i].x == cut) ? 1 : 0;
+    }
+    gt = __reduce_add_sync(0xffffffffu, gt);
+    eq = __reduce_add_sync(0xffffffffu, eq);
+    if (lane == 0 && gt) atomicAdd(&s_cnt[0], gt);
+    if (lane == 0 && eq) atomicAdd(&s_cnt[1], eq);
+    __syncthreads();
+    need_eq = p.kp - s_cnt[0];
+    if (s_cnt[1] == need_eq) need_eq = 0x7fffffff;  // every tie is selected: no ranking needed
+    a_min = fmaxf(a_min, __uint_as_float(key_to_float_bits(cut)));
   }
   // gather the selected rows
   for (int i = tid; i < m; i += kMergeThreads) {
-    if (keys[i] >= prefix) {
-      const int slot = atomicAdd(&s_sel, 1);
-      sel_row[slot] = 0xFFFFFFFFu - static_cast<uint32_t>(keys[i] & 0xFFFFFFFFu);
+    const uint2 e = items[i];
+    bool take = e.x > cut || m <= p.kp;
+    if (!take && e.x == cut) {
+      take = need_eq == 0x7fffffff;
     }
+    if (!take && e.x == cut) {
+      // exact ties straddle the cut: rank them by row id (rare)
+      int rank = 0;
+      for (int u = 0; u < m; ++u) rank += (items[u].x == cut && items[u].y < e.y) ? 1 : 0;
+      take = rank < need_eq;
+    }
+    if (take) sel_row[atomicAdd(&s_sel, 1)] = e.y;
   }
   __syncthreads();
   const int nsel = s_sel;  // == min(m, kp)
-  // exact re-score
-  for (int j = warp; j < nsel; j += kMergeThreads / 32) {
-    const double s = warp_exact_dot(cv, sel_row[j], xq, lane);
-    if (lane == 0) sel_score[j] = s;
+  // exact re-score: a warp per row, four rows in flight per warp (the rows are random gathers)
+  for (int j0 = warp * 4; j0 < nsel; j0 += (kMergeThreads / 32) * 4) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    if (cv.dtype == 1) {
+      const __half* r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        r[u] = reinterpret_cast<const __half*>(cv.rows) + static_cast<long long>(sel_row[min(j0 + u, nsel - 1)]) * cv.pitch;
+      for (int i = lane; i < cv.d; i += 32) {
+        const double x = static_cast<double>(xq[i]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(static_cast<double>(__half2float(r[u][i])), x, acc[u]);
+      }
+    } else {
+      const float* r[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        r[u] = reinterpret_cast<const float*>(cv.rows) + static_cast<long long>(sel_row[min(j0 + u, nsel - 1)]) * cv.pitch;
+      for (int i = lane; i < cv.d; i += 32) {
+        const double x = static_cast<double>(xq[i]);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) acc[u] = fma(static_cast<double>(r[u][i]), x, acc[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      if (lane == 0 && j0 + u < nsel) sel_score[j0 + u] = acc[u];
+    }
   }
   __syncthreads();
   // rank by counting, emit the top k

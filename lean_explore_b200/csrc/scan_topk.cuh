@@ -43,6 +43,8 @@ struct ScanParams {
   int* cand_count;    // [slices, nq]
   float* slice_thr;   // [slices, nq] kp-th best of the slice (scaled units) or -inf if nothing dropped
   float* dbg_scores;  // optional [nq, n] raw tensor-core scores (tests only), else nullptr
+  uint32_t* lvl;      // [slices, nq] ordered key of the lvl_r-th best score each slice has seen (0 = none yet)
+  int lvl_r;          // slices * lvl_r >= kp; 0 disables the cross-slice level
   int nq, d, num_kc;
   int n;
   int num_tiles, slices, tiles_per_slice;
@@ -230,6 +232,43 @@ __device__ __forceinline__ void compact_full_lists(ListState& ls, int limit, int
       ls.cnt = kept;
     }
   }
+}
+
+// lvl_r-th largest score of a thread's own list (thread-private walk; lists are L2 resident).
+// Returns -inf when the list is shorter than r.  r <= 8.
+__device__ __forceinline__ float own_rth_best(const uint2* __restrict__ buf, int cnt, int r) {
+  float t[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = -CUDART_INF_F;
+  for (int i = 0; i < cnt; ++i) {
+    const float v = __uint_as_float(__ldcg(buf + i).x);
+    if (v > t[7]) {
+      t[7] = v;
+#pragma unroll
+      for (int k = 7; k > 0; --k) {
+        const float hi = fmaxf(t[k - 1], t[k]), lo = fminf(t[k - 1], t[k]);
+        t[k - 1] = hi;
+        t[k] = lo;
+      }
+    }
+  }
+  float out = t[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) out = (r - 1 == i) ? t[i] : out;
+  return out;
+}
+
+// Cross-slice level: every slice publishes the r-th best score it has seen;
+// with slices * r >= kp, at least kp corpus rows score >= the minimum of the published values, so
+// no row below that minimum can be among the query's best kp - whichever slice it lives in.
+__device__ __forceinline__ void publish_level(const ScanParams& p, int slice, int q, const ListState& ls) {
+  const float v = own_rth_best(ls.buf, ls.cnt, p.lvl_r);
+  if (v > -CUDART_INF_F) __stcg(p.lvl + static_cast<size_t>(slice) * p.nq + q, float_to_key(__float_as_uint(v)));
+}
+__device__ __forceinline__ void refresh_level(const ScanParams& p, int q, ListState& ls) {
+  uint32_t lo = 0xFFFFFFFFu;
+  for (int s = 0; s < p.slices; ++s) lo = min(lo, __ldcg(p.lvl + static_cast<size_t>(s) * p.nq + q));
+  if (lo != 0u) ls.thr = fmaxf(ls.thr, __uint_as_float(key_to_float_bits(lo)));
 }
 
 // Cold path of the epilogue: (re)load one 32-column chunk of the accumulator from TMEM and append
@@ -506,6 +545,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       }
       // a tile appends at most N_T entries per list: keep that much room for the next one
       compact_full_lists(ls, cap - N_T, kp, keep_max, lane);
+      if (p.lvl_r > 0 && live) {
+        const int done = it + 1;
+        if ((done & (done - 1)) == 0) publish_level(p, slice, q, ls);  // after tiles 1, 2, 4, 8, ...
+        if ((done & (done - 1)) == 0 || (done & 7) == 0) refresh_level(p, q, ls);
+      }
     }
     // ---- final compaction to exactly the slice's top-kp
     compact_full_lists(ls, kp, kp, kp, lane);
