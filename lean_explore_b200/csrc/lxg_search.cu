@@ -142,29 +142,72 @@ int candidates_per_slice(int k) {
 
 struct Plan {
   int kp, cap, keep_max, qblocks, slices, tiles_per_slice, num_tiles;
-  bool pair;    // CTA pairs (cta_group::2) when there are at least two query blocks
-  int grid_x;   // query blocks launched (padded to even in pair mode)
+  bool pair;      // CTA pairs (cta_group::2) when there are at least two query blocks
+  int grid_x;     // query blocks launched (padded to even in pair mode)
+  int lists;      // candidate lists per query: two per slice (one per epilogue group)
+  int lvl_r;      // cross-list level: every list publishes its lvl_r-th best (0 = disabled)
+  int max_items;  // pass-2 candidate pool (entries)
 };
+
+// Lists that see at least 8*kTrack rows (the others never publish a level, scan_topk.cuh): list
+// (slice, g) holds columns [g*N_T/2, (g+1)*N_T/2) of every tile of the slice.
+int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_per_slice) {
+  const int gc = tile_rows / 2;
+  int ok = 0;
+  for (int s = 0; s < slices; ++s) {
+    const int tb = s * tiles_per_slice;
+    const int te = std::min(num_tiles, tb + tiles_per_slice);
+    const int my = std::max(0, te - tb);
+    for (int g = 0; g < 2; ++g) {
+      long long rows = static_cast<long long>(my) * gc;
+      if (my > 0 && te == num_tiles) {
+        const long long first = static_cast<long long>(num_tiles - 1) * tile_rows + g * gc;
+        const long long valid = std::max(0ll, std::min(static_cast<long long>(gc), static_cast<long long>(n) - first));
+        rows -= gc - valid;
+      }
+      if (rows >= kTrack * 8) ++ok;
+    }
+  }
+  return ok;
+}
 
 Plan make_plan(const lxg_index* ix, int nq, int k) {
   Plan pl;
+  const int nt = ix->tile_rows;
   pl.kp = candidates_per_slice(k);
-  // list capacity: room for many appends between two compactions (each one costs a warp ~1-2k
-  // cycles); a mid-scan compaction may keep up to keep_max entries (cheaper inexact cut)
-  pl.cap = pl.kp <= 64 ? 4 * pl.kp : 2 * pl.kp;
-  pl.cap = std::max(pl.cap, pl.kp + 2 * ix->tile_rows);  // a whole tile is appended between compactions
-  pl.keep_max = pl.kp + std::max(16, pl.kp / 2);
-  if (pl.keep_max > pl.cap - ix->tile_rows - 32) pl.keep_max = pl.kp;
   pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
-  pl.num_tiles = static_cast<int>((ix->cv.n + ix->tile_rows - 1) / ix->tile_rows);
+  pl.num_tiles = static_cast<int>((ix->cv.n + nt - 1) / nt);
   pl.pair = pl.qblocks >= 2 && !g_force_single;
   pl.grid_x = pl.pair ? (pl.qblocks + 1) / 2 * 2 : pl.qblocks;
-  int s = std::max(1, g_num_sms / pl.grid_x);
-  s = std::min(s, std::max(1, 24576 / pl.kp));  // merge kernel keeps slices*kp keys in shared memory
-  s = std::min(s, 148);
-  s = std::min(s, std::max(1, pl.num_tiles));
-  pl.tiles_per_slice = (pl.num_tiles + s - 1) / s;
-  pl.slices = std::max(1, (pl.num_tiles + pl.tiles_per_slice - 1) / std::max(1, pl.tiles_per_slice));
+  auto slice_up = [&](int s) {
+    s = std::min(s, 148);
+    s = std::min(s, std::max(1, pl.num_tiles));
+    s = std::max(s, 1);
+    pl.tiles_per_slice = (pl.num_tiles + s - 1) / s;
+    pl.slices = std::max(1, (pl.num_tiles + pl.tiles_per_slice - 1) / std::max(1, pl.tiles_per_slice));
+    pl.lists = 2 * pl.slices;
+  };
+  slice_up(std::max(1, g_num_sms / pl.grid_x));
+  // cross-list level: needs lists * r >= kp with r <= kTrack
+  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice);
+  pl.lvl_r = lv >= 2 ? (pl.kp + lv - 1) / lv : 0;
+  if (pl.lvl_r > kTrack) pl.lvl_r = 0;
+  if (pl.lvl_r > 0) {
+    // lists only grow (a few hundred entries); a list that does fill up is compacted exactly
+    pl.cap = std::max(1024, pl.kp + 2 * nt);
+    pl.keep_max = pl.kp;
+    pl.max_items = std::max(6144, 4 * pl.kp);
+  } else {
+    // thresholds come from compacting full lists: pass 2 holds lists * kp keys in shared memory
+    slice_up(std::min(pl.slices, std::max(1, 12288 / pl.kp)));
+    // list capacity: room for many appends between two compactions (each one costs a warp ~1-2k
+    // cycles); a mid-scan compaction may keep up to keep_max entries (cheaper inexact cut)
+    pl.cap = pl.kp <= 64 ? 4 * pl.kp : 2 * pl.kp;
+    pl.cap = std::max(pl.cap, pl.kp + 2 * nt);  // a whole tile is appended between compactions
+    pl.keep_max = pl.kp + std::max(16, pl.kp / 2);
+    if (pl.keep_max > pl.cap - nt - 32) pl.keep_max = pl.kp;
+    pl.max_items = pl.lists * pl.kp;
+  }
   return pl;
 }
 
@@ -397,9 +440,11 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
                   double* D64, float* dbg_scores, float* dbg_qscale, cudaStream_t st, bool read_flags) {
   const int d = ix->cv.d;
   const Plan pl = make_plan(ix, nq, k);
-  const size_t lists = static_cast<size_t>(pl.slices) * nq;
+  const size_t lists = static_cast<size_t>(pl.lists) * nq;
+  const int nq_pad = pl.grid_x * kQueryBlock;
+  const int dpad = ix->num_kc * kKC;
   LXG_CUDA(ix->ws_cand.reserve(lists * pl.cap * sizeof(uint2)));
-  // small arrays: cand_count, slice_thr [lists]; qscale, qnorm [nq]; flag_count(1)+overflow(1)+pad,
+  // small arrays: cand_count, slice_thr, lvl [lists]; qscale, qnorm [nq]; flag_count(1)+overflow(1)+pad,
   // flag_list [nq]; flag_theta [nq] (double)
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -416,22 +461,25 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   const size_t o_theta = take(nq * sizeof(double));
   const size_t o_lvl = take(lists * sizeof(uint32_t));
   LXG_CUDA(ix->ws_small.reserve(off));
-  LXG_CUDA(ix->ws_x.reserve(static_cast<size_t>(nq) * d * sizeof(float)));
+  // normalised fp32 queries, then the prepared fp16 query blocks
+  const size_t xn_bytes = (static_cast<size_t>(nq) * d * sizeof(float) + 255) / 256 * 256;
+  LXG_CUDA(ix->ws_x.reserve(xn_bytes + static_cast<size_t>(nq_pad) * dpad * sizeof(__half)));
   uint8_t* sm = reinterpret_cast<uint8_t*>(ix->ws_small.p);
   int* flag_count = reinterpret_cast<int*>(sm + o_flags);
   int* overflow = flag_count + 1;
+  float* xn = reinterpret_cast<float*>(ix->ws_x.p);
+  __half* xh = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(ix->ws_x.p) + xn_bytes);
+  float* qscale = dbg_qscale ? dbg_qscale : reinterpret_cast<float*>(sm + o_qscale);
+  float* qnorm = reinterpret_cast<float*>(sm + o_qnorm);
 
   ScanParams sp{};
-  sp.x = x;
-  sp.xn = reinterpret_cast<float*>(ix->ws_x.p);
-  sp.qscale = dbg_qscale ? dbg_qscale : reinterpret_cast<float*>(sm + o_qscale);
-  sp.qnorm = reinterpret_cast<float*>(sm + o_qnorm);
+  sp.xh = xh;
   sp.cand = reinterpret_cast<uint2*>(ix->ws_cand.p);
   sp.cand_count = reinterpret_cast<int*>(sm + o_count);
   sp.slice_thr = reinterpret_cast<float*>(sm + o_thr);
   sp.dbg_scores = dbg_scores;
   sp.nq = nq;
-  sp.d = d;
+  sp.dpad = dpad;
   sp.num_kc = ix->num_kc;
   sp.n = ix->cv.n;
   sp.num_tiles = pl.num_tiles;
@@ -441,10 +489,8 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.cap = pl.cap;
   sp.keep_max = pl.keep_max;
   sp.lvl = reinterpret_cast<uint32_t*>(sm + o_lvl);
-  sp.lvl_r = (pl.kp + pl.slices - 1) / pl.slices;
-  if (pl.slices < 2 || sp.lvl_r > 8 || g_no_level) sp.lvl_r = 0;
+  sp.lvl_r = pl.lvl_r;
   if (sp.lvl_r > 0) LXG_CUDA(cudaMemsetAsync(sp.lvl, 0, lists * sizeof(uint32_t), st));
-  sp.normalize = normalize;
 
   int launches = 0;
   cudaEvent_t* ev = nullptr;
@@ -461,6 +507,9 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   }
   LXG_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
+  prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize);
+  LXG_CUDA(cudaGetLastError());
+  ++launches;
   if (ix->tile_rows == 128) {
     if (pl.pair) LXG_CUDA((launch_scan<128, true>(ix, sp, pl.grid_x, st)));
     else LXG_CUDA((launch_scan<128, false>(ix, sp, pl.grid_x, st)));
@@ -484,9 +533,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.cand = sp.cand;
   mp.cand_count = sp.cand_count;
   mp.slice_thr = sp.slice_thr;
-  mp.xn = sp.xn;
-  mp.qscale = sp.qscale;
-  mp.qnorm = sp.qnorm;
+  mp.lvl = sp.lvl_r > 0 ? sp.lvl : nullptr;
+  mp.xn = xn;
+  mp.qscale = qscale;
+  mp.qnorm = qnorm;
   mp.out_d = D;
   mp.out_i = I;
   mp.out_d64 = D64;
@@ -497,8 +547,9 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.k = k;
   mp.kp = pl.kp;
   mp.cap = pl.cap;
-  mp.slices = pl.slices;
-  const size_t msmem = static_cast<size_t>(pl.slices) * pl.kp * 8 + static_cast<size_t>(pl.kp) * 12 +
+  mp.lists = pl.lists;
+  mp.max_items = pl.max_items;
+  const size_t msmem = static_cast<size_t>(pl.max_items) * 8 + static_cast<size_t>(pl.kp) * 12 +
                        static_cast<size_t>(d) * 4 + 64;
   static size_t merge_attr = 0;
   if (msmem > merge_attr) {
@@ -517,7 +568,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
                           static_cast<size_t>(nflag_max) * sizeof(int) + 256;
   LXG_CUDA(ix->ws_exact.reserve(ex_bytes));
   ExactParams ep{};
-  ep.xn = sp.xn;
+  ep.xn = xn;
   ep.flag_count = flag_count;
   ep.flag_list = mp.flag_list;
   ep.flag_theta = mp.flag_theta;
@@ -654,7 +705,7 @@ int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t bytes = static_cast<size_t>(nq) * d * sizeof(float);
   if (is_device_ptr(x)) {
-    normalize_l2_kernel<<<(nq + 127) / 128, 128, 0, st>>>(x, nq, d);
+    normalize_l2_kernel<<<(nq + 7) / 8, 256, 0, st>>>(x, nq, d);
     LXG_CUDA(cudaGetLastError());
     return LXG_OK;
   }
@@ -662,7 +713,7 @@ int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream) {
   LXG_CUDA(cudaMalloc(&tmp, bytes));
   cudaError_t e = cudaMemcpyAsync(tmp, x, bytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) {
-    normalize_l2_kernel<<<(nq + 127) / 128, 128, 0, st>>>(tmp, nq, d);
+    normalize_l2_kernel<<<(nq + 7) / 8, 256, 0, st>>>(tmp, nq, d);
     e = cudaGetLastError();
   }
   if (e == cudaSuccess) e = cudaMemcpyAsync(x, tmp, bytes, cudaMemcpyDeviceToHost, st);

@@ -33,6 +33,7 @@ struct MergeParams {
   const uint2* cand;
   const int* cand_count;
   const float* slice_thr;
+  const uint32_t* lvl;  // [nq, lists] published levels of pass 1 (nullptr: no cross-list level)
   const float* xn;
   const float* qscale;
   const float* qnorm;
@@ -42,7 +43,8 @@ struct MergeParams {
   int* flag_count;     // number of uncertified queries
   int* flag_list;      // [nq] their ids
   double* flag_theta;  // [nq] lower bound of the true k-th best exact score
-  int nq, k, kp, cap, slices;
+  int nq, k, kp, cap, lists;
+  int max_items;       // capacity of the shared-memory candidate pool
 };
 
 // Exact inner product of one corpus row with a query held in shared memory, computed by a
@@ -69,76 +71,81 @@ __device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsign
   return sa > sb || (sa == sb && ia < ib);
 }
 
-// One CTA per query.  Dynamic shared memory: slices*kp (score key, row) pairs, then kp
+// One CTA per query.  Dynamic shared memory: max_items (score key, row) pairs, then kp
 // (double,uint) pairs, then d floats.
 __global__ void __launch_bounds__(kMergeThreads)
 merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   extern __shared__ __align__(16) uint8_t msm[];
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int max_items = p.slices * p.kp;
   uint2* items = reinterpret_cast<uint2*>(msm);  // .x = ordered score key, .y = row
-  double* sel_score = reinterpret_cast<double*>(items + max_items);
+  double* sel_score = reinterpret_cast<double*>(items + p.max_items);
   unsigned* sel_row = reinterpret_cast<unsigned*>(sel_score + p.kp);
   float* xq = reinterpret_cast<float*>(sel_row + p.kp);
-  __shared__ int s_off[160];
-  __shared__ int s_wsum[kMergeThreads / 32];
-  __shared__ int s_cnt[3], s_sel;
-  __shared__ uint32_t s_kmin, s_kmax;
-  __shared__ float s_t0;
+  __shared__ int s_cnt[3], s_sel, s_m;
+  __shared__ int s_len[2 * 148];  // list lengths (at most two lists per slice, 148 slices)
+  __shared__ uint32_t s_kmin, s_kmax, s_tkey, s_lvl;
   __shared__ double s_kth;
 
-  for (int i = tid; i < cv.d; i += kMergeThreads) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
-  // offsets of the slice lists (exclusive scan of their lengths) and the largest slice threshold
-  {
-    int c = 0;
-    float t = -CUDART_INF_F;
-    if (tid < p.slices) {  // slices <= 148 < kMergeThreads
-      c = p.cand_count[static_cast<size_t>(tid) * p.nq + q];
-      t = p.slice_thr[static_cast<size_t>(tid) * p.nq + q];
-    }
-    int incl = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int v = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += v;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t = fmaxf(t, __shfl_xor_sync(0xffffffffu, t, o));
-    if (lane == 31) s_wsum[warp] = incl;
-    if (tid == 0) {
-      s_t0 = -CUDART_INF_F;
-      s_sel = 0;
-      s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
-      s_kth = 0.0;
-      s_kmin = 0xFFFFFFFFu;
-      s_kmax = 0u;
-    }
-    __syncthreads();
-    int base = 0;
-    for (int w = 0; w < warp; ++w) base += s_wsum[w];
-    if (tid < p.slices) s_off[tid] = base + incl - c;
-    if (tid == p.slices - 1) s_off[p.slices] = base + incl;
-    // largest slice threshold (ordered-key atomic max, decoded below)
-    if (lane == 0) atomicMax(&s_kmax, float_to_key(__float_as_uint(t)));
-    __syncthreads();
-    if (tid == 0) {
-      s_t0 = __uint_as_float(key_to_float_bits(s_kmax));
-      s_kmax = 0u;
-    }
-    __syncthreads();
+  if (tid == 0) {
+    s_sel = 0;
+    s_m = 0;
+    s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+    s_kth = 0.0;
+    s_kmin = 0xFFFFFFFFu;
+    s_kmax = 0u;
+    s_tkey = 0u;
+    s_lvl = kLvlSkip;
   }
-  const int m = s_off[p.slices];
+  for (int i = tid; i < cv.d; i += kMergeThreads) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
+  __syncthreads();
+  // largest final list threshold (no dropped row scored above it) and the final cross-list level
+  // (at least kp rows score >= it: entries below it cannot be among the best kp)
+  {
+    uint32_t tk = 0u, lo = kLvlSkip;
+    for (int s = tid; s < p.lists; s += kMergeThreads) {
+      s_len[s] = p.cand_count[static_cast<size_t>(s) * p.nq + q];
+      tk = max(tk, float_to_key(__float_as_uint(p.slice_thr[static_cast<size_t>(s) * p.nq + q])));
+      if (p.lvl != nullptr) lo = min(lo, __ldcg(p.lvl + static_cast<size_t>(q) * p.lists + s));
+    }
+    tk = __reduce_max_sync(0xffffffffu, tk);
+    lo = __reduce_min_sync(0xffffffffu, lo);
+    if (lane == 0) {
+      atomicMax(&s_tkey, tk);
+      atomicMin(&s_lvl, lo);
+    }
+  }
+  __syncthreads();
+  const uint32_t tau_key = (p.lvl != nullptr && s_lvl != kLvlNone && s_lvl != kLvlSkip) ? s_lvl : 0u;
+  // gather the entries at or above the level into shared memory (a warp per list, four 32-entry
+  // chunks in flight)
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-  for (int s = warp; s < p.slices; s += kMergeThreads / 32) {
+  for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
     const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
-    const int c = s_off[s + 1] - s_off[s];
-    for (int i = lane; i < c; i += 32) {
-      const uint2 e = __ldcg(lst + i);
-      const uint32_t key = float_to_key(e.x);
-      items[s_off[s] + i] = make_uint2(key, e.y);
-      kmin = min(kmin, key);
-      kmax = max(kmax, key);
+    const int c = s_len[s];
+    for (int i0 = 0; i0 < c; i0 += 128) {
+      uint2 e[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * 32 + lane;
+        e[u] = i < c ? __ldcg(lst + i) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t key = float_to_key(e[u].x);
+        const bool keep = (i0 + u * 32 + lane < c) && key >= tau_key;
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (bal == 0u) continue;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        const int pos = base + __popc(bal & ((1u << lane) - 1u));
+        if (keep && pos < p.max_items) {
+          items[pos] = make_uint2(key, e[u].y);
+          kmin = min(kmin, key);
+          kmax = max(kmax, key);
+        }
+      }
     }
   }
   kmin = __reduce_min_sync(0xffffffffu, kmin);
@@ -148,12 +155,27 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     atomicMax(&s_kmax, kmax);
   }
   __syncthreads();
+  const int m = s_m;
+  const float tau = tau_key ? __uint_as_float(key_to_float_bits(tau_key)) : -CUDART_INF_F;
+  if (m > p.max_items) {
+    // more survivors than the pool holds (adversarial row order): hand the query to the exact
+    // path.  At least kp >= k rows have a tensor-core score >= tau, which bounds the k-th best.
+    if (tid == 0) {
+      const double unscale = 1.0 / (static_cast<double>(p.qscale[q]) * cv.scan_scale);
+      const double eps = static_cast<double>(cv.max_row_norm) * p.qnorm[q] * cv.rel_err;
+      const int slot = atomicAdd(p.flag_count, 1);
+      p.flag_list[slot] = q;
+      p.flag_theta[slot] = static_cast<double>(tau) * unscale - eps;
+    }
+    return;
+  }
 
   // cut = kp-th largest score key (bisection from the highest bit in which the keys differ);
   // entries above the cut are selected, ties with the cut by ascending row
   uint32_t cut = 0;
   int need_eq = 0x7fffffff;
-  float a_min = s_t0;  // approx score no dropped row can exceed (scaled units)
+  // approx score no dropped row can exceed (scaled units)
+  float a_min = fmaxf(__uint_as_float(key_to_float_bits(s_tkey)), tau);
   if (m > p.kp) {
     kmin = s_kmin;
     kmax = s_kmax;

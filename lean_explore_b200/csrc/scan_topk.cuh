@@ -1,23 +1,26 @@
 // Pass 1 of the flat inner-product search (replaces faiss.normalize_L2 + Index.search,
 // reference call sites: src/lean_explore/search/engine.py:242 and :250).
 //
-// One persistent CTA per (corpus slice, block of 128 queries):
-//   * epilogue warps 0-3: thread t owns query t of the block.  Prologue = the fused
-//     L2-normalise (FAISS fvec_renorm_L2 semantics, engine.py:242): read the fp32 query row,
-//     normalise, scale by a power of two, convert to fp16 and park it in TENSOR MEMORY as the
-//     A operand (lane t, d/2 columns).  The queries never touch shared memory.
-//   * warp 4: TMA producer. Streams the slice of the fp16 corpus ("scan copy") through a
-//     ring of 128B-swizzled shared-memory stages (N_T rows x 64 dims each) - all ~192 KB of
-//     shared memory is corpus pipeline.
-//   * warp 5: one elected thread issues tcgen05.mma (M=128 queries, N=N_T corpus rows, K=16),
-//     A from TMEM, B from the swizzled stage, fp32 accumulators in TMEM, double buffered.
-//   * epilogue: tcgen05.ld 32 scores per thread at a time (lane = query, column = corpus
-//     row), compare against the thread's private threshold; survivors are appended to the
-//     query's candidate list (global memory, L2 resident).  When a list fills up the warp
-//     compacts it cooperatively to the best kp entries (exact k-th-largest by bit bisection)
-//     and raises the threshold.
-// The output is, per (slice, query), the exact top-kp of the slice *by fp16-input score*.
-// Pass 2 (rescore.cuh) merges slices, re-scores the survivors exactly and certifies that the
+// prep_queries_kernel (one warp per query): the fused L2-normalise (FAISS fvec_renorm_L2
+// semantics, engine.py:242), a power-of-two scale and the fp16 conversion of the query block.
+//
+// scan_topk_kernel: one persistent CTA per (corpus slice, block of 128 queries), 10 warps:
+//   * warp 8: TMA producer.  Streams the slice of the fp16 corpus ("scan copy") through a ring
+//     of 128B-swizzled shared-memory stages (N_T rows x 64 dims each) - all ~192 KB of shared
+//     memory is corpus pipeline.
+//   * warp 9: one elected thread issues tcgen05.mma (M=128 queries, N=N_T corpus rows, K=16),
+//     A (the fp16 queries) from TENSOR MEMORY, B from the swizzled stage, fp32 accumulators in
+//     TMEM, double buffered.
+//   * warps 0-7: epilogue, two groups of four.  Group g drains accumulator g (tiles g, g+2, ...):
+//     thread t owns query t of the block: tcgen05.ld 32 scores at a time (lane = query, column
+//     = corpus row), max-tree per 8 columns against the thread's threshold; survivors are
+//     appended to the (slice, group, query) candidate list in global memory (L2 resident).
+//     Thresholds come from a CROSS-LIST LEVEL: every list publishes the r-th best score it has
+//     seen (register tracker); with lists * r >= kp at least kp rows score >= the minimum of the
+//     published values, so nothing below that minimum can be among the query's best kp.
+//     Without a level (too few lists for r <= 8) a list that fills up is compacted by the warp
+//     to its best kp entries (exact k-th-largest by bit bisection) and that raises the threshold.
+// Pass 2 (rescore.cuh) merges the lists, re-scores the survivors exactly and certifies that the
 // answer equals the exact top-k.
 #pragma once
 #include <cuda_fp16.h>
@@ -27,29 +30,29 @@
 
 namespace lxg {
 
-constexpr int kEpiThreads = 128;   // warps 0..3
-constexpr int kScanThreads = 192;  // + warp 4 (TMA) + warp 5 (MMA)
+constexpr int kEpiWarps = 8;        // warps 0..7: two groups of four, one per accumulator
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kScanThreads = kEpiThreads + 64;  // + warp 8 (TMA) + warp 9 (MMA)
 constexpr int kKC = 64;            // fp16 elements per 128-byte swizzled row
 constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline
 constexpr int kStageBytes = 32768; // one pipeline stage: N_T rows x (32768 / (128 N_T)) k-chunks
 constexpr int kQueryBlock = 128;   // queries per CTA == UMMA M
+constexpr int kTrack = 8;          // register tracker: best kTrack scores a list has seen
+constexpr uint32_t kLvlNone = 0u;            // list has not published a level yet
+constexpr uint32_t kLvlSkip = 0xFFFFFFFFu;   // list too short to ever publish one: not counted
 
 struct ScanParams {
-  const float* x;     // [nq, d] fp32 queries as given by the caller
-  float* xn;          // [nq, d] fp32 queries after normalize_L2 (written by slice 0)
-  float* qscale;      // [nq] power-of-two scale applied before the fp16 conversion
-  float* qnorm;       // [nq] ||xn||_2
-  uint2* cand;        // [slices, nq, cap] (score bits, row)
-  int* cand_count;    // [slices, nq]
-  float* slice_thr;   // [slices, nq] kp-th best of the slice (scaled units) or -inf if nothing dropped
+  const __half* xh;   // [query blocks * 128, dpad] prepared queries (normalised, scaled, fp16, zero padded)
+  uint2* cand;        // [lists, nq, cap] (score bits, row);  list = slice * 2 + epilogue group
+  int* cand_count;    // [lists, nq]
+  float* slice_thr;   // [lists, nq] final threshold of the list: every dropped row scored <= it
   float* dbg_scores;  // optional [nq, n] raw tensor-core scores (tests only), else nullptr
-  uint32_t* lvl;      // [slices, nq] ordered key of the lvl_r-th best score each slice has seen (0 = none yet)
-  int lvl_r;          // slices * lvl_r >= kp; 0 disables the cross-slice level
-  int nq, d, num_kc;
+  uint32_t* lvl;      // [nq, lists] ordered key of the lvl_r-th best score the list has seen
+  int lvl_r;          // (#lists with >= 8 kTrack rows) * lvl_r >= kp; 0 disables the cross-list level
+  int nq, dpad, num_kc;
   int n;
   int num_tiles, slices, tiles_per_slice;
   int kp, cap, keep_max;
-  int normalize;
 };
 
 __device__ __forceinline__ uint32_t float_to_key(uint32_t b) {
@@ -59,37 +62,74 @@ __device__ __forceinline__ uint32_t key_to_float_bits(uint32_t k) {
   return (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
 }
 
-// ||x||^2 of one fp32 row, accumulated in fp64 in a fixed order (four interleaved partial sums),
-// rounded once to fp32: the `nr` of FAISS' fvec_renorm_L2.  Shared by the fused prologue of the
-// scan kernel and by normalize_l2_kernel so both produce bit-identical normalised queries.
-__device__ __forceinline__ float row_norm_sq(const float* xr, int d) {
-  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-  int i = 0;
-  for (; i + 3 < d; i += 4) {
-    const double a = xr[i], b = xr[i + 1], c = xr[i + 2], e = xr[i + 3];
-    s0 = fma(a, a, s0);
-    s1 = fma(b, b, s1);
-    s2 = fma(c, c, s2);
-    s3 = fma(e, e, s3);
-  }
-  for (; i < d; ++i) {
+// ||x||^2 of one fp32 row by a full warp, accumulated in fp64 in a fixed order (lane-strided
+// partial sums, xor tree), rounded once to fp32: the `nr` of FAISS' fvec_renorm_L2.  Shared by
+// prep_queries_kernel and normalize_l2_kernel so both produce bit-identical normalised queries.
+__device__ __forceinline__ float warp_row_norm_sq(const float* __restrict__ xr, int d, int lane) {
+  double s = 0.0;
+  for (int i = lane; i < d; i += 32) {
     const double a = xr[i];
-    s0 = fma(a, a, s0);
+    s = fma(a, a, s);
   }
-  return static_cast<float>((s0 + s1) + (s2 + s3));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return static_cast<float>(s);
 }
 // inv_nr = 1.0 / sqrtf(nr) evaluated in double and rounded to float, as FAISS writes it.
 __device__ __forceinline__ float inv_norm(float nr) {
   return nr > 0.0f ? static_cast<float>(1.0 / static_cast<double>(sqrtf(nr))) : 1.0f;
 }
 
-// In-place faiss.normalize_L2 (engine.py:242): one thread per row.
-__global__ void __launch_bounds__(128) normalize_l2_kernel(float* __restrict__ x, int nq, int d) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+// In-place faiss.normalize_L2 (engine.py:242): one warp per row.
+__global__ void __launch_bounds__(256) normalize_l2_kernel(float* __restrict__ x, int nq, int d) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (q >= nq) return;
   float* xr = x + static_cast<size_t>(q) * d;
-  const float inv = inv_norm(row_norm_sq(xr, d));
-  for (int i = 0; i < d; ++i) xr[i] = xr[i] * inv;
+  const float inv = inv_norm(warp_row_norm_sq(xr, d, lane));
+  for (int i = lane; i < d; i += 32) xr[i] = xr[i] * inv;
+}
+
+// Query preparation, one warp per row of the padded query block matrix:
+//   xn  = normalize_L2(x) (fp32, what the exact re-score uses),
+//   xh  = fp16(xn * 2^e), e chosen so that max|xn * 2^e| lands in [1,2): exact scaling, keeps
+//         fp16 out of the subnormals; rows >= nq and columns >= d are zero,
+//   qscale = 2^e, qnorm = ||xn||_2 rounded up (used only in the certificate's error bound).
+__global__ void __launch_bounds__(256)
+prep_queries_kernel(const float* __restrict__ x, float* __restrict__ xn, __half* __restrict__ xh,
+                    float* __restrict__ qscale, float* __restrict__ qnorm, int nq, int nq_pad, int d,
+                    int dpad, int normalize) {
+  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= nq_pad) return;
+  __half* hr = xh + static_cast<size_t>(q) * dpad;
+  if (q >= nq) {
+    for (int i = lane; i < dpad; i += 32) hr[i] = __float2half_rn(0.0f);
+    return;
+  }
+  const float* xr = x + static_cast<size_t>(q) * d;
+  float* nr = xn + static_cast<size_t>(q) * d;
+  const float inv = normalize ? inv_norm(warp_row_norm_sq(xr, d, lane)) : 1.0f;
+  float amax = 0.0f;
+  double n2 = 0.0;
+  for (int i = lane; i < d; i += 32) {
+    const float v = xr[i] * inv;
+    nr[i] = v;
+    amax = fmaxf(amax, fabsf(v));
+    n2 = fma(static_cast<double>(v), static_cast<double>(v), n2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+  }
+  float sq = 1.0f;
+  if (amax > 0.0f && amax < CUDART_INF_F) sq = ldexpf(1.0f, -ilogbf(amax));
+  for (int i = lane; i < dpad; i += 32) hr[i] = __float2half_rn(i < d ? xr[i] * inv * sq : 0.0f);
+  if (lane == 0) {
+    qscale[q] = sq;
+    qnorm[q] = static_cast<float>(sqrt(n2)) * 1.0000002f;
+  }
 }
 
 // Warp-cooperative compaction of one candidate list (c > kp entries on entry).
@@ -212,88 +252,109 @@ __device__ __noinline__ float warp_compact(uint2* __restrict__ buf, int c, int k
 // State of one epilogue thread's candidate list.
 struct ListState {
   uint2* buf;
+  uint2* wp;  // next free entry
   float thr;  // scores <= thr are dropped
-  int cnt;
+  __device__ __forceinline__ int count() const { return static_cast<int>(wp - buf); }
 };
 
 // Compacts the lists of every lane whose list is fuller than `limit` (warp-cooperative).
 __device__ __forceinline__ void compact_full_lists(ListState& ls, int limit, int kp, int keep_max, int lane) {
-  uint32_t need = __ballot_sync(0xffffffffu, ls.cnt > limit);
+  uint32_t need = __ballot_sync(0xffffffffu, ls.count() > limit);
   while (need) {
     const int src = __ffs(need) - 1;
     need &= need - 1;
     uint2* b = reinterpret_cast<uint2*>(
         __shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(ls.buf), src));
-    const int bc = __shfl_sync(0xffffffffu, ls.cnt, src);
+    const int bc = __shfl_sync(0xffffffffu, ls.count(), src);
     int kept;
     const float tnew = warp_compact(b, bc, kp, keep_max, lane, &kept);
     if (lane == src) {
-      ls.thr = tnew;
-      ls.cnt = kept;
+      ls.thr = fmaxf(ls.thr, tnew);  // a level may already have raised it above the list's cut
+      ls.wp = ls.buf + kept;
     }
   }
 }
 
-// lvl_r-th largest score of a thread's own list (thread-private walk; lists are L2 resident).
-// Returns -inf when the list is shorter than r.  r <= 8.
-__device__ __forceinline__ float own_rth_best(const uint2* __restrict__ buf, int cnt, int r) {
-  float t[8];
+// ---- register tracker: the kTrack best scores a list has seen (sorted, t[0] best).  It starts
+// with kTrack - r entries of +inf, so t[kTrack-1] is always the r-th best REAL score (no dynamic
+// register indexing).  It may miss scores (it is fed the maximum of each 8-column group that
+// produced a candidate): the r-th best of a subset is still a valid lower bound of the r-th best
+// of the list.
+__device__ __forceinline__ void track_insert(float (&t)[kTrack], float v) {
+  if (v > t[kTrack - 1]) {
+    // t is sorted descending: new t[k] = min(t[k-1], max(v, t[k])) - every slot independently
+    float nt[kTrack];
+    nt[0] = fmaxf(v, t[0]);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) t[i] = -CUDART_INF_F;
-  for (int i = 0; i < cnt; ++i) {
-    const float v = __uint_as_float(__ldcg(buf + i).x);
-    if (v > t[7]) {
-      t[7] = v;
+    for (int k = 1; k < kTrack; ++k) nt[k] = fminf(t[k - 1], fmaxf(v, t[k]));
 #pragma unroll
-      for (int k = 7; k > 0; --k) {
-        const float hi = fmaxf(t[k - 1], t[k]), lo = fminf(t[k - 1], t[k]);
-        t[k - 1] = hi;
-        t[k] = lo;
+    for (int k = 0; k < kTrack; ++k) t[k] = nt[k];
+  }
+}
+
+// Cross-list level: min over the lists of the published r-th best, for the
+// `nlive` queries q0.. of this warp (query q0 + lane gets its value).  lvl is query-major
+// [nq][lists]: the warp reads one query's levels with coalesced loads, 16 queries in flight.
+__device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int lists, int q0, int nlive, int lane) {
+  uint32_t mine = kLvlNone;
+  for (int b = 0; b < nlive; b += 16) {  // warp-uniform
+    uint32_t lo[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) lo[u] = kLvlSkip;
+    for (int s = lane; s < lists; s += 32) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (b + u < nlive) lo[u] = min(lo[u], __ldcg(p.lvl + static_cast<size_t>(q0 + b + u) * lists + s));
+    }
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const uint32_t v = __reduce_min_sync(0xffffffffu, lo[u]);
+      if (lane == b + u) mine = v;
+    }
+  }
+  return (mine != kLvlNone && mine != kLvlSkip) ? __uint_as_float(key_to_float_bits(mine)) : -CUDART_INF_F;
+}
+
+__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// One 32-column chunk of the accumulator: per 8-column group a max tree against the threshold;
+// a group with a survivor appends its survivors to the list and feeds the tracker.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& ls, float (&tk)[kTrack],
+                                           int base_row) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+    const float m = fmax3(fmax3(v[0], v[1], v[2]), fmax3(v[3], v[4], v[5]), fmaxf(v[6], v[7]));
+    if (m > ls.thr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (v[j] > ls.thr) {
+          __stcg(ls.wp, make_uint2(r[g * 8 + j], static_cast<uint32_t>(base_row + g * 8 + j)));
+          ++ls.wp;
+        }
       }
+      track_insert(tk, m);
     }
   }
-  float out = t[0];
-#pragma unroll
-  for (int i = 1; i < 8; ++i) out = (r - 1 == i) ? t[i] : out;
-  return out;
 }
 
-// Cross-slice level: every slice publishes the r-th best score it has seen;
-// with slices * r >= kp, at least kp corpus rows score >= the minimum of the published values, so
-// no row below that minimum can be among the query's best kp - whichever slice it lives in.
-__device__ __forceinline__ void publish_level(const ScanParams& p, int slice, int q, const ListState& ls) {
-  const float v = own_rth_best(ls.buf, ls.cnt, p.lvl_r);
-  if (v > -CUDART_INF_F) __stcg(p.lvl + static_cast<size_t>(slice) * p.nq + q, float_to_key(__float_as_uint(v)));
-}
-__device__ __forceinline__ void refresh_level(const ScanParams& p, int q, ListState& ls) {
-  uint32_t lo = 0xFFFFFFFFu;
-  for (int s = 0; s < p.slices; ++s) lo = min(lo, __ldcg(p.lvl + static_cast<size_t>(s) * p.nq + q));
-  if (lo != 0u) ls.thr = fmaxf(ls.thr, __uint_as_float(key_to_float_bits(lo)));
-}
-
-// Cold path of the epilogue: (re)load one 32-column chunk of the accumulator from TMEM and append
-// the scores above the thread's threshold to its list.  Lists are compacted once per tile, AFTER
-// the accumulator has been handed back to the MMA warp, so a compaction overlaps the next MMAs.
-__device__ __noinline__ void append_chunk(uint32_t taddr, ListState& ls, int base_row, int valid,
-                                          float* __restrict__ dbg_row) {
+// Cold variant (last, partial tile of the corpus; debug dump): columns >= valid are TMA zero fill.
+__device__ __forceinline__ void scan_chunk_careful(uint32_t taddr, ListState& ls, float (&tk)[kTrack], int base_row,
+                                                int valid, float* __restrict__ dbg_row) {
   uint32_t r[32];
   ptx::tmem_ld_32x32b_x32(taddr, r);
   ptx::tc_wait_ld();
-  if (dbg_row != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (j < valid) dbg_row[base_row + j] = __uint_as_float(r[j]);
-  }
-  const float thr = ls.thr;
-  int cnt = ls.cnt;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    if (j < valid && __uint_as_float(r[j]) > thr) {
-      __stcg(ls.buf + cnt, make_uint2(r[j], static_cast<uint32_t>(base_row + j)));
-      ++cnt;
+    if (j < valid) {
+      if (dbg_row != nullptr) dbg_row[base_row + j] = __uint_as_float(r[j]);
+    } else {
+      r[j] = 0xFF800000u;  // -inf
     }
   }
-  ls.cnt = cnt;
+  scan_chunk(r, ls, tk, base_row);
 }
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
@@ -309,10 +370,13 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr int kStageBytesT = kPair ? kStageBytes / 2 : kStageBytes;
   constexpr int kKcPerStage = kStageBytesT / kBoxBytes;  // k-chunks (boxes) per pipeline stage
   constexpr int kStages = kStageRing / kStageBytesT;
-  constexpr int kChunksPerTile = N_T / 32;
+  constexpr int kGroupCols = N_T / 2;          // accumulator columns (corpus rows) per epilogue group
+  constexpr int kGroupChunks = kGroupCols / 32;
   constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, N_T);
-  constexpr uint32_t kArrivals = (kPair ? 2 : 1) * (kEpiThreads / 32);  // one arrival per epilogue warp
+  constexpr uint32_t kAccArrivals = (kPair ? 2 : 1) * kEpiWarps;  // one arrival per epilogue warp
+  constexpr uint32_t kAArrivals = (kPair ? 2 : 1) * kEpiWarps;    // every epilogue warp stores part of A
+  constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -321,6 +385,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t a_ready_bar;
   __shared__ uint32_t tmem_base_holder;
+  __shared__ float thr_sh[kQueryBlock];  // per query: the latest cross-list level either group fetched
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -336,19 +401,20 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   const int tile_end = min(p.num_tiles, tile_begin + p.tiles_per_slice);
   const int my_tiles = max(0, tile_end - tile_begin);
 
-  if (warp == 5 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
-      ptx::mbar_init(&tmem_empty_bar[a], kArrivals);
+      ptx::mbar_init(&tmem_empty_bar[a], kAccArrivals);
     }
-    ptx::mbar_init(&a_ready_bar, kArrivals);
+    ptx::mbar_init(&a_ready_bar, kAArrivals);
     ptx::fence_barrier_init();
   }
-  if (warp == 4) {
+  if (threadIdx.x < kQueryBlock) thr_sh[threadIdx.x] = -CUDART_INF_F;
+  if (warp == kTmaWarp) {
     if (lane == 0) ptx::prefetch_tensormap(&tmap);
     if constexpr (kPair) {
       ptx::tmem_alloc_pair(&tmem_base_holder, 512);
@@ -363,7 +429,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     // ------------------------------------------------------------ TMA producer
     // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
     // Pair mode: both CTAs load their half of the tile; the bytes of both halves are counted on
@@ -396,7 +462,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     // -------------------------------------------------------------- MMA issuer
     if (rank == 0) {
       ptx::mbar_wait(&a_ready_bar, 0);
@@ -450,51 +516,30 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       }
     }
   } else {
-    // ------------------------------------------- epilogue warps: one query per thread
-    const int t = threadIdx.x;  // TMEM lane
+    // ------ epilogue warps: group g scans columns [g*N_T/2, (g+1)*N_T/2) of every accumulator tile,
+    // one query per thread
+    const int grp = warp >> 2;
+    const int t = threadIdx.x & (kQueryBlock - 1);  // TMEM lane == query of the block
     const int q = qblock * kQueryBlock + t;
     const bool live = q < p.nq;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    const int d = p.d;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
 
-    // ---- fused normalize_L2 (FAISS fvec_renorm_L2: nr = ||x||^2; if nr > 0: x *= 1/sqrt(nr))
-    float inv = 1.0f, sq = 1.0f, nrm = 0.0f;
-    const float* xr = p.x + static_cast<size_t>(live ? q : 0) * d;
-    if (live) {
-      if (p.normalize) inv = inv_norm(row_norm_sq(xr, d));
-      float amax = 0.0f;
-      double n2 = 0;
-      for (int j = 0; j < d; ++j) {
-        const float v = __ldg(xr + j) * inv;
-        amax = fmaxf(amax, fabsf(v));
-        n2 = fma(static_cast<double>(v), static_cast<double>(v), n2);
-      }
-      nrm = static_cast<float>(sqrt(n2)) * 1.0000002f;  // rounded up: used only in the error bound
-      // power-of-two scale so that max|x| lands in [1,2): exact, keeps fp16 out of the subnormals
-      if (amax > 0.0f && amax < CUDART_INF_F) sq = ldexpf(1.0f, -ilogbf(amax));
-      if (slice == 0) {
-        p.qscale[q] = sq;
-        p.qnorm[q] = nrm;
-      }
-    }
-    for (int kc = 0; kc < p.num_kc; ++kc) {
-      uint32_t r[32];
+    // ---- A operand: this thread's prepared fp16 query row -> tensor memory (lane t, d/2 columns);
+    // the 128-byte k-chunks of the row are split between the two groups
+    {
+      const uint4* xrow = reinterpret_cast<const uint4*>(p.xh + static_cast<size_t>(q) * p.dpad);
+      for (int kc = grp; kc < p.num_kc; kc += 2) {
+        uint32_t r[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int i0 = kc * kKC + 2 * j;
-        float v0 = 0.0f, v1 = 0.0f;
-        if (live) {
-          if (i0 < d) v0 = __ldg(xr + i0) * inv;
-          if (i0 + 1 < d) v1 = __ldg(xr + i0 + 1) * inv;
-          if (slice == 0) {
-            if (i0 < d) p.xn[static_cast<size_t>(q) * d + i0] = v0;
-            if (i0 + 1 < d) p.xn[static_cast<size_t>(q) * d + i0 + 1] = v1;
-          }
+        for (int u = 0; u < 8; ++u) {
+          const uint4 v = __ldg(xrow + kc * 8 + u);
+          r[4 * u] = v.x;
+          r[4 * u + 1] = v.y;
+          r[4 * u + 2] = v.z;
+          r[4 * u + 3] = v.w;
         }
-        const __half2 h = __floats2half2_rn(v0 * sq, v1 * sq);  // .x (low half) = even k
-        r[j] = *reinterpret_cast<const uint32_t*>(&h);
+        ptx::tmem_st_32x32b_x32(tmem_base + lane_base + kACol0 + kc * 32, r);
       }
-      ptx::tmem_st_32x32b_x32(tmem_base + lane_base + kACol0 + kc * 32, r);
     }
     ptx::tc_wait_st();
     ptx::tc_fence_before();
@@ -504,38 +549,59 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
 
     // ---- threshold scan
-    const size_t list = static_cast<size_t>(slice) * p.nq + (live ? q : 0);
+    const int lists = p.slices * 2;
+    const int list_id = slice * 2 + grp;
+    const size_t list = static_cast<size_t>(list_id) * p.nq + (live ? q : 0);
     ListState ls;
     ls.buf = p.cand + list * p.cap;
+    ls.wp = ls.buf;
     ls.thr = live ? -CUDART_INF_F : CUDART_INF_F;
-    ls.cnt = 0;
-    const int kp = p.kp, cap = p.cap, keep_max = p.keep_max, n = p.n;
+    float tk[kTrack];
+#pragma unroll
+    for (int i = 0; i < kTrack; ++i) tk[i] = (i < kTrack - p.lvl_r) ? CUDART_INF_F : -CUDART_INF_F;
+    float published = -CUDART_INF_F;
+    const int kp = p.kp, cap = p.cap, keep_max = p.keep_max, n = p.n, lvl_r = p.lvl_r;
     float* dbg_row = (p.dbg_scores != nullptr && live) ? p.dbg_scores + static_cast<size_t>(q) * n : nullptr;
     const bool dbg = p.dbg_scores != nullptr;
+    uint32_t* lvl_mine = nullptr;  // where this list publishes its level (query-major [nq][lists])
+    const int wq0 = qblock * kQueryBlock + (warp & 3) * 32;   // first query of this warp
+    const int wlive = max(0, min(32, p.nq - wq0));            // live queries of this warp
+    if (lvl_r > 0 && live) {
+      // rows this list will see (only the last tile of the corpus can be partial): a list too short
+      // to feed its tracker kTrack group maxima never publishes a level and is not counted
+      long long rows = static_cast<long long>(my_tiles) * kGroupCols;
+      if (my_tiles > 0 && tile_end == p.num_tiles) {
+        const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupCols;
+        const long long valid = max(0ll, min(static_cast<long long>(kGroupCols), static_cast<long long>(n) - first));
+        rows -= kGroupCols - valid;
+      }
+      uint32_t* slot = p.lvl + static_cast<size_t>(q) * lists + list_id;
+      if (rows >= kTrack * 8) lvl_mine = slot; else __stcg(slot, kLvlSkip);
+    }
 
+    int refreshes = 0;
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
       ptx::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
       ptx::tc_fence_after();
-      const int row0 = (tile_begin + it) * N_T;
-      const uint32_t tile_addr = tmem_base + lane_base + acc * N_T;
-      // software pipeline over the tile's 32-column chunks: chunk c+1 is in flight while c is compared
-      uint32_t r[2][32];
-      ptx::tmem_ld_32x32b_x32(tile_addr, r[0]);
+      if (lvl_r > 0) ls.thr = fmaxf(ls.thr, thr_sh[t]);  // the other group may have refreshed it
+      const int row0 = (tile_begin + it) * N_T + grp * kGroupCols;
+      const uint32_t tile_addr = tmem_base + lane_base + acc * N_T + grp * kGroupCols;
+      if (dbg || row0 + kGroupCols > n) {  // warp-uniform
+#pragma unroll 1
+        for (int c = 0; c < kGroupChunks; ++c) {
+          const int base_row = row0 + c * 32;
+          if (base_row < n) scan_chunk_careful(tile_addr + c * 32, ls, tk, base_row, min(32, n - base_row), dbg_row);
+        }
+      } else {
+        // software pipeline over the group's 32-column chunks: chunk c+1 is in flight while c is compared
+        uint32_t r[2][32];
+        ptx::tmem_ld_32x32b_x32(tile_addr, r[0]);
 #pragma unroll
-      for (int c = 0; c < kChunksPerTile; ++c) {
-        ptx::tc_wait_ld();
-        if (c + 1 < kChunksPerTile) ptx::tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, r[(c + 1) & 1]);
-        const int base_row = row0 + c * 32;
-        if (base_row < n) {  // warp-uniform: otherwise the chunk is TMA zero fill only
-          const int valid = min(32, n - base_row);
-          bool hit = false;
-#pragma unroll
-          for (int j = 0; j < 32; ++j) hit |= (__uint_as_float(r[c & 1][j]) > ls.thr);
-          if (valid < 32 || dbg || __any_sync(0xffffffffu, hit)) {
-            ptx::tc_wait_ld();  // settle the prefetched chunk before the call (registers may be saved)
-            append_chunk(tile_addr + c * 32, ls, base_row, valid, dbg_row);
-          }
+        for (int c = 0; c < kGroupChunks; ++c) {
+          ptx::tc_wait_ld();
+          if (c + 1 < kGroupChunks) ptx::tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, r[(c + 1) & 1]);
+          scan_chunk(r[c & 1], ls, tk, row0 + c * 32);
         }
       }
       ptx::tc_fence_before();
@@ -543,25 +609,40 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       if (lane == 0) {  // one arrival per warp (in pair mode the odd CTA's arrivals are remote)
         if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
       }
-      // a tile appends at most N_T entries per list: keep that much room for the next one
-      compact_full_lists(ls, cap - N_T, kp, keep_max, lane);
-      if (p.lvl_r > 0 && live) {
+      if (lvl_r > 0) {
+        if (lvl_mine != nullptr) {
+          const float lv = tk[kTrack - 1];
+          if (lv > published) {
+            published = lv;
+            __stcg(lvl_mine, float_to_key(__float_as_uint(lv)));
+          }
+        }
+        // the two groups take turns refreshing the block's thresholds (shared through thr_sh)
         const int done = it + 1;
-        if ((done & (done - 1)) == 0) publish_level(p, slice, q, ls);  // after tiles 1, 2, 4, 8, ...
-        if ((done & (done - 1)) == 0 || (done & 7) == 0) refresh_level(p, q, ls);
+        if (done <= 4 || (done <= 32 && (done & 3) == 0) || (done & 31) == 0) {
+          if ((refreshes++ & 1) == grp) {
+            const float lv = warp_refresh_level(p, lists, wq0, wlive, lane);
+            if (live && lv > ls.thr) {
+              ls.thr = lv;
+              thr_sh[t] = lv;
+            }
+          }
+        }
       }
+      // a tile appends at most N_T/2 entries per list: keep room for the next one
+      compact_full_lists(ls, cap - N_T, kp, keep_max, lane);
     }
-    // ---- final compaction to exactly the slice's top-kp
-    compact_full_lists(ls, kp, kp, kp, lane);
+    // ---- without a level the pass-2 merge expects at most kp entries per list
+    if (lvl_r == 0) compact_full_lists(ls, kp, kp, kp, lane);
     if (live) {
-      p.cand_count[list] = ls.cnt;
+      p.cand_count[list] = ls.count();
       p.slice_thr[list] = ls.thr;
     }
   }
 
   ptx::tc_fence_before();
   if constexpr (kPair) ptx::cluster_sync(); else __syncthreads();
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     ptx::tc_fence_after();
     if constexpr (kPair) ptx::tmem_dealloc_pair(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512);
   }

@@ -46,7 +46,7 @@ def make_inputs(batch: int, seq: int, vocab_size: int = 30522, seed: int = 0):
     """Synthetic token ids with ragged right padding (no tokenizer vocab exists offline)."""
     rng = np.random.default_rng(seed)
     ids = rng.integers(1000, vocab_size, size=(batch, seq)).astype(np.int32)
-    lens = rng.integers(max(2, seq // 4), seq + 1, size=batch)
+    lens = rng.integers(min(seq, max(2, seq // 4)), seq + 1, size=batch)
     lens[0] = seq
     mask = (np.arange(seq)[None, :] < lens[:, None]).astype(np.int32)
     ids[:, 0] = 101
