@@ -331,6 +331,7 @@ def main():
                     frac=round(hbm_frac, 4), traffic=None)
     roof.update(kernel="scan_topk_kernel", ms_per_launch=round(scan_ms, 4), peak_source=peaks["source"],
                 other_bound_frac=round(hbm_frac if roof["bound"] == "tensor" else tensor_frac, 4),
+                prep_ms_per_launch=round(tm.get("prep_ms", 0.0) / max(1, tm["calls"]), 4),
                 merge_ms_per_launch=round(tm["merge_ms"] / max(1, tm["calls"]), 4),
                 exact_ms_per_launch=round(tm["exact_ms"] / max(1, tm["calls"]), 4))
     traffic_file = ROOT / "profiles" / "traffic.json"
@@ -405,6 +406,8 @@ def extra_numbers(index, d, k, dev, peaks):
         index.set_timing(False)
         scan = tm["scan_ms"] / steps
         res[f"Q={q}"] = {"qps": round(q / (ms / 1e3), 1), "ms_per_step": round(ms, 4), "scan_ms": round(scan, 4),
+                         "prep_ms": round(tm.get("prep_ms", 0.0) / steps, 4), "merge_ms": round(tm["merge_ms"] / steps, 4),
+                         "exact_ms": round(tm["exact_ms"] / steps, 4),
                          "hbm_frac": round(n * d * 2 / (scan / 1e3) / 1e9 / peaks["hbm_gbs"], 4),
                          "tensor_frac": round(2.0 * q * n * d / (scan / 1e3) / 1e12 / peaks["tflops"], 4)}
     return res

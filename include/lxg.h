@@ -115,9 +115,10 @@ int lxg_index_last_stats(const lxg_index* index, lxg_search_stats* out);
  * lxg_index_get_timing synchronises them, returns the sums since the last get and resets. */
 typedef struct lxg_timing {
   int32_t calls;
-  float scan_ms;   /* pass 1: fused normalise + tcgen05 GEMM + threshold top-k' */
+  float scan_ms;   /* pass 1: TMA + tcgen05 GEMM + threshold top-k' (scan_topk_kernel alone) */
   float merge_ms;  /* pass 2: merge + exact re-score + certificate */
   float exact_ms;  /* exact collectors for uncertified queries */
+  float prep_ms;   /* query preparation: faiss.normalize_L2 + fp16 conversion (prep_queries_kernel) */
 } lxg_timing;
 int lxg_index_set_timing(lxg_index* index, int enable);
 int lxg_index_get_timing(lxg_index* index, lxg_timing* out);

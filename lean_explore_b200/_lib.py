@@ -37,7 +37,8 @@ class SearchStats(ctypes.Structure):
 
 
 class Timing(ctypes.Structure):
-    _fields_ = [("calls", c_int32), ("scan_ms", c_float), ("merge_ms", c_float), ("exact_ms", c_float)]
+    _fields_ = [("calls", c_int32), ("scan_ms", c_float), ("merge_ms", c_float), ("exact_ms", c_float),
+                ("prep_ms", c_float)]
 
 
 class BertLayer(ctypes.Structure):

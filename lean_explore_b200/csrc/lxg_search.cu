@@ -30,6 +30,7 @@ static bool g_inited = false;
 static int g_device = -1;
 static int g_num_sms = 0;
 static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
+static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
 static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -112,7 +113,7 @@ struct lxg_index {
   HostBuf h_stage;
   lxg_search_stats stats{};
   bool timing = false;
-  std::vector<cudaEvent_t> ev_pool;   // 4 events per timed call
+  std::vector<cudaEvent_t> ev_pool;   // 5 events per timed call
   size_t ev_used = 0;
 };
 
@@ -149,10 +150,13 @@ struct Plan {
   int max_items;  // pass-2 candidate pool (entries)
 };
 
-// Lists that see at least 8*kTrack rows (the others never publish a level, scan_topk.cuh): list
-// (slice, g) holds columns [g*N_T/2, (g+1)*N_T/2) of every tile of the slice.
-int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_per_slice) {
-  const int gc = tile_rows / 2;
+// Lists that see at least 8*kTrack rows (the others never publish a level, scan_topk.cuh).  List
+// (slice, g) holds, of every tile of the slice, the 32-row chunks c at tile row g*row0 + c*step
+// (the same constants as kGroupRow0 / kChunkRowStep of the kernel).
+int lists_with_level(int n, int tile_rows, bool pair, int num_tiles, int slices, int tiles_per_slice) {
+  const int gc = tile_rows / 2, chunks = gc / 32;
+  const bool split = false;  // kSplit of the kernel
+  const int row0 = (split && pair) ? 32 : gc, step = (split && pair) ? 64 : 32;
   int ok = 0;
   for (int s = 0; s < slices; ++s) {
     const int tb = s * tiles_per_slice;
@@ -161,9 +165,10 @@ int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_
     for (int g = 0; g < 2; ++g) {
       long long rows = static_cast<long long>(my) * gc;
       if (my > 0 && te == num_tiles) {
-        const long long first = static_cast<long long>(num_tiles - 1) * tile_rows + g * gc;
-        const long long valid = std::max(0ll, std::min(static_cast<long long>(gc), static_cast<long long>(n) - first));
-        rows -= gc - valid;
+        for (int c = 0; c < chunks; ++c) {
+          const long long first = static_cast<long long>(num_tiles - 1) * tile_rows + g * row0 + c * step;
+          rows -= 32 - std::max(0ll, std::min(32ll, static_cast<long long>(n) - first));
+        }
       }
       if (rows >= kTrack * 8) ++ok;
     }
@@ -189,7 +194,7 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
   };
   slice_up(std::max(1, g_num_sms / pl.grid_x));
   // cross-list level: needs lists * r >= kp with r <= kTrack
-  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice);
+  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.pair, pl.num_tiles, pl.slices, pl.tiles_per_slice);
   pl.lvl_r = lv >= 2 ? (pl.kp + lv - 1) / lv : 0;
   if (pl.lvl_r > kTrack) pl.lvl_r = 0;
   if (pl.lvl_r > 0) {
@@ -240,7 +245,7 @@ cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, c
 
 extern "C" {
 
-int lxg_abi_version(void) { return 1; }
+int lxg_abi_version(void) { return 2; }
 
 const char* lxg_last_error(void) { return g_last_error.c_str(); }
 
@@ -276,6 +281,8 @@ int lxg_init(int device) {
   g_force_single = fs && fs[0] == '1';
   const char* nl = std::getenv("LXG_SCAN_NOLEVEL");
   g_no_level = nl && nl[0] == '1';
+  const char* pm = std::getenv("LXG_SCAN_PERF_MODE");
+  g_perf_mode = pm ? std::atoi(pm) : 0;
   g_device = device;
   g_inited = true;
   return LXG_OK;
@@ -410,12 +417,14 @@ int lxg_index_get_timing(lxg_index* ix, lxg_timing* out) {
   if (!ix || !out) return set_error(LXG_EINVAL, "NULL argument");
   std::lock_guard<std::mutex> lock(ix->mu);
   *out = lxg_timing{};
-  for (size_t i = 0; i + 4 <= ix->ev_used; i += 4) {
-    LXG_CUDA(cudaEventSynchronize(ix->ev_pool[i + 3]));
-    float a = 0, b = 0, c = 0;
-    LXG_CUDA(cudaEventElapsedTime(&a, ix->ev_pool[i], ix->ev_pool[i + 1]));
-    LXG_CUDA(cudaEventElapsedTime(&b, ix->ev_pool[i + 1], ix->ev_pool[i + 2]));
-    LXG_CUDA(cudaEventElapsedTime(&c, ix->ev_pool[i + 2], ix->ev_pool[i + 3]));
+  for (size_t i = 0; i + 5 <= ix->ev_used; i += 5) {
+    LXG_CUDA(cudaEventSynchronize(ix->ev_pool[i + 4]));
+    float p = 0, a = 0, b = 0, c = 0;
+    LXG_CUDA(cudaEventElapsedTime(&p, ix->ev_pool[i], ix->ev_pool[i + 1]));
+    LXG_CUDA(cudaEventElapsedTime(&a, ix->ev_pool[i + 1], ix->ev_pool[i + 2]));
+    LXG_CUDA(cudaEventElapsedTime(&b, ix->ev_pool[i + 2], ix->ev_pool[i + 3]));
+    LXG_CUDA(cudaEventElapsedTime(&c, ix->ev_pool[i + 3], ix->ev_pool[i + 4]));
+    out->prep_ms += p;
     out->scan_ms += a;
     out->merge_ms += b;
     out->exact_ms += c;
@@ -490,26 +499,28 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.keep_max = pl.keep_max;
   sp.lvl = reinterpret_cast<uint32_t*>(sm + o_lvl);
   sp.lvl_r = pl.lvl_r;
+  sp.perf_mode = g_perf_mode;
   if (sp.lvl_r > 0) LXG_CUDA(cudaMemsetAsync(sp.lvl, 0, lists * sizeof(uint32_t), st));
 
   int launches = 0;
   cudaEvent_t* ev = nullptr;
   if (ix->timing && !dbg_scores) {
-    if (ix->ev_used + 4 > ix->ev_pool.size()) {
-      for (int i = 0; i < 4; ++i) {
+    if (ix->ev_used + 5 > ix->ev_pool.size()) {
+      for (int i = 0; i < 5; ++i) {
         cudaEvent_t e;
         LXG_CUDA(cudaEventCreate(&e));
         ix->ev_pool.push_back(e);
       }
     }
     ev = &ix->ev_pool[ix->ev_used];
-    ix->ev_used += 4;
+    ix->ev_used += 5;
   }
   LXG_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
   prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize);
   LXG_CUDA(cudaGetLastError());
   ++launches;
+  if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
   if (ix->tile_rows == 128) {
     if (pl.pair) LXG_CUDA((launch_scan<128, true>(ix, sp, pl.grid_x, st)));
     else LXG_CUDA((launch_scan<128, false>(ix, sp, pl.grid_x, st)));
@@ -518,13 +529,17 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
     else LXG_CUDA((launch_scan<64, false>(ix, sp, pl.grid_x, st)));
   }
   ++launches;
-  if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
+  if (ev) LXG_CUDA(cudaEventRecord(ev[2], st));
   ix->stats.slices = pl.slices;
   ix->stats.query_blocks = pl.qblocks;
   ix->stats.kp = pl.kp;
   ix->stats.tile_rows = ix->tile_rows;
   ix->stats.uncertified = -1;
-  if (dbg_scores) {
+  if (dbg_scores || g_perf_mode) {  // perf mode: pass 1 only, results are not produced
+    if (ev) {
+      LXG_CUDA(cudaEventRecord(ev[3], st));
+      LXG_CUDA(cudaEventRecord(ev[4], st));
+    }
     ix->stats.kernel_launches = launches;
     return LXG_OK;
   }
@@ -560,7 +575,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   merge_rescore_kernel<<<nq, kMergeThreads, msmem, st>>>(mp, ix->cv);
   LXG_CUDA(cudaGetLastError());
   ++launches;
-  if (ev) LXG_CUDA(cudaEventRecord(ev[2], st));
+  if (ev) LXG_CUDA(cudaEventRecord(ev[3], st));
 
   // exact path for uncertified queries (normally zero of them: both kernels exit at once)
   const int nflag_max = std::min(nq, 256);
@@ -588,7 +603,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   exact_finalize_kernel<<<nflag_max, 256, 0, st>>>(ep, ix->cv);
   LXG_CUDA(cudaGetLastError());
   launches += 2;
-  if (ev) LXG_CUDA(cudaEventRecord(ev[3], st));
+  if (ev) LXG_CUDA(cudaEventRecord(ev[4], st));
   ix->stats.kernel_launches = launches;
 
   if (read_flags) {

@@ -53,6 +53,7 @@ struct ScanParams {
   int n;
   int num_tiles, slices, tiles_per_slice;
   int kp, cap, keep_max;
+  int perf_mode;      // measurements only (LXG_SCAN_PERF_MODE): 1 = epilogue releases tiles unread, 2 = no candidate ever passes, 3 = TMEM reads only
 };
 
 __device__ __forceinline__ uint32_t float_to_key(uint32_t b) {
@@ -280,15 +281,21 @@ __device__ __forceinline__ void compact_full_lists(ListState& ls, int limit, int
 // register indexing).  It may miss scores (it is fed the maximum of each 8-column group that
 // produced a candidate): the r-th best of a subset is still a valid lower bound of the r-th best
 // of the list.
-__device__ __forceinline__ void track_insert(float (&t)[kTrack], float v) {
+__device__ __forceinline__ void track_insert(float (&t)[kTrack], float v, bool two_slots) {
   if (v > t[kTrack - 1]) {
     // t is sorted descending: new t[k] = min(t[k-1], max(v, t[k])) - every slot independently
-    float nt[kTrack];
-    nt[0] = fmaxf(v, t[0]);
+    if (two_slots) {  // r <= 2 (warp-uniform): the other slots hold the +inf sentinels
+      const float hi = fmaxf(v, t[kTrack - 2]);
+      t[kTrack - 1] = fminf(t[kTrack - 2], fmaxf(v, t[kTrack - 1]));
+      t[kTrack - 2] = hi;
+    } else {
+      float nt[kTrack];
+      nt[0] = fmaxf(v, t[0]);
 #pragma unroll
-    for (int k = 1; k < kTrack; ++k) nt[k] = fminf(t[k - 1], fmaxf(v, t[k]));
+      for (int k = 1; k < kTrack; ++k) nt[k] = fminf(t[k - 1], fmaxf(v, t[k]));
 #pragma unroll
-    for (int k = 0; k < kTrack; ++k) t[k] = nt[k];
+      for (int k = 0; k < kTrack; ++k) t[k] = nt[k];
+    }
   }
 }
 
@@ -320,7 +327,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 // One 32-column chunk of the accumulator: per 8-column group a max tree against the threshold;
 // a group with a survivor appends its survivors to the list and feeds the tracker.
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& ls, float (&tk)[kTrack],
-                                           int base_row) {
+                                           int base_row, bool two_slots) {
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float v[8];
@@ -335,14 +342,14 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& l
           ++ls.wp;
         }
       }
-      track_insert(tk, m);
+      track_insert(tk, m, two_slots);
     }
   }
 }
 
 // Cold variant (last, partial tile of the corpus; debug dump): columns >= valid are TMA zero fill.
 __device__ __forceinline__ void scan_chunk_careful(uint32_t taddr, ListState& ls, float (&tk)[kTrack], int base_row,
-                                                int valid, float* __restrict__ dbg_row) {
+                                                int valid, float* __restrict__ dbg_row, bool two_slots) {
   uint32_t r[32];
   ptx::tmem_ld_32x32b_x32(taddr, r);
   ptx::tc_wait_ld();
@@ -354,7 +361,7 @@ __device__ __forceinline__ void scan_chunk_careful(uint32_t taddr, ListState& ls
       r[j] = 0xFF800000u;  // -inf
     }
   }
-  scan_chunk(r, ls, tk, base_row);
+  scan_chunk(r, ls, tk, base_row, two_slots);
 }
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
@@ -370,19 +377,33 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr int kStageBytesT = kPair ? kStageBytes / 2 : kStageBytes;
   constexpr int kKcPerStage = kStageBytesT / kBoxBytes;  // k-chunks (boxes) per pipeline stage
   constexpr int kStages = kStageRing / kStageBytesT;
+  // kSplit: every tile is computed as two N = N_T/2 halves with their own full/empty barriers,
+  // half g drained by epilogue group g alone (a slow group then never stalls the other one).
+  // Measured on B200 (cfg2, N_T = 128): N = 64 MMAs with A in tensor memory run at ~2/3 of the
+  // N = 128 rate (0.331 vs 0.270 ms for the bare TMA/MMA pipeline), which costs more than the
+  // decoupling gains - so it stays off; the code path is kept for the A/B.
+  constexpr bool kSplit = false;
   constexpr int kGroupCols = N_T / 2;          // accumulator columns (corpus rows) per epilogue group
   constexpr int kGroupChunks = kGroupCols / 32;
+  // Corpus rows behind the columns of group g, chunk c: tile row g * kGroupRow0 + c * kChunkRowStep + j.
+  // An N = 64 half of a CTA pair takes 32 rows from each CTA's box (columns 0-31 | 32-63), so the
+  // two chunks of a group are 64 tile rows apart.
+  constexpr int kGroupRow0 = (kSplit && kPair) ? 32 : kGroupCols;
+  constexpr int kChunkRowStep = (kSplit && kPair) ? 64 : 32;
   constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
-  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, N_T);
-  constexpr uint32_t kAccArrivals = (kPair ? 2 : 1) * kEpiWarps;  // one arrival per epilogue warp
+  constexpr int kMmaN = kSplit ? N_T / 2 : N_T;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, kMmaN);
+  constexpr uint32_t kHalfDesc = (kBoxRows / 2) * 128 >> 4;  // descriptor step to the B rows of half 1
+  // arrivals that free an accumulator (half): one per epilogue warp that reads it
+  constexpr uint32_t kAccArrivals = (kPair ? 2 : 1) * (kSplit ? kEpiWarps / 2 : kEpiWarps);
   constexpr uint32_t kAArrivals = (kPair ? 2 : 1) * kEpiWarps;    // every epilogue warp stores part of A
   constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar[2];
-  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ __align__(8) uint64_t tmem_full_bar[4];   // [accumulator * 2 + half]
+  __shared__ __align__(8) uint64_t tmem_empty_bar[4];
   __shared__ __align__(8) uint64_t a_ready_bar;
   __shared__ uint32_t tmem_base_holder;
   __shared__ float thr_sh[kQueryBlock];  // per query: the latest cross-list level either group fetched
@@ -406,7 +427,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < 4; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], kAccArrivals);
     }
@@ -431,86 +452,111 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
 
   if (warp == kTmaWarp) {
     // ------------------------------------------------------------ TMA producer
-    // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
     // Pair mode: both CTAs load their half of the tile; the bytes of both halves are counted on
     // the even CTA's full barrier (it issues the MMAs), which therefore expects 2x the bytes.
-    uint32_t stage = 0, phase = 0;
-    for (int t = tile_begin; t < tile_end; ++t) {
-      const int row = t * N_T + static_cast<int>(rank) * kBoxRows;
-      for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
-        const int nb = min(kKcPerStage, p.num_kc - kc0);
-        ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-        if (ptx::elect_one()) {
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], nb * kBoxBytes * (kPair ? 2 : 1));
-          uint8_t* dst = ring + stage * kStageBytesT;
-#pragma unroll
-          for (int b = 0; b < kKcPerStage; ++b) {
-            if (b < nb) {
-              if constexpr (kPair)
-                ptx::tma_load_2d_pair(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, row, &full_bar[stage],
-                                      ptx::kEvictNormal);
-              else
-                ptx::tma_load_2d(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, row, &full_bar[stage],
-                                 ptx::kEvictNormal);
-            }
-          }
-        }
-        __syncwarp();
-        if (++stage == kStages) {
-          stage = 0;
-          phase ^= 1u;
-        }
-      }
-    }
-  } else if (warp == kMmaWarp) {
-    // -------------------------------------------------------------- MMA issuer
-    if (rank == 0) {
-      ptx::mbar_wait(&a_ready_bar, 0);
-      ptx::tc_fence_after();
+    // The whole warp walks the loop (warp-uniform control flow); one elected lane issues.
+    {
+      const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
+      const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
+      const uint32_t ring0 = ptx::opaque(ring_u32);
       uint32_t stage = 0, phase = 0;
-      for (int it = 0; it < my_tiles; ++it) {
-        const uint32_t acc = it & 1;
-        ptx::mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1u);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * N_T;
+      for (int t = tile_begin; t < tile_end; ++t) {
+        const int row = t * N_T + static_cast<int>(rank) * kBoxRows;
         for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
           const int nb = min(kKcPerStage, p.num_kc - kc0);
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
+          ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
           if (ptx::elect_one()) {
-            const uint32_t stage_addr = ring_u32 + stage * kStageBytesT;
+            const uint32_t fb = full0 + stage * 8;
+            if (rank == 0) ptx::mbar_arrive_expect_tx_a(fb, nb * kBoxBytes * (kPair ? 2 : 1));
+            const uint32_t dst = ring0 + stage * kStageBytesT;
 #pragma unroll
             for (int b = 0; b < kKcPerStage; ++b) {
               if (b < nb) {
-                const uint64_t bdesc = ptx::make_kmajor_sw128_desc(stage_addr + b * kBoxBytes);
-                const uint32_t a_tmem = tmem_base + kACol0 + (kc0 + b) * 32;
-#pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
-                  // 8 TMEM columns in A.
-                  const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
-                  if constexpr (kPair)
-                    ptx::mma_f16_ts_pair(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc,
-                                         accum);
-                  else
-                    ptx::mma_f16_ts(d_tmem, a_tmem + k4 * 8, bdesc + static_cast<uint64_t>(k4 * 2), kIdesc, accum);
-                }
+                if constexpr (kPair)
+                  ptx::tma_load_2d_pair_a(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, row, fb, ptx::kEvictNormal);
+                else
+                  ptx::tma_load_2d_a(dst + b * kBoxBytes, &tmap, (kc0 + b) * kKC, row, fb, ptx::kEvictNormal);
               }
-            }
-            // stage reusable (in both CTAs) once these MMAs retire
-            const bool last = kc0 + kKcPerStage >= p.num_kc;
-            if constexpr (kPair) {
-              ptx::tc_commit_pair(&empty_bar[stage], 3);
-              if (last) ptx::tc_commit_pair(&tmem_full_bar[acc], 3);
-            } else {
-              ptx::tc_commit(&empty_bar[stage]);
-              if (last) ptx::tc_commit(&tmem_full_bar[acc]);
             }
           }
           __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // -------------------------------------------------------------- MMA issuer
+    // (warp-uniform loop, one elected lane issues: in divergent code every tcgen05 instruction
+    // would be wrapped in its own elect loop)
+    if (rank == 0) {
+      ptx::mbar_wait(&a_ready_bar, 0);
+      ptx::tc_fence_after();
+      const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
+      const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
+      const uint32_t tfull0 = ptx::opaque(ptx::smem_u32(&tmem_full_bar[0]));
+      const uint32_t tempty0 = ptx::opaque(ptx::smem_u32(&tmem_empty_bar[0]));
+      // shared-memory matrix descriptor of (stage 0, box 0, k step 0); see make_kmajor_sw128_desc
+      const uint32_t desc_lo0 = ptx::opaque(((ring_u32 & 0x3FFFFu) >> 4) | (1u << 16));
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t a_tmem0 = ptx::opaque(tmem_base + kACol0);
+      uint32_t stage = 0, phase = 0;
+      for (int it = 0; it < my_tiles; ++it) {
+        const uint32_t acc = it & 1;
+        const uint32_t stage_t = stage, phase_t = phase;  // first pipeline stage of this tile
+#pragma unroll
+        for (int half = 0; half < (kSplit ? 2 : 1); ++half) {
+          // half 1 walks the same stages again (they stay full until its MMAs retire)
+          stage = stage_t;
+          phase = phase_t;
+          const uint32_t hb = (acc * 2 + half) * 8;
+          ptx::mbar_wait_a(tempty0 + hb, ((it >> 1) & 1) ^ 1u);
+          ptx::tc_fence_after();
+          const uint32_t d_tmem = tmem_base + acc * N_T + half * kMmaN;
+          const bool release = !kSplit || half == 1;
+          for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
+            const int nb = min(kKcPerStage, p.num_kc - kc0);
+            if (half == 0) {
+              ptx::mbar_wait_a(full0 + stage * 8, phase);
+              ptx::tc_fence_after();
+            }
+            if (ptx::elect_one()) {
+              const uint32_t lo = desc_lo0 + stage * (kStageBytesT >> 4) + half * kHalfDesc;
+              const uint32_t a_kc = a_tmem0 + kc0 * 32;
+#pragma unroll
+              for (int b = 0; b < kKcPerStage; ++b) {
+                if (b < nb) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
+                    // 8 TMEM columns in A.
+                    const uint64_t bdesc =
+                        (static_cast<uint64_t>(kDescHi) << 32) | (lo + b * (kBoxBytes >> 4) + k4 * 2);
+                    const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
+                    if constexpr (kPair)
+                      ptx::mma_f16_ts_pair(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
+                    else
+                      ptx::mma_f16_ts(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
+                  }
+                }
+              }
+              // stage reusable (in both CTAs) once the MMAs of its last reader retire
+              const bool last = kc0 + kKcPerStage >= p.num_kc;
+              if constexpr (kPair) {
+                if (release) ptx::tc_commit_pair_a(empty0 + stage * 8, 3);
+                if (last) ptx::tc_commit_pair_a(tfull0 + hb, 3);
+              } else {
+                if (release) ptx::tc_commit_a(empty0 + stage * 8);
+                if (last) ptx::tc_commit_a(tfull0 + hb);
+              }
+            }
+            __syncwarp();
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1u;
+            }
           }
         }
       }
@@ -555,11 +601,12 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     ListState ls;
     ls.buf = p.cand + list * p.cap;
     ls.wp = ls.buf;
-    ls.thr = live ? -CUDART_INF_F : CUDART_INF_F;
+    ls.thr = (live && p.perf_mode != 2) ? -CUDART_INF_F : CUDART_INF_F;
     float tk[kTrack];
 #pragma unroll
     for (int i = 0; i < kTrack; ++i) tk[i] = (i < kTrack - p.lvl_r) ? CUDART_INF_F : -CUDART_INF_F;
     float published = -CUDART_INF_F;
+    const bool two_slots = p.lvl_r <= 2;
     const int kp = p.kp, cap = p.cap, keep_max = p.keep_max, n = p.n, lvl_r = p.lvl_r;
     float* dbg_row = (p.dbg_scores != nullptr && live) ? p.dbg_scores + static_cast<size_t>(q) * n : nullptr;
     const bool dbg = p.dbg_scores != nullptr;
@@ -571,27 +618,31 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       // to feed its tracker kTrack group maxima never publishes a level and is not counted
       long long rows = static_cast<long long>(my_tiles) * kGroupCols;
       if (my_tiles > 0 && tile_end == p.num_tiles) {
-        const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupCols;
-        const long long valid = max(0ll, min(static_cast<long long>(kGroupCols), static_cast<long long>(n) - first));
-        rows -= kGroupCols - valid;
+        for (int c = 0; c < kGroupChunks; ++c) {
+          const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupRow0 + c * kChunkRowStep;
+          rows -= 32 - max(0ll, min(32ll, static_cast<long long>(n) - first));
+        }
       }
       uint32_t* slot = p.lvl + static_cast<size_t>(q) * lists + list_id;
       if (rows >= kTrack * 8) lvl_mine = slot; else __stcg(slot, kLvlSkip);
     }
 
     int refreshes = 0;
+    const uint32_t tfull0 = ptx::opaque(ptx::smem_u32(&tmem_full_bar[0]));
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
-      ptx::mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      const uint32_t hb = (acc * 2 + (kSplit ? grp : 0)) * 8;  // barrier of the accumulator (half) this group reads
+      ptx::mbar_wait_a(tfull0 + hb, (it >> 1) & 1);
       ptx::tc_fence_after();
       if (lvl_r > 0) ls.thr = fmaxf(ls.thr, thr_sh[t]);  // the other group may have refreshed it
-      const int row0 = (tile_begin + it) * N_T + grp * kGroupCols;
+      const int row0 = (tile_begin + it) * N_T + grp * kGroupRow0;  // corpus row of the group's chunk 0, column 0
       const uint32_t tile_addr = tmem_base + lane_base + acc * N_T + grp * kGroupCols;
-      if (dbg || row0 + kGroupCols > n) {  // warp-uniform
+      if (p.perf_mode == 1) {
+      } else if (dbg || (tile_begin + it + 1) * N_T > n) {  // warp-uniform
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {
-          const int base_row = row0 + c * 32;
-          if (base_row < n) scan_chunk_careful(tile_addr + c * 32, ls, tk, base_row, min(32, n - base_row), dbg_row);
+          const int base_row = row0 + c * kChunkRowStep;
+          if (base_row < n) scan_chunk_careful(tile_addr + c * 32, ls, tk, base_row, min(32, n - base_row), dbg_row, two_slots);
         }
       } else {
         // software pipeline over the group's 32-column chunks: chunk c+1 is in flight while c is compared
@@ -601,13 +652,17 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         for (int c = 0; c < kGroupChunks; ++c) {
           ptx::tc_wait_ld();
           if (c + 1 < kGroupChunks) ptx::tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, r[(c + 1) & 1]);
-          scan_chunk(r[c & 1], ls, tk, row0 + c * 32);
+          if (p.perf_mode == 3) {  // measurements only: TMEM reads without the compare
+          } else {
+            scan_chunk(r[c & 1], ls, tk, row0 + c * kChunkRowStep, two_slots);
+          }
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // one arrival per warp (in pair mode the odd CTA's arrivals are remote)
-        if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
+        uint64_t* eb = &tmem_empty_bar[acc * 2 + (kSplit ? grp : 0)];
+        if constexpr (kPair) ptx::mbar_arrive_cluster(eb, 0); else ptx::mbar_arrive(eb);
       }
       if (lvl_r > 0) {
         if (lvl_mine != nullptr) {
