@@ -31,6 +31,13 @@ import threading
 import time
 from pathlib import Path
 
+# The reference arm times the CPU path "with all the host threads it can use": torchrun exports
+# OMP_NUM_THREADS=1 to every rank, which would silently make it a one-core baseline.  Must happen
+# before numpy (OpenBLAS) and the OpenMP oracle library are loaded.
+if "reference" in sys.argv[1:] or "--impl=reference" in sys.argv[1:]:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np
 
 ROOT = Path(__file__).resolve().parent
@@ -289,7 +296,7 @@ def main():
         # end to end through the public host API: numpy in, numpy out, copies inside the timing
         e2e = None
         if not sharded:
-            xh = [b.cpu().numpy() for b in batches]
+            xh = [b.cpu().pin_memory().numpy() for b in batches]  # pinned host inputs (bench contract)
             index.search(xh[0], k, normalize=True)
             barrier()
             t0 = time.perf_counter()
@@ -351,7 +358,8 @@ def main():
                    "l2_policy": "corpus (%.0f MB) larger than L2; 4 rotating query batches" % (n * d * 2 / 1e6)
                    if n * d * 2 > 126e6 else "inputs fit L2 (config as specified by BASELINE.json)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": q * d * 4,
-                "d2h_bytes_per_step": q * k * 12, "api": "GpuIndexFlatIP.search(numpy) -> lxg_search"},
+                "d2h_bytes_per_step": q * k * 12, "api": "GpuIndexFlatIP.search(numpy) -> lxg_search",
+                "host_buffers": "pinned"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "clocks": sampler.summary(),
@@ -373,6 +381,10 @@ def main():
 
     if rank == 0 and world == 1 and not args.no_extra and args.workload == "cfg2":
         out["extra"] = extra_numbers(index, d, k, dev, peaks)
+        try:
+            out["extra"]["encoder"] = encoder_numbers(dev, cpu=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001 - secondary numbers must not lose the headline line
+            out["extra"]["encoder"] = {"error": repr(exc)}
 
     if world > 1:
         dist.barrier()
@@ -410,6 +422,73 @@ def extra_numbers(index, d, k, dev, peaks):
                          "exact_ms": round(tm["exact_ms"] / steps, 4),
                          "hbm_frac": round(n * d * 2 / (scan / 1e3) / 1e9 / peaks["hbm_gbs"], 4),
                          "tensor_frac": round(2.0 * q * n * d / (scan / 1e3) / 1e12 / peaks["tflops"], 4)}
+    return res
+
+
+def encoder_numbers(dev, cpu: bool):
+    """Row a2 of the hot path (SentenceTransformer.encode inside EmbeddingClient.embed): the
+    sentence-encoder forward on random-init weights of the real geometries (no checkpoints exist
+    offline), synthetic token ids.  Query path = one text per call (B=1); bulk path = the
+    reference's corpus-embedding batches.  CPU leg: HF BertModel fp32 on the host cores through
+    oracle/bert_encoder.py (what sentence-transformers runs), reference batch size 8."""
+    import torch
+    from transformers import BertConfig, BertModel
+
+    from lean_explore_b200.encoder import POOL_CLS, POOL_MEAN, BertSentenceEncoder
+
+    geoms = {"minilm-l6 (d=384)": (dict(hidden_size=384, num_hidden_layers=6, num_attention_heads=12,
+                                        intermediate_size=1536), POOL_MEAN, "mean"),
+             "bge-base (d=768)": (dict(hidden_size=768, num_hidden_layers=12, num_attention_heads=12,
+                                       intermediate_size=3072), POOL_CLS, "cls")}
+    res = {}
+    for name, (g, pool, pool_name) in geoms.items():
+        torch.manual_seed(0)
+        model = BertModel(BertConfig(vocab_size=30522, max_position_embeddings=512, **g), add_pooling_layer=False).eval()
+        enc = BertSentenceEncoder(model.state_dict(), hidden=g["hidden_size"], layers=g["num_hidden_layers"],
+                                  heads=g["num_attention_heads"], ffn=g["intermediate_size"], pool=pool,
+                                  device=dev.index or 0)
+        entry = {}
+        for label, b, sl, iters in (("query B=1 S=16", 1, 16, 200), ("bulk B=256 S=64", 256, 64, 20)):
+            gen = torch.Generator(device=dev).manual_seed(5)
+            ids = torch.randint(1000, 30000, (b, sl), generator=gen, device=dev, dtype=torch.int32)
+            mask = torch.ones((b, sl), dtype=torch.int32, device=dev)
+            for _ in range(3):
+                enc.encode_ids_torch(ids, mask)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                enc.encode_ids_torch(ids, mask)
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / iters
+            flops = 2.0 * b * sl * g["num_hidden_layers"] * (4 * g["hidden_size"] ** 2 + 2 * g["hidden_size"] * g["intermediate_size"])
+            entry[label] = {"ms_per_call": round(ms, 4), "sentences_per_s": round(b / (ms / 1e3), 1),
+                            "gemm_tflops": round(flops / (ms / 1e3) / 1e12, 2), "launches": enc.last_launches()}
+        # host API, one query text per call (numpy ids in, numpy vector out; copies inside the timing)
+        ids_h = np.random.default_rng(0).integers(1000, 30000, (1, 16)).astype(np.int32)
+        mask_h = np.ones((1, 16), dtype=np.int32)
+        enc.encode_ids(ids_h, mask_h)
+        t0 = time.perf_counter()
+        for _ in range(200):
+            enc.encode_ids(ids_h, mask_h)
+        entry["query B=1 S=16"]["e2e_ms_per_call"] = round((time.perf_counter() - t0) / 200 * 1e3, 4)
+        if cpu:
+            from oracle import bert_encoder as be
+
+            entry["cpu_baseline"] = {}
+            for label, b, sl, reps in (("query B=1 S=16", 1, 16, 10), ("bulk B=8 S=64", 8, 64, 3)):
+                ids_c = np.random.default_rng(1).integers(1000, 30000, (b, sl)).astype(np.int32)
+                mask_c = np.ones((b, sl), dtype=np.int32)
+                be.encode(model, ids_c, mask_c, pool_name)
+                t0 = time.perf_counter()
+                for _ in range(reps):
+                    be.encode(model, ids_c, mask_c, pool_name)
+                dt = (time.perf_counter() - t0) / reps
+                entry["cpu_baseline"][label] = {"ms_per_call": round(dt * 1e3, 3), "sentences_per_s": round(b / dt, 1)}
+            entry["cpu_baseline"]["kind"] = "HF BertModel fp32 (what sentence-transformers runs), torch %d threads" % torch.get_num_threads()
+        res[name] = entry
+        del enc, model
     return res
 
 

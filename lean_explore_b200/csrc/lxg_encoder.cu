@@ -26,6 +26,21 @@ struct lxg_encoder {
   CUtensorMap map_h{}, map_ctx{}, map_ffn{};  // A operands (activations)
   std::vector<CUtensorMap> map_wqkv, map_wo, map_w1, map_w2;
   int launches = 0;
+  // One captured CUDA graph per (b, s, pool): a query-time forward pass is 2 + 7 * layers tiny
+  // kernels, i.e. launch bound; replaying a graph removes the per-launch host cost and most of the
+  // inter-kernel gaps.  All graph nodes use workspace pointers only (ids/mask/out are staged).
+  struct Graph {
+    int b, s, pool;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Graph> graphs;
+  bool use_graphs = true;
+  float* out_buf = nullptr;  // [out_cap, H] pooled vectors (graph nodes cannot point at caller memory)
+  int out_cap = 0;
+  // The forward runs on a private stream ordered after / before the caller's stream by events:
+  // the caller's stream may be the legacy default stream, which cannot be captured.
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
 };
 
 namespace {
@@ -44,7 +59,16 @@ int make_map(CUtensorMap* m, const void* base, int rows, int cols) {
   return LXG_OK;
 }
 
+void drop_graphs(lxg_encoder* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
 void free_ws(lxg_encoder* e) {
+  drop_graphs(e);  // they reference the workspace
+  cudaFree(e->out_buf);
+  e->out_buf = nullptr;
+  e->out_cap = 0;
   cudaFree(e->h);
   cudaFree(e->qkv);
   cudaFree(e->ctx);
@@ -95,77 +119,11 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmPa
   return cudaGetLastError();
 }
 
-}  // namespace
 
-extern "C" {
-
-int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w) {
-  if (!out) return set_error(LXG_EINVAL, "out is NULL");
-  *out = nullptr;
-  if (!w || !w->layer) return set_error(LXG_EINVAL, "weights are NULL");
-  if (!lxg::encode_tensor_map_ready()) return set_error(LXG_EINVAL, "lxg_init has not been called");
-  if (w->hidden <= 0 || w->hidden > 1024 || w->hidden % kGemmBN != 0 || w->ffn % kGemmBN != 0 || w->layers <= 0 ||
-      w->heads <= 0 || w->hidden % w->heads != 0)
-    return set_error(LXG_EUNSUPPORTED, "encoder geometry: hidden and ffn must be multiples of 128, hidden <= 1024");
-  const int dh = w->hidden / w->heads;
-  if (dh > 64 || dh % 2 != 0) return set_error(LXG_EUNSUPPORTED, "encoder geometry: head size must be even and <= 64");
-  if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b)
-    return set_error(LXG_EINVAL, "embedding weights are NULL");
-  lxg_encoder* e = new lxg_encoder();
-  e->w = *w;
-  e->layers.assign(w->layer, w->layer + w->layers);
-  e->w.layer = e->layers.data();
-  const int H = w->hidden, F = w->ffn;
-  e->map_wqkv.resize(w->layers);
-  e->map_wo.resize(w->layers);
-  e->map_w1.resize(w->layers);
-  e->map_w2.resize(w->layers);
-  for (int l = 0; l < w->layers; ++l) {
-    const lxg_bert_layer& L = e->layers[l];
-    const void* ptrs[] = {L.wqkv, L.bqkv, L.wo, L.bo, L.ln1_g, L.ln1_b, L.w1, L.b1, L.w2, L.b2, L.ln2_g, L.ln2_b};
-    for (const void* p : ptrs)
-      if (!p || !is_device_ptr(p)) {
-        delete e;
-        return set_error(LXG_EINVAL, "layer " + std::to_string(l) + ": weight pointer is not device memory");
-      }
-    int rc;
-    if ((rc = make_map(&e->map_wqkv[l], L.wqkv, 3 * H, H)) != LXG_OK || (rc = make_map(&e->map_wo[l], L.wo, H, H)) != LXG_OK ||
-        (rc = make_map(&e->map_w1[l], L.w1, F, H)) != LXG_OK || (rc = make_map(&e->map_w2[l], L.w2, H, F)) != LXG_OK) {
-      delete e;
-      return rc;
-    }
-  }
-  *out = e;
-  return LXG_OK;
-}
-
-int lxg_encoder_destroy(lxg_encoder* e) {
-  if (!e) return LXG_OK;
-  free_ws(e);
-  delete e;
-  return LXG_OK;
-}
-
-int lxg_encoder_last_launches(const lxg_encoder* e) { return e ? e->launches : -1; }
-
-int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, int pool, float* out,
-               void* stream) {
-  if (!e || !ids || !mask || !out) return set_error(LXG_EINVAL, "NULL argument");
-  if (b < 0 || s <= 0) return set_error(LXG_EINVAL, "b must be >= 0 and s >= 1");
-  if (s > e->w.max_pos) return set_error(LXG_EINVAL, "sequence longer than the position table");
-  if (pool != LXG_POOL_MEAN && pool != LXG_POOL_CLS) return set_error(LXG_EINVAL, "bad pooling mode");
-  if (b == 0) return LXG_OK;
-  std::lock_guard<std::mutex> lock(e->mu);
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const long long tokens_ll = static_cast<long long>(b) * s;
-  if (tokens_ll > (1 << 22)) return set_error(LXG_EUNSUPPORTED, "more than 4M tokens per call");
-  const int tokens = static_cast<int>(tokens_ll);
-  int rc = reserve_ws(e, tokens);
-  if (rc != LXG_OK) return rc;
+// The forward pass proper: 2 + 7 * layers launches on `st`, workspace pointers only.
+int launch_forward(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
+  const int tokens = b * s;
   const int H = e->w.hidden, F = e->w.ffn, heads = e->w.heads, dh = H / heads;
-  const bool ids_dev = is_device_ptr(ids), mask_dev = is_device_ptr(mask), out_dev = is_device_ptr(out);
-  LXG_CUDA(cudaMemcpyAsync(e->ids, ids, tokens * sizeof(int), ids_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-  LXG_CUDA(cudaMemcpyAsync(e->mask, mask, tokens * sizeof(int), mask_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
   int launches = 0;
   const int warps_per_block = 8;
   const int row_blocks = (tokens + warps_per_block - 1) / warps_per_block;
@@ -225,19 +183,148 @@ int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t 
     LXG_CUDA(cudaGetLastError());
     launches += 7;
   }
-  float* out_d = out;
-  float* staged = nullptr;
-  if (!out_dev) {
-    staged = e->pre;  // fp32 [cap, H] scratch is free again after the last LayerNorm
-    out_d = staged;
-  }
-  pool_normalize_kernel<<<b, 256, H * sizeof(float), st>>>(e->h, e->mask, s, H, pool == LXG_POOL_CLS ? 1 : 0, out_d);
+  pool_normalize_kernel<<<b, 256, H * sizeof(float), st>>>(e->h, e->mask, s, H, pool == LXG_POOL_CLS ? 1 : 0, e->out_buf);
   LXG_CUDA(cudaGetLastError());
   ++launches;
   e->launches = launches;
+  return LXG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w) {
+  if (!out) return set_error(LXG_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!w || !w->layer) return set_error(LXG_EINVAL, "weights are NULL");
+  if (!lxg::encode_tensor_map_ready()) return set_error(LXG_EINVAL, "lxg_init has not been called");
+  if (w->hidden <= 0 || w->hidden > 1024 || w->hidden % kGemmBN != 0 || w->ffn % kGemmBN != 0 || w->layers <= 0 ||
+      w->heads <= 0 || w->hidden % w->heads != 0)
+    return set_error(LXG_EUNSUPPORTED, "encoder geometry: hidden and ffn must be multiples of 128, hidden <= 1024");
+  const int dh = w->hidden / w->heads;
+  if (dh > 64 || dh % 2 != 0) return set_error(LXG_EUNSUPPORTED, "encoder geometry: head size must be even and <= 64");
+  if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b)
+    return set_error(LXG_EINVAL, "embedding weights are NULL");
+  lxg_encoder* e = new lxg_encoder();
+  e->w = *w;
+  e->layers.assign(w->layer, w->layer + w->layers);
+  e->w.layer = e->layers.data();
+  const int H = w->hidden, F = w->ffn;
+  e->map_wqkv.resize(w->layers);
+  e->map_wo.resize(w->layers);
+  e->map_w1.resize(w->layers);
+  e->map_w2.resize(w->layers);
+  for (int l = 0; l < w->layers; ++l) {
+    const lxg_bert_layer& L = e->layers[l];
+    const void* ptrs[] = {L.wqkv, L.bqkv, L.wo, L.bo, L.ln1_g, L.ln1_b, L.w1, L.b1, L.w2, L.b2, L.ln2_g, L.ln2_b};
+    for (const void* p : ptrs)
+      if (!p || !is_device_ptr(p)) {
+        delete e;
+        return set_error(LXG_EINVAL, "layer " + std::to_string(l) + ": weight pointer is not device memory");
+      }
+    int rc;
+    if ((rc = make_map(&e->map_wqkv[l], L.wqkv, 3 * H, H)) != LXG_OK || (rc = make_map(&e->map_wo[l], L.wo, H, H)) != LXG_OK ||
+        (rc = make_map(&e->map_w1[l], L.w1, F, H)) != LXG_OK || (rc = make_map(&e->map_w2[l], L.w2, H, F)) != LXG_OK) {
+      delete e;
+      return rc;
+    }
+  }
+  *out = e;
+  return LXG_OK;
+}
+
+int lxg_encoder_destroy(lxg_encoder* e) {
+  if (!e) return LXG_OK;
+  free_ws(e);
+  if (e->own) cudaStreamDestroy(e->own);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  delete e;
+  return LXG_OK;
+}
+
+int lxg_encoder_last_launches(const lxg_encoder* e) { return e ? e->launches : -1; }
+
+int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, int pool, float* out,
+               void* stream) {
+  if (!e || !ids || !mask || !out) return set_error(LXG_EINVAL, "NULL argument");
+  if (b < 0 || s <= 0) return set_error(LXG_EINVAL, "b must be >= 0 and s >= 1");
+  if (s > e->w.max_pos) return set_error(LXG_EINVAL, "sequence longer than the position table");
+  if (pool != LXG_POOL_MEAN && pool != LXG_POOL_CLS) return set_error(LXG_EINVAL, "bad pooling mode");
+  if (b == 0) return LXG_OK;
+  std::lock_guard<std::mutex> lock(e->mu);
+  cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+  const long long tokens_ll = static_cast<long long>(b) * s;
+  if (tokens_ll > (1 << 22)) return set_error(LXG_EUNSUPPORTED, "more than 4M tokens per call");
+  const int tokens = static_cast<int>(tokens_ll);
+  int rc = reserve_ws(e, tokens);
+  if (rc != LXG_OK) return rc;
+  if (!e->own) {
+    LXG_CUDA(cudaStreamCreateWithFlags(&e->own, cudaStreamNonBlocking));
+    LXG_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    LXG_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t st = e->own;
+  LXG_CUDA(cudaEventRecord(e->ev_in, caller));
+  LXG_CUDA(cudaStreamWaitEvent(st, e->ev_in, 0));
+  const int H = e->w.hidden;
+  const bool ids_dev = is_device_ptr(ids), mask_dev = is_device_ptr(mask), out_dev = is_device_ptr(out);
+  LXG_CUDA(cudaMemcpyAsync(e->ids, ids, tokens * sizeof(int), ids_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  LXG_CUDA(cudaMemcpyAsync(e->mask, mask, tokens * sizeof(int), mask_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  // pooled vectors land in a workspace buffer first (fixed address: graph-capturable)
+  if (b > e->out_cap) {
+    drop_graphs(e);
+    cudaFree(e->out_buf);
+    e->out_buf = nullptr;
+    e->out_cap = 0;
+    const int cap = std::max(b, 64);
+    LXG_CUDA(cudaMalloc(&e->out_buf, static_cast<size_t>(cap) * H * sizeof(float)));
+    e->out_cap = cap;
+  }
+  cudaGraphExec_t exec = nullptr;
+  if (e->use_graphs) {
+    for (auto& g : e->graphs)
+      if (g.b == b && g.s == s && g.pool == pool) exec = g.exec;
+    if (!exec) {
+      // first call with this shape: run once eagerly (sets kernel attributes, validates the
+      // launch configuration), then capture the same sequence for every later call
+      rc = launch_forward(e, b, s, pool, st);
+      if (rc != LXG_OK) return rc;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc2 = launch_forward(e, b, s, pool, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc2 == LXG_OK && ce == cudaSuccess && graph &&
+            cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          if (e->graphs.size() >= 32) drop_graphs(e);
+          e->graphs.push_back({b, s, pool, exec});
+        } else {
+          exec = nullptr;
+          e->use_graphs = false;  // capture unsupported here: stay on plain launches
+        }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+      } else {
+        cudaGetLastError();
+        e->use_graphs = false;
+      }
+      exec = nullptr;  // this call already ran eagerly
+    } else {
+      LXG_CUDA(cudaGraphLaunch(exec, st));
+    }
+  }
+  if (!e->use_graphs) {
+    rc = launch_forward(e, b, s, pool, st);
+    if (rc != LXG_OK) return rc;
+  }
+  const size_t out_bytes = static_cast<size_t>(b) * H * sizeof(float);
+  LXG_CUDA(cudaMemcpyAsync(out, e->out_buf, out_bytes, out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   if (!out_dev) {
-    LXG_CUDA(cudaMemcpyAsync(out, staged, static_cast<size_t>(b) * H * sizeof(float), cudaMemcpyDeviceToHost, st));
     LXG_CUDA(cudaStreamSynchronize(st));
+  } else {
+    LXG_CUDA(cudaEventRecord(e->ev_out, st));
+    LXG_CUDA(cudaStreamWaitEvent(caller, e->ev_out, 0));
   }
   return LXG_OK;
 }

@@ -56,6 +56,17 @@ bool is_device_ptr(const void* p) {
   return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch tensor): DMA can
+// read and write it directly, so the pinned staging bounce is skipped.
+bool is_pinned_host_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
 // One growable device allocation.
 struct DevBuf {
   void* p = nullptr;
@@ -662,9 +673,13 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   uint8_t* stg = reinterpret_cast<uint8_t*>(ix->ws_out.p);
   const float* xd = x;
   if (!x_dev) {
-    LXG_CUDA(ix->h_stage.reserve(std::max(x_bytes, out_elems * 12)));
-    std::memcpy(ix->h_stage.p, x, x_bytes);
-    LXG_CUDA(cudaMemcpyAsync(stg, ix->h_stage.p, x_bytes, cudaMemcpyHostToDevice, st));
+    const void* src = x;
+    if (!is_pinned_host_ptr(x)) {  // pageable caller memory: bounce through the pinned stage
+      LXG_CUDA(ix->h_stage.reserve(std::max(x_bytes, out_elems * 12)));
+      std::memcpy(ix->h_stage.p, x, x_bytes);
+      src = ix->h_stage.p;
+    }
+    LXG_CUDA(cudaMemcpyAsync(stg, src, x_bytes, cudaMemcpyHostToDevice, st));
     xd = reinterpret_cast<const float*>(stg);
     stg += (x_bytes + 255) / 256 * 256;
   }
@@ -690,11 +705,17 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   ix->stats.kernel_launches = total_launches;
   if (!out_dev) {
     ix->stats.uncertified = total_flag;
-    LXG_CUDA(ix->h_stage.reserve(out_elems * 12));
-    LXG_CUDA(cudaMemcpyAsync(ix->h_stage.p, Id, out_elems * 12, cudaMemcpyDeviceToHost, st));
-    LXG_CUDA(cudaStreamSynchronize(st));
-    std::memcpy(I_out, ix->h_stage.p, out_elems * 8);
-    std::memcpy(D_out, reinterpret_cast<uint8_t*>(ix->h_stage.p) + out_elems * 8, out_elems * 4);
+    if (is_pinned_host_ptr(D_out) && is_pinned_host_ptr(I_out)) {
+      LXG_CUDA(cudaMemcpyAsync(I_out, Id, out_elems * 8, cudaMemcpyDeviceToHost, st));
+      LXG_CUDA(cudaMemcpyAsync(D_out, Dd, out_elems * 4, cudaMemcpyDeviceToHost, st));
+      LXG_CUDA(cudaStreamSynchronize(st));
+    } else {
+      LXG_CUDA(ix->h_stage.reserve(out_elems * 12));
+      LXG_CUDA(cudaMemcpyAsync(ix->h_stage.p, Id, out_elems * 12, cudaMemcpyDeviceToHost, st));
+      LXG_CUDA(cudaStreamSynchronize(st));
+      std::memcpy(I_out, ix->h_stage.p, out_elems * 8);
+      std::memcpy(D_out, reinterpret_cast<uint8_t*>(ix->h_stage.p) + out_elems * 8, out_elems * 4);
+    }
   }
   return LXG_OK;
 }

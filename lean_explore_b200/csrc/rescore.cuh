@@ -99,6 +99,18 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   }
   for (int i = tid; i < cv.d; i += kMergeThreads) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
   __syncthreads();
+  if (p.qnorm[q] == 0.0f) {
+    // all-zero query (normalize_L2 leaves it untouched): every inner product is exactly 0, so the
+    // answer is the k lowest row ids.  Pass 1 keeps no candidates for it (every score ties with
+    // its threshold), hence the closed form here.
+    for (int r = tid; r < p.k; r += kMergeThreads) {
+      const bool have = r < cv.n;
+      p.out_d[static_cast<size_t>(q) * p.k + r] = have ? 0.0f : -FLT_MAX;
+      p.out_i[static_cast<size_t>(q) * p.k + r] = have ? static_cast<long long>(r) + cv.row_offset : -1;
+      if (p.out_d64) p.out_d64[static_cast<size_t>(q) * p.k + r] = have ? 0.0 : -static_cast<double>(FLT_MAX);
+    }
+    return;
+  }
   // largest final list threshold (no dropped row scored above it) and the final cross-list level
   // (at least kp rows score >= it: entries below it cannot be among the best kp)
   {
@@ -288,8 +300,6 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     double theta = 0.0;
     if (a_min == -CUDART_INF_F) {
       certified = true;  // nothing was ever dropped: every row of the corpus was re-scored
-    } else if (p.qnorm[q] == 0.0f) {
-      certified = true;  // all-zero query: every score is exactly 0 and ties are ordered exactly
     } else {
       const double unscale = 1.0 / (static_cast<double>(p.qscale[q]) * cv.scan_scale);
       const double eps = static_cast<double>(cv.max_row_norm) * p.qnorm[q] * cv.rel_err;

@@ -326,6 +326,7 @@ __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf
 
 // One 32-column chunk of the accumulator: per 8-column group a max tree against the threshold;
 // a group with a survivor appends its survivors to the list and feeds the tracker.
+template <bool kFeedTracker = true>
 __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& ls, float (&tk)[kTrack],
                                            int base_row, bool two_slots) {
 #pragma unroll
@@ -342,9 +343,25 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& l
           ++ls.wp;
         }
       }
-      track_insert(tk, m, two_slots);
+      if (kFeedTracker) track_insert(tk, m, two_slots);
     }
   }
+}
+
+// First tile of a list, pass 1: feed the tracker with every 8-column maximum, append nothing.
+__device__ __forceinline__ void track_chunk(const uint32_t (&r)[32], float (&tk)[kTrack], bool two_slots) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
+    track_insert(tk, fmax3(fmax3(v[0], v[1], v[2]), fmax3(v[3], v[4], v[5]), fmaxf(v[6], v[7])), two_slots);
+  }
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
 }
 
 // Cold variant (last, partial tile of the corpus; debug dump): columns >= valid are TMA zero fill.
@@ -637,7 +654,40 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       if (lvl_r > 0) ls.thr = fmaxf(ls.thr, thr_sh[t]);  // the other group may have refreshed it
       const int row0 = (tile_begin + it) * N_T + grp * kGroupRow0;  // corpus row of the group's chunk 0, column 0
       const uint32_t tile_addr = tmem_base + lane_base + acc * N_T + grp * kGroupCols;
-      if (p.perf_mode == 1) {
+      if (it == 0 && lvl_r > 0 && lvl_r <= kGroupCols / 8 && !dbg && p.perf_mode == 0 && (tile_begin + 1) * N_T <= n) {
+        // ---- first tile: instead of dumping all of it into the list (no threshold exists yet),
+        // pass 1 only feeds the tracker and publishes the list's level; then the warp waits
+        // (bounded: ~20 us, the other CTAs are co-resident and do the same) until every list has
+        // published, and pass 2 re-reads the accumulator - still in tensor memory - against the
+        // first cross-list level.  Lists stay ~4x shorter, which pass 2 of the search reads.
+#pragma unroll 1
+        for (int c = 0; c < kGroupChunks; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tile_addr + c * 32, r);
+          ptx::tc_wait_ld();
+          track_chunk(r, tk, two_slots);
+        }
+        if (lvl_mine != nullptr && tk[kTrack - 1] > published) {
+          published = tk[kTrack - 1];
+          __stcg(lvl_mine, float_to_key(__float_as_uint(published)));
+        }
+        const unsigned long long t0 = global_timer_ns();
+        float lv;
+        do {
+          lv = warp_refresh_level(p, lists, wq0, wlive, lane);
+        } while (!__all_sync(0xffffffffu, !live || lv > -CUDART_INF_F) && global_timer_ns() - t0 < 20000ull);
+        if (live && lv > ls.thr) {
+          ls.thr = lv;
+          thr_sh[t] = lv;
+        }
+#pragma unroll 1
+        for (int c = 0; c < kGroupChunks; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tile_addr + c * 32, r);
+          ptx::tc_wait_ld();
+          scan_chunk<false>(r, ls, tk, row0 + c * kChunkRowStep, two_slots);
+        }
+      } else if (p.perf_mode == 1) {
       } else if (dbg || (tile_begin + it + 1) * N_T > n) {  // warp-uniform
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {

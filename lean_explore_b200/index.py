@@ -127,8 +127,10 @@ class GpuIndexFlatIP:
             raise ValueError("k must be positive")
         self._materialise()
         nq = x.shape[0]
-        D = np.empty((nq, k), dtype=np.float32)
-        I = np.empty((nq, k), dtype=np.int64)
+        # results land in page-locked memory (torch's caching host allocator): the library then
+        # copies device -> host straight into them; a pinned `x` is likewise read without a bounce
+        D = torch.empty((nq, k), dtype=torch.float32, pin_memory=True).numpy()
+        I = torch.empty((nq, k), dtype=torch.int64, pin_memory=True).numpy()
         _lib.check(self._lib.lxg_search(self._handle, x.ctypes.data, nq, k, int(normalize),
                                         D.ctypes.data, I.ctypes.data, _current_stream_ptr(self.device)))
         return D, I
