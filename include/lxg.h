@@ -128,6 +128,14 @@ int lxg_index_get_timing(lxg_index* index, lxg_timing* out);
 int lxg_debug_scores(lxg_index* index, const float* x_dev, int32_t nq, int normalize,
                      float* scores_dev, float* qscale_dev, float* scan_scale_host, void* stream);
 
+/* Test / measurement hook: selects code paths of pass 1 that the planner would otherwise pick by
+ * shape (each argument: 0 / 1 sets, -1 leaves unchanged).  no_level: never use the cross-list
+ * level (thresholds from list compaction only); force_single: never pair CTAs (cta_group::1
+ * only); perf_mode: see LXG_SCAN_PERF_MODE in DESIGN.md (results are NOT produced when != 0).
+ * The same switches are read from the environment (LXG_SCAN_NOLEVEL, LXG_SCAN_SINGLE,
+ * LXG_SCAN_PERF_MODE) by lxg_init. */
+int lxg_debug_config(int no_level, int force_single, int perf_mode);
+
 /* ---- sentence encoder (BERT-class) --------------------------------------------------
  * Replaces SentenceTransformer.encode inside EmbeddingClient.embed
  * (src/lean_explore/util/embedding_client.py:88-101): transformer forward -> pooling ->

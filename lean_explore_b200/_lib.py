@@ -11,7 +11,10 @@ import threading
 from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_void_p
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "liblxg.so"
+import os
+
+# LXG_LIB_PATH selects an A/B build variant of the same ABI (lean_explore_b200.build.build(defines=...))
+LIB_PATH = Path(os.environ.get("LXG_LIB_PATH") or Path(__file__).resolve().parent / "liblxg.so")
 
 LXG_F32, LXG_F16 = 0, 1
 LXG_POOL_MEAN, LXG_POOL_CLS = 0, 1
@@ -76,6 +79,7 @@ SIGNATURES = {
     "lxg_index_get_timing": (c_int, [c_void_p, POINTER(Timing)]),
     "lxg_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p,
                                  POINTER(c_float), c_void_p]),
+    "lxg_debug_config": (c_int, [c_int, c_int, c_int]),
     "lxg_encoder_create": (c_int, [POINTER(c_void_p), POINTER(BertWeights)]),
     "lxg_encoder_destroy": (c_int, [c_void_p]),
     "lxg_encoder_last_launches": (c_int, [c_void_p]),

@@ -37,21 +37,25 @@ def needs_build() -> bool:
     return any(p.stat().st_mtime > lib_mtime for p in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every CUDA source of the package into one shared library."""
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, defines: tuple[str, ...] = (), lib_path: Path | None = None) -> Path:
+    """Compile every CUDA source of the package into one shared library.  `defines` / `lib_path`
+    build an A/B variant next to the product library (e.g. ("LXG_EPI_GROUPS=2",), liblxg_g2.so;
+    selected at run time with LXG_LIB_PATH)."""
+    variant = lib_path is not None
+    lib_path = lib_path or LIB_PATH
+    if not force and not variant and not needs_build():
         return LIB_PATH
     objs = []
     for src in SOURCES:
-        obj = CSRC / (Path(src).stem + ".o")
-        cmd = [_nvcc(), *NVCC_FLAGS, "-c", str(CSRC / src), "-o", str(obj)]
+        obj = CSRC / (Path(src).stem + (("." + lib_path.stem) if variant else "") + ".o")
+        cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", str(CSRC / src), "-o", str(obj)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         subprocess.run(cmd, check=True)
         objs.append(str(obj))
-    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB_PATH), *objs, "-lcudart"]
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(lib_path), *objs, "-lcudart"]
     subprocess.run(cmd, check=True)
-    return LIB_PATH
+    return lib_path
 
 
 if __name__ == "__main__":

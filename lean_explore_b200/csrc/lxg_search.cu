@@ -156,30 +156,25 @@ struct Plan {
   int kp, cap, keep_max, qblocks, slices, tiles_per_slice, num_tiles;
   bool pair;      // CTA pairs (cta_group::2) when there are at least two query blocks
   int grid_x;     // query blocks launched (padded to even in pair mode)
-  int lists;      // candidate lists per query: two per slice (one per epilogue group)
+  int lists;      // candidate lists per query: one per slice and epilogue group
   int lvl_r;      // cross-list level: every list publishes its lvl_r-th best (0 = disabled)
   int max_items;  // pass-2 candidate pool (entries)
 };
 
 // Lists that see at least 8*kTrack rows (the others never publish a level, scan_topk.cuh).  List
-// (slice, g) holds, of every tile of the slice, the 32-row chunks c at tile row g*row0 + c*step
-// (the same constants as kGroupRow0 / kChunkRowStep of the kernel).
-int lists_with_level(int n, int tile_rows, bool pair, int num_tiles, int slices, int tiles_per_slice) {
-  const int gc = tile_rows / 2, chunks = gc / 32;
-  const bool split = false;  // kSplit of the kernel
-  const int row0 = (split && pair) ? 32 : gc, step = (split && pair) ? 64 : 32;
+// (slice, g) holds columns [g*gc, (g+1)*gc) of every tile of the slice, gc = tile_rows / kGroups.
+int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_per_slice) {
+  const int gc = tile_rows / kGroups;
   int ok = 0;
   for (int s = 0; s < slices; ++s) {
     const int tb = s * tiles_per_slice;
     const int te = std::min(num_tiles, tb + tiles_per_slice);
     const int my = std::max(0, te - tb);
-    for (int g = 0; g < 2; ++g) {
+    for (int g = 0; g < kGroups; ++g) {
       long long rows = static_cast<long long>(my) * gc;
       if (my > 0 && te == num_tiles) {
-        for (int c = 0; c < chunks; ++c) {
-          const long long first = static_cast<long long>(num_tiles - 1) * tile_rows + g * row0 + c * step;
-          rows -= 32 - std::max(0ll, std::min(32ll, static_cast<long long>(n) - first));
-        }
+        const long long first = static_cast<long long>(num_tiles - 1) * tile_rows + g * gc;
+        rows -= gc - std::max(0ll, std::min(static_cast<long long>(gc), static_cast<long long>(n) - first));
       }
       if (rows >= kTrack * 8) ++ok;
     }
@@ -201,11 +196,11 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     s = std::max(s, 1);
     pl.tiles_per_slice = (pl.num_tiles + s - 1) / s;
     pl.slices = std::max(1, (pl.num_tiles + pl.tiles_per_slice - 1) / std::max(1, pl.tiles_per_slice));
-    pl.lists = 2 * pl.slices;
+    pl.lists = kGroups * pl.slices;
   };
   slice_up(std::max(1, g_num_sms / pl.grid_x));
   // cross-list level: needs lists * r >= kp with r <= kTrack
-  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.pair, pl.num_tiles, pl.slices, pl.tiles_per_slice);
+  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice);
   pl.lvl_r = lv >= 2 ? (pl.kp + lv - 1) / lv : 0;
   if (pl.lvl_r > kTrack) pl.lvl_r = 0;
   if (pl.lvl_r > 0) {
@@ -215,7 +210,7 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     pl.max_items = std::max(6144, 4 * pl.kp);
   } else {
     // thresholds come from compacting full lists: pass 2 holds lists * kp keys in shared memory
-    slice_up(std::min(pl.slices, std::max(1, 12288 / pl.kp)));
+    slice_up(std::min(pl.slices, std::max(1, 24576 / kGroups / pl.kp)));
     // list capacity: room for many appends between two compactions (each one costs a warp ~1-2k
     // cycles); a mid-scan compaction may keep up to keep_max entries (cheaper inexact cut)
     pl.cap = pl.kp <= 64 ? 4 * pl.kp : 2 * pl.kp;
@@ -296,6 +291,13 @@ int lxg_init(int device) {
   g_perf_mode = pm ? std::atoi(pm) : 0;
   g_device = device;
   g_inited = true;
+  return LXG_OK;
+}
+
+int lxg_debug_config(int no_level, int force_single, int perf_mode) {
+  if (no_level >= 0) g_no_level = no_level != 0;
+  if (force_single >= 0) g_force_single = force_single != 0;
+  if (perf_mode >= 0) g_perf_mode = perf_mode;
   return LXG_OK;
 }
 

@@ -83,7 +83,7 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   unsigned* sel_row = reinterpret_cast<unsigned*>(sel_score + p.kp);
   float* xq = reinterpret_cast<float*>(sel_row + p.kp);
   __shared__ int s_cnt[3], s_sel, s_m;
-  __shared__ int s_len[2 * 148];  // list lengths (at most two lists per slice, 148 slices)
+  __shared__ int s_len[kGroups * 148];  // list lengths (kGroups lists per slice, at most 148 slices)
   __shared__ uint32_t s_kmin, s_kmax, s_tkey, s_lvl;
   __shared__ double s_kth;
 
@@ -128,37 +128,77 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     }
   }
   __syncthreads();
-  const uint32_t tau_key = (p.lvl != nullptr && s_lvl != kLvlNone && s_lvl != kLvlSkip) ? s_lvl : 0u;
+  uint32_t tau_key = (p.lvl != nullptr && s_lvl != kLvlNone && s_lvl != kLvlSkip) ? s_lvl : 0u;
   // gather the entries at or above the level into shared memory (a warp per list, four 32-entry
-  // chunks in flight)
+  // chunks in flight).  If they do not fit the pool (row orders that defeat the running thresholds:
+  // a sorted or strongly clustered corpus), the level is first tightened by bisection over the
+  // lists in global memory - slow, but exact and only taken then.
   uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
-  for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
-    const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
-    const int c = s_len[s];
-    for (int i0 = 0; i0 < c; i0 += 128) {
-      uint2 e[4];
+  int m = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    kmin = 0xFFFFFFFFu;
+    kmax = 0u;
+    for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
+      const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
+      const int c = s_len[s];
+      for (int i0 = 0; i0 < c; i0 += 128) {
+        uint2 e[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * 32 + lane;
-        e[u] = i < c ? __ldcg(lst + i) : make_uint2(0u, 0u);
-      }
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u * 32 + lane;
+          e[u] = i < c ? __ldcg(lst + i) : make_uint2(0u, 0u);
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t key = float_to_key(e[u].x);
-        const bool keep = (i0 + u * 32 + lane < c) && key >= tau_key;
-        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-        if (bal == 0u) continue;
-        int base = 0;
-        if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        const int pos = base + __popc(bal & ((1u << lane) - 1u));
-        if (keep && pos < p.max_items) {
-          items[pos] = make_uint2(key, e[u].y);
-          kmin = min(kmin, key);
-          kmax = max(kmax, key);
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t key = float_to_key(e[u].x);
+          const bool keep = (i0 + u * 32 + lane < c) && key >= tau_key;
+          const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+          if (bal == 0u) continue;
+          int base = 0;
+          if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const int pos = base + __popc(bal & ((1u << lane) - 1u));
+          if (keep && pos < p.max_items) {
+            items[pos] = make_uint2(key, e[u].y);
+            kmin = min(kmin, key);
+            kmax = max(kmax, key);
+          }
         }
       }
     }
+    __syncthreads();
+    m = s_m;
+    if (m <= p.max_items || attempt == 1) break;
+    // ---- tighten: largest prefix with count(key >= prefix) >= kp, stopping as soon as that
+    // count fits the pool (three rotating counters: one barrier per step)
+    uint32_t prefix = 0u;
+    int cur = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const uint32_t cnd = prefix | (1u << bit);
+      int mine = 0;
+      for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
+        const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
+        const int c = s_len[s];
+        for (int i = lane; i < c; i += 32) mine += (float_to_key(__ldcg(lst + i).x) >= cnd) ? 1 : 0;
+      }
+      mine = __reduce_add_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicAdd(&s_cnt[cur], mine);
+      __syncthreads();
+      const int ge = s_cnt[cur];
+      if (tid == 0) s_cnt[(cur + 2) % 3] = 0;
+      cur = (cur + 1) % 3;
+      if (ge >= p.kp) {
+        prefix = cnd;
+        if (ge <= p.max_items) break;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      s_cnt[0] = s_cnt[1] = s_cnt[2] = 0;
+      s_m = 0;
+    }
+    tau_key = max(tau_key, prefix);
+    __syncthreads();
   }
   kmin = __reduce_min_sync(0xffffffffu, kmin);
   kmax = __reduce_max_sync(0xffffffffu, kmax);
@@ -167,11 +207,11 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     atomicMax(&s_kmax, kmax);
   }
   __syncthreads();
-  const int m = s_m;
   const float tau = tau_key ? __uint_as_float(key_to_float_bits(tau_key)) : -CUDART_INF_F;
   if (m > p.max_items) {
-    // more survivors than the pool holds (adversarial row order): hand the query to the exact
-    // path.  At least kp >= k rows have a tensor-core score >= tau, which bounds the k-th best.
+    // still more survivors than the pool holds: more than max_items - kp rows tie (in tensor-core
+    // score) around the kp-th best.  Hand the query to the exact path; at least kp >= k rows have
+    // a tensor-core score >= tau, which bounds the true k-th best.
     if (tid == 0) {
       const double unscale = 1.0 / (static_cast<double>(p.qscale[q]) * cv.scan_scale);
       const double eps = static_cast<double>(cv.max_row_norm) * p.qnorm[q] * cv.rel_err;

@@ -30,9 +30,17 @@
 
 namespace lxg {
 
-constexpr int kEpiWarps = 8;        // warps 0..7: two groups of four, one per accumulator
+// Epilogue warp groups.  Measured on B200 (same box, r1p): 2 groups (8 epilogue warps, 64 columns
+// each at N_T = 128) 0.336 ms on cfg2 / 2.61 ms on cfg3; 4 groups (16 warps, 32 columns each, 96
+// registers per thread, twice the lists) 0.394 / 2.83 ms.  More warps do not help: the kernel sits
+// at the chip's power wall and the extra per-tile bookkeeping costs more than the latency it hides.
+#ifndef LXG_EPI_GROUPS
+#define LXG_EPI_GROUPS 2
+#endif
+constexpr int kGroups = LXG_EPI_GROUPS;   // epilogue warp groups: each owns N_T / kGroups columns of every tile
+constexpr int kEpiWarps = 4 * kGroups;    // four warps (the four TMEM lane quarters) per group
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kScanThreads = kEpiThreads + 64;  // + warp 8 (TMA) + warp 9 (MMA)
+constexpr int kScanThreads = kEpiThreads + 64;  // + one TMA warp + one MMA warp
 constexpr int kKC = 64;            // fp16 elements per 128-byte swizzled row
 constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline
 constexpr int kStageBytes = 32768; // one pipeline stage: N_T rows x (32768 / (128 N_T)) k-chunks
@@ -43,7 +51,7 @@ constexpr uint32_t kLvlSkip = 0xFFFFFFFFu;   // list too short to ever publish o
 
 struct ScanParams {
   const __half* xh;   // [query blocks * 128, dpad] prepared queries (normalised, scaled, fp16, zero padded)
-  uint2* cand;        // [lists, nq, cap] (score bits, row);  list = slice * 2 + epilogue group
+  uint2* cand;        // [lists, nq, cap] (score bits, row);  list = slice * kGroups + epilogue group
   int* cand_count;    // [lists, nq]
   float* slice_thr;   // [lists, nq] final threshold of the list: every dropped row scored <= it
   float* dbg_scores;  // optional [nq, n] raw tensor-core scores (tests only), else nullptr
@@ -301,20 +309,20 @@ __device__ __forceinline__ void track_insert(float (&t)[kTrack], float v, bool t
 
 // Cross-list level: min over the lists of the published r-th best, for the
 // `nlive` queries q0.. of this warp (query q0 + lane gets its value).  lvl is query-major
-// [nq][lists]: the warp reads one query's levels with coalesced loads, 16 queries in flight.
+// [nq][lists]: the warp reads one query's levels with coalesced loads, 8 queries in flight.
 __device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int lists, int q0, int nlive, int lane) {
   uint32_t mine = kLvlNone;
-  for (int b = 0; b < nlive; b += 16) {  // warp-uniform
-    uint32_t lo[16];
+  for (int b = 0; b < nlive; b += 8) {  // warp-uniform
+    uint32_t lo[8];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) lo[u] = kLvlSkip;
+    for (int u = 0; u < 8; ++u) lo[u] = kLvlSkip;
     for (int s = lane; s < lists; s += 32) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u)
+      for (int u = 0; u < 8; ++u)
         if (b + u < nlive) lo[u] = min(lo[u], __ldcg(p.lvl + static_cast<size_t>(q0 + b + u) * lists + s));
     }
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
+    for (int u = 0; u < 8; ++u) {
       const uint32_t v = __reduce_min_sync(0xffffffffu, lo[u]);
       if (lane == b + u) mine = v;
     }
@@ -324,13 +332,13 @@ __device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int lis
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
 
-// One 32-column chunk of the accumulator: per 8-column group a max tree against the threshold;
-// a group with a survivor appends its survivors to the list and feeds the tracker.
-template <bool kFeedTracker = true>
-__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& ls, float (&tk)[kTrack],
+// One chunk (32 or 16 columns) of the accumulator: per 8-column group a max tree against the
+// threshold; a group with a survivor appends its survivors to the list and feeds the tracker.
+template <bool kFeedTracker = true, int NC>
+__device__ __forceinline__ void scan_chunk(const uint32_t (&r)[NC], ListState& ls, float (&tk)[kTrack],
                                            int base_row, bool two_slots) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NC / 8; ++g) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
@@ -349,9 +357,10 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&r)[32], ListState& l
 }
 
 // First tile of a list, pass 1: feed the tracker with every 8-column maximum, append nothing.
-__device__ __forceinline__ void track_chunk(const uint32_t (&r)[32], float (&tk)[kTrack], bool two_slots) {
+template <int NC>
+__device__ __forceinline__ void track_chunk(const uint32_t (&r)[NC], float (&tk)[kTrack], bool two_slots) {
 #pragma unroll
-  for (int g = 0; g < 4; ++g) {
+  for (int g = 0; g < NC / 8; ++g) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
@@ -365,20 +374,21 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
 }
 
 // Cold variant (last, partial tile of the corpus; debug dump): columns >= valid are TMA zero fill.
+template <int NC>
 __device__ __forceinline__ void scan_chunk_careful(uint32_t taddr, ListState& ls, float (&tk)[kTrack], int base_row,
-                                                int valid, float* __restrict__ dbg_row, bool two_slots) {
-  uint32_t r[32];
-  ptx::tmem_ld_32x32b_x32(taddr, r);
+                                                   int valid, float* __restrict__ dbg_row, bool two_slots) {
+  uint32_t r[NC];
+  ptx::tmem_ld_cols(taddr, r);
   ptx::tc_wait_ld();
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
+  for (int j = 0; j < NC; ++j) {
     if (j < valid) {
       if (dbg_row != nullptr) dbg_row[base_row + j] = __uint_as_float(r[j]);
     } else {
       r[j] = 0xFF800000u;  // -inf
     }
   }
-  scan_chunk(r, ls, tk, base_row, two_slots);
+  scan_chunk<true>(r, ls, tk, base_row, two_slots);
 }
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
@@ -394,36 +404,28 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr int kStageBytesT = kPair ? kStageBytes / 2 : kStageBytes;
   constexpr int kKcPerStage = kStageBytesT / kBoxBytes;  // k-chunks (boxes) per pipeline stage
   constexpr int kStages = kStageRing / kStageBytesT;
-  // kSplit: every tile is computed as two N = N_T/2 halves with their own full/empty barriers,
-  // half g drained by epilogue group g alone (a slow group then never stalls the other one).
-  // Measured on B200 (cfg2, N_T = 128): N = 64 MMAs with A in tensor memory run at ~2/3 of the
-  // N = 128 rate (0.331 vs 0.270 ms for the bare TMA/MMA pipeline), which costs more than the
-  // decoupling gains - so it stays off; the code path is kept for the A/B.
-  constexpr bool kSplit = false;
-  constexpr int kGroupCols = N_T / 2;          // accumulator columns (corpus rows) per epilogue group
-  constexpr int kGroupChunks = kGroupCols / 32;
-  // Corpus rows behind the columns of group g, chunk c: tile row g * kGroupRow0 + c * kChunkRowStep + j.
-  // An N = 64 half of a CTA pair takes 32 rows from each CTA's box (columns 0-31 | 32-63), so the
-  // two chunks of a group are 64 tile rows apart.
-  constexpr int kGroupRow0 = (kSplit && kPair) ? 32 : kGroupCols;
-  constexpr int kChunkRowStep = (kSplit && kPair) ? 64 : 32;
+  // Epilogue group g owns accumulator columns [g * kGroupCols, (g+1) * kGroupCols) of every tile,
+  // read in chunks of kChunkCols columns.  (Computing every tile as N = N_T/2 halves with
+  // per-group barriers was measured and dropped: N = 64 MMAs with A in tensor memory run at
+  // ~2/3 of the N = 128 rate - 0.331 vs 0.270 ms for the bare cfg2 pipeline.)
+  constexpr int kGroupCols = N_T / kGroups;
+  constexpr int kChunkCols = kGroupCols < 32 ? kGroupCols : 32;
+  constexpr int kGroupChunks = kGroupCols / kChunkCols;
+  static_assert(kChunkCols == 32 || kChunkCols == 16, "tcgen05.ld shapes used: x32, x16");
   constexpr uint32_t kACol0 = 2 * N_T;  // TMEM columns: [0,N_T) acc0, [N_T,2N_T) acc1, then A
-  constexpr int kMmaN = kSplit ? N_T / 2 : N_T;
-  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, kMmaN);
-  constexpr uint32_t kHalfDesc = (kBoxRows / 2) * 128 >> 4;  // descriptor step to the B rows of half 1
-  // arrivals that free an accumulator (half): one per epilogue warp that reads it
-  constexpr uint32_t kAccArrivals = (kPair ? 2 : 1) * (kSplit ? kEpiWarps / 2 : kEpiWarps);
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, N_T);
+  constexpr uint32_t kAccArrivals = (kPair ? 2 : 1) * kEpiWarps;  // one arrival per epilogue warp
   constexpr uint32_t kAArrivals = (kPair ? 2 : 1) * kEpiWarps;    // every epilogue warp stores part of A
   constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ __align__(8) uint64_t empty_bar[kStages];
-  __shared__ __align__(8) uint64_t tmem_full_bar[4];   // [accumulator * 2 + half]
-  __shared__ __align__(8) uint64_t tmem_empty_bar[4];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t a_ready_bar;
   __shared__ uint32_t tmem_base_holder;
-  __shared__ float thr_sh[kQueryBlock];  // per query: the latest cross-list level either group fetched
+  __shared__ float thr_sh[kQueryBlock];  // per query: the latest cross-list level any group fetched
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -444,7 +446,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 4; ++a) {
+    for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&tmem_full_bar[a], 1);
       ptx::mbar_init(&tmem_empty_bar[a], kAccArrivals);
     }
@@ -522,65 +524,54 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t acc = it & 1;
-        const uint32_t stage_t = stage, phase_t = phase;  // first pipeline stage of this tile
-#pragma unroll
-        for (int half = 0; half < (kSplit ? 2 : 1); ++half) {
-          // half 1 walks the same stages again (they stay full until its MMAs retire)
-          stage = stage_t;
-          phase = phase_t;
-          const uint32_t hb = (acc * 2 + half) * 8;
-          ptx::mbar_wait_a(tempty0 + hb, ((it >> 1) & 1) ^ 1u);
+        ptx::mbar_wait_a(tempty0 + acc * 8, ((it >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * N_T;
+        for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
+          const int nb = min(kKcPerStage, p.num_kc - kc0);
+          ptx::mbar_wait_a(full0 + stage * 8, phase);
           ptx::tc_fence_after();
-          const uint32_t d_tmem = tmem_base + acc * N_T + half * kMmaN;
-          const bool release = !kSplit || half == 1;
-          for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
-            const int nb = min(kKcPerStage, p.num_kc - kc0);
-            if (half == 0) {
-              ptx::mbar_wait_a(full0 + stage * 8, phase);
-              ptx::tc_fence_after();
-            }
-            if (ptx::elect_one()) {
-              const uint32_t lo = desc_lo0 + stage * (kStageBytesT >> 4) + half * kHalfDesc;
-              const uint32_t a_kc = a_tmem0 + kc0 * 32;
+          if (ptx::elect_one()) {
+            const uint32_t lo = desc_lo0 + stage * (kStageBytesT >> 4);
+            const uint32_t a_kc = a_tmem0 + kc0 * 32;
 #pragma unroll
-              for (int b = 0; b < kKcPerStage; ++b) {
-                if (b < nb) {
+            for (int b = 0; b < kKcPerStage; ++b) {
+              if (b < nb) {
 #pragma unroll
-                  for (int k4 = 0; k4 < 4; ++k4) {
-                    // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
-                    // 8 TMEM columns in A.
-                    const uint64_t bdesc =
-                        (static_cast<uint64_t>(kDescHi) << 32) | (lo + b * (kBoxBytes >> 4) + k4 * 2);
-                    const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
-                    if constexpr (kPair)
-                      ptx::mma_f16_ts_pair(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
-                    else
-                      ptx::mma_f16_ts(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
-                  }
+                for (int k4 = 0; k4 < 4; ++k4) {
+                  // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
+                  // 8 TMEM columns in A.
+                  const uint64_t bdesc =
+                      (static_cast<uint64_t>(kDescHi) << 32) | (lo + b * (kBoxBytes >> 4) + k4 * 2);
+                  const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
+                  if constexpr (kPair)
+                    ptx::mma_f16_ts_pair(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
+                  else
+                    ptx::mma_f16_ts(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
                 }
               }
-              // stage reusable (in both CTAs) once the MMAs of its last reader retire
-              const bool last = kc0 + kKcPerStage >= p.num_kc;
-              if constexpr (kPair) {
-                if (release) ptx::tc_commit_pair_a(empty0 + stage * 8, 3);
-                if (last) ptx::tc_commit_pair_a(tfull0 + hb, 3);
-              } else {
-                if (release) ptx::tc_commit_a(empty0 + stage * 8);
-                if (last) ptx::tc_commit_a(tfull0 + hb);
-              }
             }
-            __syncwarp();
-            if (++stage == kStages) {
-              stage = 0;
-              phase ^= 1u;
+            // stage reusable (in both CTAs) once these MMAs retire
+            const bool last = kc0 + kKcPerStage >= p.num_kc;
+            if constexpr (kPair) {
+              ptx::tc_commit_pair_a(empty0 + stage * 8, 3);
+              if (last) ptx::tc_commit_pair_a(tfull0 + acc * 8, 3);
+            } else {
+              ptx::tc_commit_a(empty0 + stage * 8);
+              if (last) ptx::tc_commit_a(tfull0 + acc * 8);
             }
+          }
+          __syncwarp();
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }
     }
   } else {
-    // ------ epilogue warps: group g scans columns [g*N_T/2, (g+1)*N_T/2) of every accumulator tile,
-    // one query per thread
+    // ------ epilogue warps: group g scans columns [g*kGroupCols, (g+1)*kGroupCols) of every
+    // accumulator tile, one query per thread
     const int grp = warp >> 2;
     const int t = threadIdx.x & (kQueryBlock - 1);  // TMEM lane == query of the block
     const int q = qblock * kQueryBlock + t;
@@ -588,10 +579,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
 
     // ---- A operand: this thread's prepared fp16 query row -> tensor memory (lane t, d/2 columns);
-    // the 128-byte k-chunks of the row are split between the two groups
+    // the 128-byte k-chunks of the row are dealt round robin to the groups
     {
       const uint4* xrow = reinterpret_cast<const uint4*>(p.xh + static_cast<size_t>(q) * p.dpad);
-      for (int kc = grp; kc < p.num_kc; kc += 2) {
+      for (int kc = grp; kc < p.num_kc; kc += kGroups) {
         uint32_t r[32];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -612,8 +603,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
 
     // ---- threshold scan
-    const int lists = p.slices * 2;
-    const int list_id = slice * 2 + grp;
+    const int lists = p.slices * kGroups;
+    const int list_id = slice * kGroups + grp;
     const size_t list = static_cast<size_t>(list_id) * p.nq + (live ? q : 0);
     ListState ls;
     ls.buf = p.cand + list * p.cap;
@@ -635,10 +626,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       // to feed its tracker kTrack group maxima never publishes a level and is not counted
       long long rows = static_cast<long long>(my_tiles) * kGroupCols;
       if (my_tiles > 0 && tile_end == p.num_tiles) {
-        for (int c = 0; c < kGroupChunks; ++c) {
-          const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupRow0 + c * kChunkRowStep;
-          rows -= 32 - max(0ll, min(32ll, static_cast<long long>(n) - first));
-        }
+        const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupCols;
+        rows -= kGroupCols - max(0ll, min(static_cast<long long>(kGroupCols), static_cast<long long>(n) - first));
       }
       uint32_t* slot = p.lvl + static_cast<size_t>(q) * lists + list_id;
       if (rows >= kTrack * 8) lvl_mine = slot; else __stcg(slot, kLvlSkip);
@@ -648,11 +637,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const uint32_t tfull0 = ptx::opaque(ptx::smem_u32(&tmem_full_bar[0]));
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
-      const uint32_t hb = (acc * 2 + (kSplit ? grp : 0)) * 8;  // barrier of the accumulator (half) this group reads
-      ptx::mbar_wait_a(tfull0 + hb, (it >> 1) & 1);
+      ptx::mbar_wait_a(tfull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-      if (lvl_r > 0) ls.thr = fmaxf(ls.thr, thr_sh[t]);  // the other group may have refreshed it
-      const int row0 = (tile_begin + it) * N_T + grp * kGroupRow0;  // corpus row of the group's chunk 0, column 0
+      if (lvl_r > 0) ls.thr = fmaxf(ls.thr, thr_sh[t]);  // another group may have refreshed it
+      const int row0 = (tile_begin + it) * N_T + grp * kGroupCols;  // corpus row of the group's column 0
       const uint32_t tile_addr = tmem_base + lane_base + acc * N_T + grp * kGroupCols;
       if (it == 0 && lvl_r > 0 && lvl_r <= kGroupCols / 8 && !dbg && p.perf_mode == 0 && (tile_begin + 1) * N_T <= n) {
         // ---- first tile: instead of dumping all of it into the list (no threshold exists yet),
@@ -662,8 +650,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         // first cross-list level.  Lists stay ~4x shorter, which pass 2 of the search reads.
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tile_addr + c * 32, r);
+          uint32_t r[kChunkCols];
+          ptx::tmem_ld_cols(tile_addr + c * kChunkCols, r);
           ptx::tc_wait_ld();
           track_chunk(r, tk, two_slots);
         }
@@ -682,37 +670,40 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tile_addr + c * 32, r);
+          uint32_t r[kChunkCols];
+          ptx::tmem_ld_cols(tile_addr + c * kChunkCols, r);
           ptx::tc_wait_ld();
-          scan_chunk<false>(r, ls, tk, row0 + c * kChunkRowStep, two_slots);
+          scan_chunk<false>(r, ls, tk, row0 + c * kChunkCols, two_slots);
         }
       } else if (p.perf_mode == 1) {
       } else if (dbg || (tile_begin + it + 1) * N_T > n) {  // warp-uniform
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {
-          const int base_row = row0 + c * kChunkRowStep;
-          if (base_row < n) scan_chunk_careful(tile_addr + c * 32, ls, tk, base_row, min(32, n - base_row), dbg_row, two_slots);
+          const int base_row = row0 + c * kChunkCols;
+          if (base_row < n)
+            scan_chunk_careful<kChunkCols>(tile_addr + c * kChunkCols, ls, tk, base_row, min(kChunkCols, n - base_row),
+                                           dbg_row, two_slots);
         }
+      } else if constexpr (kGroupChunks == 1) {
+        uint32_t r[kChunkCols];
+        ptx::tmem_ld_cols(tile_addr, r);
+        ptx::tc_wait_ld();
+        if (p.perf_mode != 3) scan_chunk<true>(r, ls, tk, row0, two_slots);
       } else {
-        // software pipeline over the group's 32-column chunks: chunk c+1 is in flight while c is compared
-        uint32_t r[2][32];
-        ptx::tmem_ld_32x32b_x32(tile_addr, r[0]);
+        // software pipeline over the group's chunks: chunk c+1 is in flight while c is compared
+        uint32_t r[2][kChunkCols];
+        ptx::tmem_ld_cols(tile_addr, r[0]);
 #pragma unroll
         for (int c = 0; c < kGroupChunks; ++c) {
           ptx::tc_wait_ld();
-          if (c + 1 < kGroupChunks) ptx::tmem_ld_32x32b_x32(tile_addr + (c + 1) * 32, r[(c + 1) & 1]);
-          if (p.perf_mode == 3) {  // measurements only: TMEM reads without the compare
-          } else {
-            scan_chunk(r[c & 1], ls, tk, row0 + c * kChunkRowStep, two_slots);
-          }
+          if (c + 1 < kGroupChunks) ptx::tmem_ld_cols(tile_addr + (c + 1) * kChunkCols, r[(c + 1) & 1]);
+          if (p.perf_mode != 3) scan_chunk<true>(r[c & 1], ls, tk, row0 + c * kChunkCols, two_slots);
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {  // one arrival per warp (in pair mode the odd CTA's arrivals are remote)
-        uint64_t* eb = &tmem_empty_bar[acc * 2 + (kSplit ? grp : 0)];
-        if constexpr (kPair) ptx::mbar_arrive_cluster(eb, 0); else ptx::mbar_arrive(eb);
+        if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
       }
       if (lvl_r > 0) {
         if (lvl_mine != nullptr) {
@@ -722,10 +713,10 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
             __stcg(lvl_mine, float_to_key(__float_as_uint(lv)));
           }
         }
-        // the two groups take turns refreshing the block's thresholds (shared through thr_sh)
+        // the groups take turns refreshing the block's thresholds (shared through thr_sh)
         const int done = it + 1;
         if (done <= 4 || (done <= 32 && (done & 3) == 0) || (done & 31) == 0) {
-          if ((refreshes++ & 1) == grp) {
+          if ((refreshes++ % kGroups) == grp) {
             const float lv = warp_refresh_level(p, lists, wq0, wlive, lane);
             if (live && lv > ls.thr) {
               ls.thr = lv;
@@ -734,7 +725,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           }
         }
       }
-      // a tile appends at most N_T/2 entries per list: keep room for the next one
+      // a tile appends at most kGroupCols entries per list: keep room for the next one
       compact_full_lists(ls, cap - N_T, kp, keep_max, lane);
     }
     // ---- without a level the pass-2 merge expects at most kp entries per list

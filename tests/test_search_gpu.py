@@ -198,3 +198,63 @@ def test_merge_topk_shards():
     _lib.check(lib.lxg_merge_topk(Dg.data_ptr(), Ig.data_ptr(), 40, k, 2, D.data_ptr(), I.data_ptr(), None))
     torch.cuda.synchronize()
     assert np.array_equal(I.cpu().numpy(), If) and np.array_equal(D.cpu().numpy(), Df)
+
+
+@pytest.fixture
+def scan_modes():
+    """Toggle pass-1 code paths through the lxg_debug_config test hook; always restored."""
+    from lean_explore_b200 import _lib
+
+    lib = _lib.init(0)
+    yield lambda **kw: _lib.check(lib.lxg_debug_config(kw.get("no_level", -1), kw.get("force_single", -1), -1))
+    _lib.check(lib.lxg_debug_config(0, 0, 0))
+
+
+def test_every_scan_mode_returns_the_same_exact_result(scan_modes):
+    """Cross-list level vs compaction-only thresholds, CTA pairs vs single CTAs: four code paths of
+    pass 1, one answer (ids exact against the oracle in each)."""
+    corpus = make_corpus(30000, 384)
+    x = make_queries(300, 384)
+    want = None
+    for no_level in (0, 1):
+        for single in (0, 1):
+            scan_modes(no_level=no_level, force_single=single)
+            ix = _check(corpus, x, 50)
+            D, I = ix.search(x, 50, normalize=True)
+            if want is None:
+                want = (D, I)
+            assert np.array_equal(I, want[1]) and np.array_equal(D, want[0])
+
+
+@pytest.mark.parametrize("d", [64, 768])
+def test_adversarial_row_order_overflows_the_lists(d):
+    """Rows sorted by ascending score for the probe query: every tile beats everything seen before,
+    thresholds always lag, the candidate lists overflow and are compacted exactly."""
+    n = 60000
+    corpus = make_corpus(n, d).astype(np.float32)
+    q = make_queries(2, d)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    order = np.argsort(corpus @ q[0], kind="stable")
+    corpus = np.ascontiguousarray(corpus[order]).astype(np.float16)
+    _check(corpus, q, 10)     # 1 query block: many short lists, pass 2 has to tighten the level
+    _check(corpus, q, 100)
+    many = np.concatenate([q, make_queries(1198, d)])  # 10 query blocks: few long lists overflow
+    _check(corpus, many, 10)
+
+
+def test_large_k_with_many_query_blocks():
+    """k' too large for the cross-list level (lists * 8 < k'): compaction thresholds, pair mode."""
+    corpus = make_corpus(20000, 256)
+    x = make_queries(300, 256)
+    _check(corpus, x, 200)
+    _check(corpus[:5000], x[:130], 1000)
+
+
+def test_near_duplicate_heavy_corpus_goes_through_the_exact_path():
+    """Many exact duplicates around rank k for several queries: uncertified -> exact collectors."""
+    corpus = make_corpus(20000, 128)
+    for j in range(8):
+        corpus[1000 * j + 7 : 1000 * j + 47] = corpus[j]  # 40 copies of rows 0..7
+    x = corpus[:8].astype(np.float32)
+    ix = _check(corpus, x, 25)
+    assert ix.last_stats()["uncertified"] >= 1
