@@ -207,7 +207,7 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     // lists only grow (a few hundred entries); a list that does fill up is compacted exactly
     pl.cap = std::max(1024, pl.kp + 2 * nt);
     pl.keep_max = pl.kp;
-    pl.max_items = std::max(6144, 4 * pl.kp);
+    pl.max_items = std::max(2048, 4 * pl.kp);  // typical survivors: 2-3 k'; overflow is tightened exactly
   } else {
     // thresholds come from compacting full lists: pass 2 holds lists * kp keys in shared memory
     slice_up(std::min(pl.slices, std::max(1, 24576 / kGroups / pl.kp)));
@@ -478,9 +478,9 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   const size_t o_thr = take(lists * sizeof(float));
   const size_t o_qscale = take(nq * sizeof(float));
   const size_t o_qnorm = take(nq * sizeof(float));
-  const size_t o_flags = take(64);
   const size_t o_flist = take(nq * sizeof(int));
   const size_t o_theta = take(nq * sizeof(double));
+  const size_t o_flags = take(256);  // cleared together with the levels right behind it (prep kernel)
   const size_t o_lvl = take(lists * sizeof(uint32_t));
   LXG_CUDA(ix->ws_small.reserve(off));
   // normalised fp32 queries, then the prepared fp16 query blocks
@@ -513,7 +513,14 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.lvl = reinterpret_cast<uint32_t*>(sm + o_lvl);
   sp.lvl_r = pl.lvl_r;
   sp.perf_mode = g_perf_mode;
-  if (sp.lvl_r > 0) LXG_CUDA(cudaMemsetAsync(sp.lvl, 0, lists * sizeof(uint32_t), st));
+  // exact-path workspace (its counters are cleared by the prep kernel as well)
+  const int nflag_max = std::min(nq, 256);
+  const size_t ex_bytes = static_cast<size_t>(nflag_max) * kExactListCap * (sizeof(double) + sizeof(unsigned)) +
+                          static_cast<size_t>(nflag_max) * sizeof(int) + 256;
+  LXG_CUDA(ix->ws_exact.reserve(ex_bytes));
+  double* ex_score = reinterpret_cast<double*>(ix->ws_exact.p);
+  unsigned* ex_row = reinterpret_cast<unsigned*>(ex_score + static_cast<size_t>(nflag_max) * kExactListCap);
+  int* ex_count = reinterpret_cast<int*>(ex_row + static_cast<size_t>(nflag_max) * kExactListCap);
 
   int launches = 0;
   cudaEvent_t* ev = nullptr;
@@ -528,9 +535,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
     ev = &ix->ev_pool[ix->ev_used];
     ix->ev_used += 5;
   }
-  LXG_CUDA(cudaMemsetAsync(flag_count, 0, 64, st));
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
-  prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize);
+  prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(
+      x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize, reinterpret_cast<uint32_t*>(flag_count),
+      64 + (sp.lvl_r > 0 ? static_cast<int>(lists) : 0), reinterpret_cast<uint32_t*>(ex_count), nflag_max);
   LXG_CUDA(cudaGetLastError());
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
@@ -591,18 +599,14 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   if (ev) LXG_CUDA(cudaEventRecord(ev[3], st));
 
   // exact path for uncertified queries (normally zero of them: both kernels exit at once)
-  const int nflag_max = std::min(nq, 256);
-  const size_t ex_bytes = static_cast<size_t>(nflag_max) * kExactListCap * (sizeof(double) + sizeof(unsigned)) +
-                          static_cast<size_t>(nflag_max) * sizeof(int) + 256;
-  LXG_CUDA(ix->ws_exact.reserve(ex_bytes));
   ExactParams ep{};
   ep.xn = xn;
   ep.flag_count = flag_count;
   ep.flag_list = mp.flag_list;
   ep.flag_theta = mp.flag_theta;
-  ep.list_score = reinterpret_cast<double*>(ix->ws_exact.p);
-  ep.list_row = reinterpret_cast<unsigned*>(ep.list_score + static_cast<size_t>(nflag_max) * kExactListCap);
-  ep.list_count = reinterpret_cast<int*>(ep.list_row + static_cast<size_t>(nflag_max) * kExactListCap);
+  ep.list_score = ex_score;
+  ep.list_row = ex_row;
+  ep.list_count = ex_count;
   ep.out_d = D;
   ep.out_i = I;
   ep.out_d64 = D64;
@@ -610,7 +614,6 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   ep.nq = nq;
   ep.k = k;
   ep.nflag_max = nflag_max;
-  LXG_CUDA(cudaMemsetAsync(ep.list_count, 0, nflag_max * sizeof(int), st));
   exact_collect_kernel<<<2 * g_num_sms, 256, d * sizeof(float), st>>>(ep, ix->cv);
   LXG_CUDA(cudaGetLastError());
   exact_finalize_kernel<<<nflag_max, 256, 0, st>>>(ep, ix->cv);

@@ -15,7 +15,7 @@
 
 namespace lxg {
 
-constexpr int kMergeThreads = 256;
+constexpr int kMergeThreads = 128;  // small CTAs: the whole 1024-query batch is resident in one wave
 constexpr int kExactListCap = 16384;  // rows an uncertified query may collect before we give up
 
 struct CorpusView {
@@ -47,24 +47,80 @@ struct MergeParams {
   int max_items;       // capacity of the shared-memory candidate pool
 };
 
-// Exact inner product of one corpus row with a query held in shared memory, computed by a
-// full warp.  Products of an fp32 by an fp16/fp32 value are exact in fp64; the summation order
-// is fixed (lane-strided, then xor tree), so the value is identical wherever it is computed.
-__device__ __forceinline__ double warp_exact_dot(const CorpusView& cv, long long row,
-                                                 const float* __restrict__ xq, int lane) {
-  double acc = 0.0;
+// Exact inner products of R corpus rows with a query held in shared memory, computed by a full
+// warp with all R row gathers in flight.  Products of an fp32 by an fp16/fp32 value are exact in
+// fp64; the summation order is fixed - lane L owns the element quads 4*(L + 32*j)..+3 in
+// increasing j, then an xor tree - so a row's score has the same bits wherever it is computed
+// (merge kernel, exact collectors, any shard).  Rows are read with 8 / 16-byte loads when the
+// layout allows it.
+template <int R>
+__device__ __forceinline__ void warp_exact_dots(const CorpusView& cv, const long long (&row)[R],
+                                                const float* __restrict__ xq, int lane, double (&acc)[R]) {
+#pragma unroll
+  for (int u = 0; u < R; ++u) acc[u] = 0.0;
+  const int d = cv.d;
   if (cv.dtype == 1) {
-    const __half* r = reinterpret_cast<const __half*>(cv.rows) + row * cv.pitch;
-    for (int i = lane; i < cv.d; i += 32)
-      acc = fma(static_cast<double>(__half2float(r[i])), static_cast<double>(xq[i]), acc);
+    const __half* base = reinterpret_cast<const __half*>(cv.rows);
+    const bool vec = (cv.pitch % 4 == 0) && (reinterpret_cast<uintptr_t>(base) % 8 == 0);
+    for (int i = 4 * lane; i < d; i += 128) {
+      float v[R][4];
+      if (vec && i + 3 < d) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(base + row[u] * cv.pitch + i));
+          const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+          const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+          v[u][0] = lo.x, v[u][1] = lo.y, v[u][2] = hi.x, v[u][3] = hi.y;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[u][e] = i + e < d ? __half2float(base[row[u] * cv.pitch + i + e]) : 0.0f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double x = i + e < d ? static_cast<double>(xq[i + e]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < R; ++u) acc[u] = fma(static_cast<double>(v[u][e]), x, acc[u]);
+      }
+    }
   } else {
-    const float* r = reinterpret_cast<const float*>(cv.rows) + row * cv.pitch;
-    for (int i = lane; i < cv.d; i += 32)
-      acc = fma(static_cast<double>(r[i]), static_cast<double>(xq[i]), acc);
+    const float* base = reinterpret_cast<const float*>(cv.rows);
+    const bool vec = (cv.pitch % 4 == 0) && (reinterpret_cast<uintptr_t>(base) % 16 == 0);
+    for (int i = 4 * lane; i < d; i += 128) {
+      float v[R][4];
+      if (vec && i + 3 < d) {
+#pragma unroll
+        for (int u = 0; u < R; ++u) {
+          const float4 w = __ldg(reinterpret_cast<const float4*>(base + row[u] * cv.pitch + i));
+          v[u][0] = w.x, v[u][1] = w.y, v[u][2] = w.z, v[u][3] = w.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < R; ++u)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[u][e] = i + e < d ? base[row[u] * cv.pitch + i + e] : 0.0f;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const double x = i + e < d ? static_cast<double>(xq[i + e]) : 0.0;
+#pragma unroll
+        for (int u = 0; u < R; ++u) acc[u] = fma(static_cast<double>(v[u][e]), x, acc[u]);
+      }
+    }
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  return acc;
+  for (int u = 0; u < R; ++u)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+}
+__device__ __forceinline__ double warp_exact_dot(const CorpusView& cv, long long row,
+                                                 const float* __restrict__ xq, int lane) {
+  const long long rows[1] = {row};
+  double acc[1];
+  warp_exact_dots<1>(cv, rows, xq, lane, acc);
+  return acc[0];
 }
 
 __device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsigned ib) {
@@ -73,7 +129,7 @@ __device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsign
 
 // One CTA per query.  Dynamic shared memory: max_items (score key, row) pairs, then kp
 // (double,uint) pairs, then d floats.
-__global__ void __launch_bounds__(kMergeThreads)
+__global__ void __launch_bounds__(kMergeThreads, 8)
 merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   extern __shared__ __align__(16) uint8_t msm[];
   const int q = blockIdx.x;
@@ -283,36 +339,16 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   }
   __syncthreads();
   const int nsel = s_sel;  // == min(m, kp)
-  // exact re-score: a warp per row, four rows in flight per warp (the rows are random gathers)
+  // exact re-score: four rows in flight per warp (the rows are random gathers from HBM)
   for (int j0 = warp * 4; j0 < nsel; j0 += (kMergeThreads / 32) * 4) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-    if (cv.dtype == 1) {
-      const __half* r[4];
+    long long rows[4];
+    double acc[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u)
-        r[u] = reinterpret_cast<const __half*>(cv.rows) + static_cast<long long>(sel_row[min(j0 + u, nsel - 1)]) * cv.pitch;
-      for (int i = lane; i < cv.d; i += 32) {
-        const double x = static_cast<double>(xq[i]);
+    for (int u = 0; u < 4; ++u) rows[u] = static_cast<long long>(sel_row[min(j0 + u, nsel - 1)]);
+    warp_exact_dots<4>(cv, rows, xq, lane, acc);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fma(static_cast<double>(__half2float(r[u][i])), x, acc[u]);
-      }
-    } else {
-      const float* r[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        r[u] = reinterpret_cast<const float*>(cv.rows) + static_cast<long long>(sel_row[min(j0 + u, nsel - 1)]) * cv.pitch;
-      for (int i = lane; i < cv.d; i += 32) {
-        const double x = static_cast<double>(xq[i]);
-#pragma unroll
-        for (int u = 0; u < 4; ++u) acc[u] = fma(static_cast<double>(r[u][i]), x, acc[u]);
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    for (int u = 0; u < 4; ++u)
       if (lane == 0 && j0 + u < nsel) sel_score[j0 + u] = acc[u];
-    }
   }
   __syncthreads();
   // rank by counting, emit the top k

@@ -104,10 +104,16 @@ __global__ void __launch_bounds__(256) normalize_l2_kernel(float* __restrict__ x
 //   xh  = fp16(xn * 2^e), e chosen so that max|xn * 2^e| lands in [1,2): exact scaling, keeps
 //         fp16 out of the subnormals; rows >= nq and columns >= d are zero,
 //   qscale = 2^e, qnorm = ||xn||_2 rounded up (used only in the certificate's error bound).
+// It also clears the per-search counters (zero_a / zero_b: published levels, flag and exact-list
+// counters) so that a search needs no memset nodes on its stream.
 __global__ void __launch_bounds__(256)
 prep_queries_kernel(const float* __restrict__ x, float* __restrict__ xn, __half* __restrict__ xh,
                     float* __restrict__ qscale, float* __restrict__ qnorm, int nq, int nq_pad, int d,
-                    int dpad, int normalize) {
+                    int dpad, int normalize, uint32_t* __restrict__ zero_a, int zero_a_words,
+                    uint32_t* __restrict__ zero_b, int zero_b_words) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < zero_a_words + zero_b_words; i += gridDim.x * blockDim.x) {
+    if (i < zero_a_words) zero_a[i] = 0u; else zero_b[i - zero_a_words] = 0u;
+  }
   const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= nq_pad) return;
