@@ -399,7 +399,9 @@ def extra_numbers(index, d, k, dev, peaks):
 
     res = {}
     n = index.ntotal
-    for q in (1, 8, 64, 256, 4096):
+    # (Q, k): the batch sweep at the workload's k, plus the reference's own request shape - one
+    # query, faiss_k = 1000 candidates (SearchEngine.search default, engine.py:538)
+    for q, k in ((1, k), (8, k), (64, k), (256, k), (4096, k), (1, 1000)):
         xs = [make_queries_gpu(q, d, dev, seed=100 + s) for s in range(4)]
         for i in range(3):
             index.search_torch(xs[i], k, normalize=True)
@@ -417,7 +419,7 @@ def extra_numbers(index, d, k, dev, peaks):
         tm = index.get_timing()
         index.set_timing(False)
         scan = tm["scan_ms"] / steps
-        res[f"Q={q}"] = {"qps": round(q / (ms / 1e3), 1), "ms_per_step": round(ms, 4), "scan_ms": round(scan, 4),
+        res[f"Q={q}" if (q, k) != (1, 1000) else "Q=1 k=1000 (engine default faiss_k)"] = {"qps": round(q / (ms / 1e3), 1), "ms_per_step": round(ms, 4), "scan_ms": round(scan, 4),
                          "prep_ms": round(tm.get("prep_ms", 0.0) / steps, 4), "merge_ms": round(tm["merge_ms"] / steps, 4),
                          "exact_ms": round(tm["exact_ms"] / steps, 4),
                          "hbm_frac": round(n * d * 2 / (scan / 1e3) / 1e9 / peaks["hbm_gbs"], 4),

@@ -247,6 +247,19 @@ cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, c
   return cudaLaunchKernelEx(&cfg, scan_topk_kernel<N_T, kPair>, kPair ? ix->tmap_pair : ix->tmap, sp);
 }
 
+template <int THREADS>
+cudaError_t launch_merge(int nq, size_t smem, const MergeParams& mp, const CorpusView& cv, cudaStream_t st) {
+  static size_t attr = 0;
+  if (smem > attr) {
+    cudaError_t e = cudaFuncSetAttribute(merge_rescore_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+    attr = smem;
+  }
+  merge_rescore_kernel<THREADS><<<nq, THREADS, smem, st>>>(mp, cv);
+  return cudaGetLastError();
+}
+
 }  // namespace
 
 extern "C" {
@@ -587,13 +600,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.max_items = pl.max_items;
   const size_t msmem = static_cast<size_t>(pl.max_items) * 8 + static_cast<size_t>(pl.kp) * 12 +
                        static_cast<size_t>(d) * 4 + 64;
-  static size_t merge_attr = 0;
-  if (msmem > merge_attr) {
-    LXG_CUDA(cudaFuncSetAttribute(merge_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(msmem)));
-    merge_attr = msmem;
-  }
-  merge_rescore_kernel<<<nq, kMergeThreads, msmem, st>>>(mp, ix->cv);
+  // one CTA per query, sized by the batch (see rescore.cuh)
+  if (nq <= 64) LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
+  else if (nq <= 512) LXG_CUDA((launch_merge<256>(nq, msmem, mp, ix->cv, st)));
+  else LXG_CUDA((launch_merge<128>(nq, msmem, mp, ix->cv, st)));
   LXG_CUDA(cudaGetLastError());
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[3], st));

@@ -15,7 +15,9 @@
 
 namespace lxg {
 
-constexpr int kMergeThreads = 128;  // small CTAs: the whole 1024-query batch is resident in one wave
+// merge_rescore_kernel is one CTA per query; its size is picked by the batch: 128 threads when there
+// are many queries (a 1024-query batch is resident in one wave), up to 1024 threads for a handful of
+// queries, where the gather / re-score of one query is all the parallelism there is.
 constexpr int kExactListCap = 16384;  // rows an uncertified query may collect before we give up
 
 struct CorpusView {
@@ -127,9 +129,10 @@ __device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsign
   return sa > sb || (sa == sb && ia < ib);
 }
 
-// One CTA per query.  Dynamic shared memory: max_items (score key, row) pairs, then kp
-// (double,uint) pairs, then d floats.
-__global__ void __launch_bounds__(kMergeThreads, 8)
+// One CTA (kMergeThreads threads) per query.  Dynamic shared memory: max_items (score key, row)
+// pairs, then kp (double,uint) pairs, then d floats.
+template <int kMergeThreads>
+__global__ void __launch_bounds__(kMergeThreads, kMergeThreads <= 128 ? 8 : (kMergeThreads <= 256 ? 4 : 1))
 merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   extern __shared__ __align__(16) uint8_t msm[];
   const int q = blockIdx.x;
