@@ -157,13 +157,15 @@ struct Plan {
   bool pair;      // CTA pairs (cta_group::2) when there are at least two query blocks
   int grid_x;     // query blocks launched (padded to even in pair mode)
   int lists;      // candidate lists per query: one per slice and epilogue group
-  int lvl_r;      // cross-list level: every list publishes its lvl_r-th best (0 = disabled)
+  int lvl_r;      // cross-list level: every publishing list publishes its lvl_r-th best (0 = disabled)
+  int lvl_stride, lvl_slots;  // every lvl_stride-th list publishes; slots per query
   int max_items;  // pass-2 candidate pool (entries)
 };
 
-// Lists that see at least 8*kTrack rows (the others never publish a level, scan_topk.cuh).  List
-// (slice, g) holds columns [g*gc, (g+1)*gc) of every tile of the slice, gc = tile_rows / kGroups.
-int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_per_slice) {
+// Publishing lists (every stride-th one) that see at least 8*kTrack rows - the others never
+// publish a level (scan_topk.cuh).  List (slice, g) holds columns [g*gc, (g+1)*gc) of every tile of
+// the slice, gc = tile_rows / kGroups.
+int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_per_slice, int stride) {
   const int gc = tile_rows / kGroups;
   int ok = 0;
   for (int s = 0; s < slices; ++s) {
@@ -171,6 +173,7 @@ int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_
     const int te = std::min(num_tiles, tb + tiles_per_slice);
     const int my = std::max(0, te - tb);
     for (int g = 0; g < kGroups; ++g) {
+      if ((s * kGroups + g) % stride != 0) continue;
       long long rows = static_cast<long long>(my) * gc;
       if (my > 0 && te == num_tiles) {
         const long long first = static_cast<long long>(num_tiles - 1) * tile_rows + g * gc;
@@ -200,14 +203,24 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
   };
   slice_up(std::max(1, g_num_sms / pl.grid_x));
   // cross-list level: needs lists * r >= kp with r <= kTrack
-  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice);
+  // with hundreds of lists (one or two query blocks) only every stride-th list publishes, so that a
+  // refresh reads ~32 values per query - as long as that still leaves lists * 8 >= kp
+  pl.lvl_stride = pl.lists > 64 ? (pl.lists + 31) / 32 : 1;
+  int lv = 0;
+  for (;; --pl.lvl_stride) {
+    lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice, pl.lvl_stride);
+    if (pl.lvl_stride == 1 || (lv >= 2 && (pl.kp + lv - 1) / lv <= kTrack)) break;
+  }
+  pl.lvl_slots = (pl.lists + pl.lvl_stride - 1) / pl.lvl_stride;
   pl.lvl_r = lv >= 2 ? (pl.kp + lv - 1) / lv : 0;
   if (pl.lvl_r > kTrack) pl.lvl_r = 0;
   if (pl.lvl_r > 0) {
     // lists only grow (a few hundred entries); a list that does fill up is compacted exactly
     pl.cap = std::max(1024, pl.kp + 2 * nt);
     pl.keep_max = pl.kp;
-    pl.max_items = std::max(2048, 4 * pl.kp);  // typical survivors: 2-3 k'; overflow is tightened exactly
+    // typical survivors: 2-3 k' when every list publishes, ~stride/2 times more when only every
+    // stride-th does (the level then bounds a sample of the corpus); overflow is tightened exactly
+    pl.max_items = std::max(2048, 4 * pl.kp) * (pl.lvl_stride > 1 ? 3 : 1);
   } else {
     // thresholds come from compacting full lists: pass 2 holds lists * kp keys in shared memory
     slice_up(std::min(pl.slices, std::max(1, 24576 / kGroups / pl.kp)));
@@ -525,6 +538,8 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.keep_max = pl.keep_max;
   sp.lvl = reinterpret_cast<uint32_t*>(sm + o_lvl);
   sp.lvl_r = pl.lvl_r;
+  sp.lvl_stride = pl.lvl_stride;
+  sp.lvl_slots = pl.lvl_slots;
   sp.perf_mode = g_perf_mode;
   // exact-path workspace (its counters are cleared by the prep kernel as well)
   const int nflag_max = std::min(nq, 256);
@@ -597,6 +612,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.kp = pl.kp;
   mp.cap = pl.cap;
   mp.lists = pl.lists;
+  mp.lvl_slots = pl.lvl_slots;
   mp.max_items = pl.max_items;
   const size_t msmem = static_cast<size_t>(pl.max_items) * 8 + static_cast<size_t>(pl.kp) * 12 +
                        static_cast<size_t>(d) * 4 + 64;

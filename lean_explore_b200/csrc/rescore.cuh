@@ -35,7 +35,7 @@ struct MergeParams {
   const uint2* cand;
   const int* cand_count;
   const float* slice_thr;
-  const uint32_t* lvl;  // [nq, lists] published levels of pass 1 (nullptr: no cross-list level)
+  const uint32_t* lvl;  // [nq, lvl_slots] published levels of pass 1 (nullptr: no cross-list level)
   const float* xn;
   const float* qscale;
   const float* qnorm;
@@ -45,7 +45,7 @@ struct MergeParams {
   int* flag_count;     // number of uncertified queries
   int* flag_list;      // [nq] their ids
   double* flag_theta;  // [nq] lower bound of the true k-th best exact score
-  int nq, k, kp, cap, lists;
+  int nq, k, kp, cap, lists, lvl_slots;
   int max_items;       // capacity of the shared-memory candidate pool
 };
 
@@ -177,8 +177,9 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     for (int s = tid; s < p.lists; s += kMergeThreads) {
       s_len[s] = p.cand_count[static_cast<size_t>(s) * p.nq + q];
       tk = max(tk, float_to_key(__float_as_uint(p.slice_thr[static_cast<size_t>(s) * p.nq + q])));
-      if (p.lvl != nullptr) lo = min(lo, __ldcg(p.lvl + static_cast<size_t>(q) * p.lists + s));
     }
+    if (p.lvl != nullptr)
+      for (int s = tid; s < p.lvl_slots; s += kMergeThreads) lo = min(lo, __ldcg(p.lvl + static_cast<size_t>(q) * p.lvl_slots + s));
     tk = __reduce_max_sync(0xffffffffu, tk);
     lo = __reduce_min_sync(0xffffffffu, lo);
     if (lane == 0) {

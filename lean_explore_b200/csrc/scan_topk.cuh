@@ -55,8 +55,10 @@ struct ScanParams {
   int* cand_count;    // [lists, nq]
   float* slice_thr;   // [lists, nq] final threshold of the list: every dropped row scored <= it
   float* dbg_scores;  // optional [nq, n] raw tensor-core scores (tests only), else nullptr
-  uint32_t* lvl;      // [nq, lists] ordered key of the lvl_r-th best score the list has seen
-  int lvl_r;          // (#lists with >= 8 kTrack rows) * lvl_r >= kp; 0 disables the cross-list level
+  uint32_t* lvl;      // [nq, lvl_slots] ordered key of the lvl_r-th best score a publishing list has seen
+  int lvl_r;          // (#publishing lists) * lvl_r >= kp; 0 disables the cross-list level
+  int lvl_stride;     // every lvl_stride-th list publishes (slot list / lvl_stride of lvl_slots per query):
+  int lvl_slots;      // with hundreds of lists (few queries) a refresh reads ~32 values instead of all
   int nq, dpad, num_kc;
   int n;
   int num_tiles, slices, tiles_per_slice;
@@ -316,7 +318,8 @@ __device__ __forceinline__ void track_insert(float (&t)[kTrack], float v, bool t
 // Cross-list level: min over the lists of the published r-th best, for the
 // `nlive` queries q0.. of this warp (query q0 + lane gets its value).  lvl is query-major
 // [nq][lists]: the warp reads one query's levels with coalesced loads, 8 queries in flight.
-__device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int lists, int q0, int nlive, int lane) {
+__device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int q0, int nlive, int lane) {
+  const int lists = p.lvl_slots;
   uint32_t mine = kLvlNone;
   for (int b = 0; b < nlive; b += 8) {  // warp-uniform
     uint32_t lo[8];
@@ -609,7 +612,6 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     }
 
     // ---- threshold scan
-    const int lists = p.slices * kGroups;
     const int list_id = slice * kGroups + grp;
     const size_t list = static_cast<size_t>(list_id) * p.nq + (live ? q : 0);
     ListState ls;
@@ -627,7 +629,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     uint32_t* lvl_mine = nullptr;  // where this list publishes its level (query-major [nq][lists])
     const int wq0 = qblock * kQueryBlock + (warp & 3) * 32;   // first query of this warp
     const int wlive = max(0, min(32, p.nq - wq0));            // live queries of this warp
-    if (lvl_r > 0 && live) {
+    if (lvl_r > 0 && live && list_id % p.lvl_stride == 0) {
       // rows this list will see (only the last tile of the corpus can be partial): a list too short
       // to feed its tracker kTrack group maxima never publishes a level and is not counted
       long long rows = static_cast<long long>(my_tiles) * kGroupCols;
@@ -635,7 +637,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupCols;
         rows -= kGroupCols - max(0ll, min(static_cast<long long>(kGroupCols), static_cast<long long>(n) - first));
       }
-      uint32_t* slot = p.lvl + static_cast<size_t>(q) * lists + list_id;
+      uint32_t* slot = p.lvl + static_cast<size_t>(q) * p.lvl_slots + list_id / p.lvl_stride;
       if (rows >= kTrack * 8) lvl_mine = slot; else __stcg(slot, kLvlSkip);
     }
 
@@ -668,7 +670,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const unsigned long long t0 = global_timer_ns();
         float lv;
         do {
-          lv = warp_refresh_level(p, lists, wq0, wlive, lane);
+          lv = warp_refresh_level(p, wq0, wlive, lane);
         } while (!__all_sync(0xffffffffu, !live || lv > -CUDART_INF_F) && global_timer_ns() - t0 < 20000ull);
         if (live && lv > ls.thr) {
           ls.thr = lv;
@@ -723,7 +725,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         const int done = it + 1;
         if (done <= 4 || (done <= 32 && (done & 3) == 0) || (done & 31) == 0) {
           if ((refreshes++ % kGroups) == grp) {
-            const float lv = warp_refresh_level(p, lists, wq0, wlive, lane);
+            const float lv = warp_refresh_level(p, wq0, wlive, lane);
             if (live && lv > ls.thr) {
               ls.thr = lv;
               thr_sh[t] = lv;
