@@ -258,3 +258,34 @@ def test_near_duplicate_heavy_corpus_goes_through_the_exact_path():
     x = corpus[:8].astype(np.float32)
     ix = _check(corpus, x, 25)
     assert ix.last_stats()["uncertified"] >= 1
+
+
+def test_more_queries_than_one_launch_holds():
+    """nq > 148 * 128: lxg_search splits the batch over several launches."""
+    corpus = make_corpus(3000, 64)
+    x = make_queries(19500, 64)
+    _check(corpus, x, 5)
+
+
+def test_concurrent_host_threads_share_one_index():
+    """SURVEY.md section 8(b) threading: calls on one handle from several host threads (the MCP
+    event loop plus its executor) are serialised inside the library and all return exact results."""
+    import threading
+
+    corpus = make_corpus(20000, 128)
+    ix = _index(corpus)
+    xs = [make_queries(50 + 7 * i, 128, seed=40 + i) for i in range(6)]
+    want = [ix.search(x, 10, normalize=True) for x in xs]
+    got = [None] * len(xs)
+
+    def work(i):
+        for _ in range(5):
+            got[i] = ix.search(xs[i], 10, normalize=True)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(len(xs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for (Dw, Iw), (Dg, Ig) in zip(want, got):
+        assert np.array_equal(Iw, Ig) and np.array_equal(Dw, Dg)
