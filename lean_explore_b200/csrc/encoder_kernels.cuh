@@ -131,9 +131,10 @@ enum GemmEpilogue { kEpiStore = 0, kEpiGelu = 1, kEpiResid = 2 };
 constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 128;
 constexpr int kGemmBK = 64;
-constexpr int kGemmStages = 4;
+constexpr int kGemmStages = 6;
 constexpr int kGemmStageBytes = (kGemmBM + kGemmBN) * kGemmBK * 2;  // 32 KB
-constexpr int kGemmThreads = 192;                                   // 4 epilogue warps + TMA + MMA
+constexpr int kGemmEpiWarps = 8;                                    // 2 per TMEM lane quarter (column halves)
+constexpr int kGemmThreads = (kGemmEpiWarps + 2) * 32;              // + TMA warp + MMA warp
 constexpr int kGemmSmem = kGemmStages * kGemmStageBytes + 1024;
 
 struct GemmParams {
@@ -143,39 +144,49 @@ struct GemmParams {
   int m, n, k;
 };
 
+// Persistent, warp-specialised: grid = min(#tiles, #SMs), every CTA walks tiles
+// t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so concurrently running CTAs share a W
+// tile in L2).  Warp 8 streams A / W k-blocks through a 6-stage TMA ring, warp 9 issues
+// tcgen05.mma (SS, M=128 N=128 K=16) into one of TWO TMEM accumulators, warps 0-7 drain the other
+// one (thread = output row, warp >> 2 = column half): the epilogue of tile i (bias, erf-GELU,
+// residual, stores) overlaps the main loop of tile i+1.
 template <int EPI>
-__global__ void __launch_bounds__(kGemmThreads)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kGemmStages];
   __shared__ __align__(8) uint64_t empty_bar[kGemmStages];
-  __shared__ __align__(8) uint64_t acc_bar;
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
   __shared__ uint32_t tmem_base_holder;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * kGemmBM;
-  const int n0 = blockIdx.y * kGemmBN;
+  const int tiles_m = (p.m + kGemmBM - 1) / kGemmBM;
+  const int tiles = tiles_m * (p.n / kGemmBN);
   const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
   const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* ring = smem_raw + (ring_u32 - ptx::smem_u32(smem_raw));
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kGemmBM, kGemmBN);
+  constexpr int kTmaWarp = kGemmEpiWarps, kMmaWarp = kGemmEpiWarps + 1;
 
-  if (warp == 5 && lane == 0) {
+  if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < kGemmStages; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(&acc_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full_bar[a], 1);
+      ptx::mbar_init(&acc_empty_bar[a], kGemmEpiWarps);
+    }
     ptx::fence_barrier_init();
   }
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     if (lane == 0) {
       ptx::prefetch_tensormap(&tmap_a);
       ptx::prefetch_tensormap(&tmap_w);
     }
-    ptx::tmem_alloc(&tmem_base_holder, kGemmBN);
+    ptx::tmem_alloc(&tmem_base_holder, 2 * kGemmBN);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -183,122 +194,312 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
+    const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
+    const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
+    const uint32_t ring0 = ptx::opaque(ring_u32);
     uint32_t stage = 0, phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      ptx::mbar_wait(&empty_bar[stage], phase ^ 1u);
-      if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], kGemmStageBytes);
-        uint8_t* dst = ring + stage * kGemmStageBytes;
-        ptx::tma_load_2d(dst, &tmap_a, kb * kGemmBK, m0, &full_bar[stage], ptx::kEvictFirst);
-        ptx::tma_load_2d(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, &full_bar[stage],
-                         ptx::kEvictLast);
-      }
-      __syncwarp();
-      if (++stage == kGemmStages) {
-        stage = 0;
-        phase ^= 1u;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+      const int m0 = (t % tiles_m) * kGemmBM, n0 = (t / tiles_m) * kGemmBN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t fb = full0 + stage * 8;
+          ptx::mbar_arrive_expect_tx_a(fb, kGemmStageBytes);
+          const uint32_t dst = ring0 + stage * kGemmStageBytes;
+          ptx::tma_load_2d_a(dst, &tmap_a, kb * kGemmBK, m0, fb, ptx::kEvictNormal);
+          ptx::tma_load_2d_a(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, fb, ptx::kEvictLast);
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
+    const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
+    const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
+    const uint32_t afull0 = ptx::opaque(ptx::smem_u32(&acc_full_bar[0]));
+    const uint32_t aempty0 = ptx::opaque(ptx::smem_u32(&acc_empty_bar[0]));
+    const uint32_t desc_lo0 = ptx::opaque(((ring_u32 & 0x3FFFFu) >> 4) | (1u << 16));
+    constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
     uint32_t stage = 0, phase = 0;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      ptx::mbar_wait(&full_bar[stage], phase);
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      ptx::mbar_wait_a(aempty0 + acc * 8, ((it >> 1) & 1) ^ 1u);
       ptx::tc_fence_after();
-      if (ptx::elect_one()) {
-        const uint32_t a_addr = ring_u32 + stage * kGemmStageBytes;
-        const uint64_t adesc = ptx::make_kmajor_sw128_desc(a_addr);
-        const uint64_t bdesc = ptx::make_kmajor_sw128_desc(a_addr + kGemmBM * kGemmBK * 2);
+      const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait_a(full0 + stage * 8, phase);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t lo = desc_lo0 + stage * (kGemmStageBytes >> 4);
 #pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4)
-          ptx::mma_f16_ss(tmem_base, adesc + static_cast<uint64_t>(k4 * 2), bdesc + static_cast<uint64_t>(k4 * 2),
-                          kIdesc, (kb | k4) != 0 ? 1u : 0u);
-        ptx::tc_commit(&empty_bar[stage]);
-        if (kb == num_kb - 1) ptx::tc_commit(&acc_bar);
-      }
-      __syncwarp();
-      if (++stage == kGemmStages) {
-        stage = 0;
-        phase ^= 1u;
+          for (int k4 = 0; k4 < 4; ++k4) {
+            const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (lo + k4 * 2);
+            const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (lo + ((kGemmBM * kGemmBK * 2) >> 4) + k4 * 2);
+            ptx::mma_f16_ss(d_tmem, adesc, bdesc, kIdesc, (kb | k4) != 0 ? 1u : 0u);
+          }
+          ptx::tc_commit_a(empty0 + stage * 8);
+          if (kb == num_kb - 1) ptx::tc_commit_a(afull0 + acc * 8);
+        }
+        __syncwarp();
+        if (++stage == kGemmStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
       }
     }
   } else {
-    // epilogue: thread = output row of the tile
-    const int row = m0 + threadIdx.x;
-    const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
-    ptx::mbar_wait(&acc_bar, 0);
-    ptx::tc_fence_after();
+    // epilogue: thread = output row of the tile, warp >> 2 = which 64 columns
+    const int half = warp >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t afull0 = ptx::opaque(ptx::smem_u32(&acc_full_bar[0]));
+    int it = 0;
+    for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
+      const uint32_t acc = it & 1;
+      const int m0 = (t % tiles_m) * kGemmBM, n0 = (t / tiles_m) * kGemmBN;
+      const int row = m0 + (warp & 3) * 32 + lane;
+      ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
+      ptx::tc_fence_after();
 #pragma unroll 1
-    for (int c = 0; c < kGemmBN / 32; ++c) {
-      uint32_t r[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + c * 32, r);
-      ptx::tc_wait_ld();
-      const int col0 = n0 + c * 32;
-      if (row < p.m && col0 < p.n) {
-        const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-        float v[32];
+      for (int c = half * 2; c < half * 2 + 2; ++c) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + c * 32, r);
+        ptx::tc_wait_ld();
+        const int col0 = n0 + c * 32;
+        if (row < p.m && col0 < p.n) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 bb = __ldg(b4 + j);
-          v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-          v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-          v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-          v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
-        }
-        if constexpr (EPI == kEpiGelu) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
-        }
-        if constexpr (EPI == kEpiResid) {
-          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
-          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 rr = __ldg(r4 + j);
-            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
-            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
-            const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
-            const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
-            o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
-            o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
+            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
+            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
+            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
           }
-        } else {
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+          if constexpr (EPI == kEpiGelu) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            __half2 h;
-            h = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
-            o.x = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-            o.y = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-            o.z = *reinterpret_cast<uint32_t*>(&h);
-            h = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-            o.w = *reinterpret_cast<uint32_t*>(&h);
-            o4[j] = o;
+            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+          }
+          if constexpr (EPI == kEpiResid) {
+            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
+            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 rr = __ldg(r4 + j);
+              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+              const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+              const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
+              const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
+              o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
+              o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
+            }
+          } else {
+            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __half2 h;
+              h = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
+              o.x = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+              o.y = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+              o.z = *reinterpret_cast<uint32_t*>(&h);
+              h = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+              o.w = *reinterpret_cast<uint32_t*>(&h);
+              o4[j] = o;
+            }
           }
         }
       }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);
     }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, kGemmBN);
+    ptx::tmem_dealloc(tmem_base, 2 * kGemmBN);
   }
 }
 
-// ------------------------------------------------------------------ attention
+// ------------------------------------------------------------------ attention (tensor cores)
+// One CTA per (sequence, head), one warp per 16 query rows.  K (row-major) and V (transposed) of
+// the head live in shared memory as fp16; scores and context run on mma.sync m16n8k16 (fp16 in,
+// fp32 accumulate) with an online softmax over blocks of 64 keys, so a sequence of any length up
+// to the position table needs the same registers.  The attention tiles of this model family
+// (S <= 512, head size 32 / 64) are far too small for a 128-row tcgen05 tile; it is < 2 % of the
+// encoder's FLOPs.  Additive -inf key mask and fp32 softmax as transformers.BertModel.
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(256)
+attention_mma_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int hidden,
+                     int heads, __half* __restrict__ ctx) {
+  constexpr int kKSteps = DH / 16;   // k-steps of Q.K^T
+  constexpr int kOTiles = DH / 8;    // n-tiles of the context
+  constexpr int kKPitch = DH + 8;    // halves; (DH+8)/2 words = 4 * odd: conflict-free fragment loads
+  extern __shared__ __align__(16) uint8_t asm_raw[];
+  const int b = blockIdx.x / heads, h = blockIdx.x % heads;
+  const int seq_pad = (seq + 15) & ~15;
+  const int vpitch = seq_pad + 8;
+  __half* ks = reinterpret_cast<__half*>(asm_raw);             // [seq_pad][kKPitch]
+  __half* vt = ks + static_cast<size_t>(seq_pad) * kKPitch;    // [DH][vpitch]  (V transposed)
+  float* bias = reinterpret_cast<float*>(vt + static_cast<size_t>(DH) * vpitch);  // [seq_pad], log2 domain
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t row_stride = static_cast<size_t>(3) * hidden;
+  const __half* base = qkv + static_cast<size_t>(b) * seq * row_stride + h * DH;
+
+  for (int i = threadIdx.x; i < seq_pad * (DH / 2); i += blockDim.x) {
+    const int j = i / (DH / 2), c = i % (DH / 2);
+    __half2 kk = __floats2half2_rn(0.f, 0.f), vv = kk;
+    if (j < seq) {
+      kk = *reinterpret_cast<const __half2*>(base + j * row_stride + hidden + 2 * c);
+      vv = *reinterpret_cast<const __half2*>(base + j * row_stride + 2 * hidden + 2 * c);
+    }
+    *reinterpret_cast<__half2*>(ks + j * kKPitch + 2 * c) = kk;
+    vt[(2 * c) * vpitch + j] = __low2half(vv);
+    vt[(2 * c + 1) * vpitch + j] = __high2half(vv);
+  }
+  for (int j = threadIdx.x; j < seq_pad; j += blockDim.x)
+    bias[j] = (j < seq && mask[b * seq + j] != 0) ? 0.f : -CUDART_INF_F;
+  __syncthreads();
+
+  const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // softmax in base 2
+  for (int rt = warp; rt * 16 < seq_pad; rt += nwarps) {
+    const int r0 = rt * 16 + g, r1 = r0 + 8;
+    // Q fragments (A operand), straight from global memory
+    uint32_t qa[kKSteps][4];
+#pragma unroll
+    for (int kk = 0; kk < kKSteps; ++kk) {
+      const int c = kk * 16 + 2 * t;
+      qa[kk][0] = r0 < seq ? *reinterpret_cast<const uint32_t*>(base + r0 * row_stride + c) : 0u;
+      qa[kk][1] = r1 < seq ? *reinterpret_cast<const uint32_t*>(base + r1 * row_stride + c) : 0u;
+      qa[kk][2] = r0 < seq ? *reinterpret_cast<const uint32_t*>(base + r0 * row_stride + c + 8) : 0u;
+      qa[kk][3] = r1 < seq ? *reinterpret_cast<const uint32_t*>(base + r1 * row_stride + c + 8) : 0u;
+    }
+    float o[kOTiles][4];
+#pragma unroll
+    for (int n = 0; n < kOTiles; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+
+    for (int kb0 = 0; kb0 < seq_pad; kb0 += 64) {
+      const int ntiles = min(8, (seq_pad - kb0) >> 3);  // warp-uniform, even
+      float sc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+        if (j < ntiles) {
+          const __half* kr = ks + (kb0 + j * 8 + g) * kKPitch + 2 * t;
+#pragma unroll
+          for (int kk = 0; kk < kKSteps; ++kk)
+            mma_m16n8k16(sc[j], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16),
+                         *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+        }
+      }
+      // scale + key mask, block row maxima
+      float bm0 = -CUDART_INF_F, bm1 = -CUDART_INF_F;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (j < ntiles) {
+          const float b0 = bias[kb0 + j * 8 + 2 * t], b1 = bias[kb0 + j * 8 + 2 * t + 1];
+          sc[j][0] = sc[j][0] * scale + b0;
+          sc[j][1] = sc[j][1] * scale + b1;
+          sc[j][2] = sc[j][2] * scale + b0;
+          sc[j][3] = sc[j][3] * scale + b1;
+          bm0 = fmaxf(bm0, fmaxf(sc[j][0], sc[j][1]));
+          bm1 = fmaxf(bm1, fmaxf(sc[j][2], sc[j][3]));
+        }
+      }
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+      bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+      bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+      const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+      // every key masked so far: keep exponents finite (the row then sums to 0 and yields 0)
+      const float mu0 = mn0 == -CUDART_INF_F ? 0.f : mn0, mu1 = mn1 == -CUDART_INF_F ? 0.f : mn1;
+      const float corr0 = exp2f(m0 - mu0), corr1 = exp2f(m1 - mu1);
+      m0 = mn0;
+      m1 = mn1;
+      float s0 = 0.f, s1 = 0.f;
+      uint32_t pa[4][4];  // P as A fragments: k-step kk covers keys kb0 + 16 kk .. + 15
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f, p3 = 0.f;
+        if (j < ntiles) {
+          p0 = exp2f(sc[j][0] - mu0);
+          p1 = exp2f(sc[j][1] - mu0);
+          p2 = exp2f(sc[j][2] - mu1);
+          p3 = exp2f(sc[j][3] - mu1);
+        }
+        s0 += p0 + p1;
+        s1 += p2 + p3;
+        pa[j >> 1][(j & 1) * 2] = pack_half2(p0, p1);
+        pa[j >> 1][(j & 1) * 2 + 1] = pack_half2(p2, p3);
+      }
+      l0 = l0 * corr0 + s0;
+      l1 = l1 * corr1 + s1;
+#pragma unroll
+      for (int n = 0; n < kOTiles; ++n) {
+        o[n][0] *= corr0;
+        o[n][1] *= corr0;
+        o[n][2] *= corr1;
+        o[n][3] *= corr1;
+      }
+      // context += P . V
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        if (kk * 2 < ntiles) {
+#pragma unroll
+          for (int n = 0; n < kOTiles; ++n) {
+            const __half* vr = vt + (n * 8 + g) * vpitch + kb0 + kk * 16 + 2 * t;
+            mma_m16n8k16(o[n], pa[kk], *reinterpret_cast<const uint32_t*>(vr), *reinterpret_cast<const uint32_t*>(vr + 8));
+          }
+        }
+      }
+    }
+    // row sums live in the quad
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+    __half* out0 = ctx + (static_cast<size_t>(b) * seq + r0) * hidden + h * DH + 2 * t;
+    __half* out1 = ctx + (static_cast<size_t>(b) * seq + r1) * hidden + h * DH + 2 * t;
+#pragma unroll
+    for (int n = 0; n < kOTiles; ++n) {
+      if (r0 < seq) *reinterpret_cast<__half2*>(out0 + n * 8) = __floats2half2_rn(o[n][0] * inv0, o[n][1] * inv0);
+      if (r1 < seq) *reinterpret_cast<__half2*>(out1 + n * 8) = __floats2half2_rn(o[n][2] * inv1, o[n][3] * inv1);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ attention (scalar fallback)
 // One CTA per (sequence, head); K and V of the head live in shared memory (fp16), one warp per
 // query row at a time: scores over keys (lane = key), fp32 softmax with the additive -inf key
-// mask of BertModel, then context (lane = feature).  CUDA-core kernel: at the query path's
-// S <= 64 attention is < 2 % of the encoder's FLOPs.
+// mask of BertModel, then context (lane = feature).  CUDA-core kernel, used only when the head size is
+// not a multiple of 16 (no shipped model).
 constexpr int kAttnThreads = 256;
 
 __global__ void __launch_bounds__(kAttnThreads)
-attention_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int hidden,
+attention_scalar_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int hidden,
                  int heads, __half* __restrict__ ctx) {
   extern __shared__ __align__(16) uint8_t asm_raw[];
   const int dh = hidden / heads;

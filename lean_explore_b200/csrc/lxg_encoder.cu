@@ -114,8 +114,8 @@ cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmPa
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  dim3 grid((gp.m + kGemmBM - 1) / kGemmBM, gp.n / kGemmBN, 1);
-  gemm_tc_kernel<EPI><<<grid, kGemmThreads, kGemmSmem, st>>>(a, w, gp);
+  const int tiles = ((gp.m + kGemmBM - 1) / kGemmBM) * (gp.n / kGemmBN);
+  gemm_tc_kernel<EPI><<<std::min(tiles, std::max(1, lxg::num_sms())), kGemmThreads, kGemmSmem, st>>>(a, w, gp);
   return cudaGetLastError();
 }
 
@@ -134,13 +134,26 @@ int launch_forward(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
                                               reinterpret_cast<const float*>(e->w.emb_ln_b), e->w.ln_eps, e->h);
   LXG_CUDA(cudaGetLastError());
   ++launches;
-  const int kpitch = dh + 2;
-  const size_t attn_smem = static_cast<size_t>(2) * s * kpitch * sizeof(__half) + static_cast<size_t>(s) * sizeof(float) +
-                           static_cast<size_t>(kAttnThreads / 32) * s * sizeof(float);
-  static size_t attn_attr = 48 * 1024;
-  if (attn_smem > attn_attr) {
-    LXG_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
-    attn_attr = attn_smem;
+  // attention: tensor-core kernel for head sizes 32 / 64 (every shipped model), scalar fallback otherwise
+  const bool attn_mma = dh == 32 || dh == 64;
+  const int seq_pad = (s + 15) / 16 * 16;
+  const int attn_warps = std::min(8, seq_pad / 16);
+  const size_t attn_smem = attn_mma
+      ? static_cast<size_t>(seq_pad) * (dh + 8) * sizeof(__half) + static_cast<size_t>(dh) * (seq_pad + 8) * sizeof(__half) +
+            static_cast<size_t>(seq_pad) * sizeof(float)
+      : static_cast<size_t>(2) * s * (dh + 2) * sizeof(__half) + static_cast<size_t>(s) * sizeof(float) +
+            static_cast<size_t>(kAttnThreads / 32) * s * sizeof(float);
+  if (attn_smem > 200 * 1024) return set_error(LXG_EUNSUPPORTED, "sequence too long for the attention kernel's shared memory");
+  static size_t attn_attr[3] = {48 * 1024, 48 * 1024, 48 * 1024};
+  const int attn_which = !attn_mma ? 0 : (dh == 32 ? 1 : 2);
+  if (attn_smem > attn_attr[attn_which]) {
+    if (attn_which == 0)
+      LXG_CUDA(cudaFuncSetAttribute(attention_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
+    else if (attn_which == 1)
+      LXG_CUDA(cudaFuncSetAttribute(attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
+    else
+      LXG_CUDA(cudaFuncSetAttribute(attention_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
+    attn_attr[attn_which] = attn_smem;
   }
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_bert_layer& L = e->layers[l];
@@ -152,7 +165,12 @@ int launch_forward(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
     gp.n = 3 * H;
     gp.k = H;
     LXG_CUDA(launch_gemm<kEpiStore>(e->map_h, e->map_wqkv[l], gp, st));
-    attention_kernel<<<b * heads, kAttnThreads, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
+    if (attn_which == 1)
+      attention_mma_kernel<32><<<b * heads, attn_warps * 32, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
+    else if (attn_which == 2)
+      attention_mma_kernel<64><<<b * heads, attn_warps * 32, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
+    else
+      attention_scalar_kernel<<<b * heads, kAttnThreads, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
     LXG_CUDA(cudaGetLastError());
     // attention.output.dense + residual -> LayerNorm
     gp.bias = reinterpret_cast<const float*>(L.bo);
