@@ -614,7 +614,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.lists = pl.lists;
   mp.lvl_slots = pl.lvl_slots;
   mp.max_items = pl.max_items;
-  const size_t msmem = static_cast<size_t>(pl.max_items) * 8 + static_cast<size_t>(pl.kp) * 12 +
+  int sort_n = 1;
+  while (sort_n < pl.kp) sort_n <<= 1;
+  mp.sort_n = sort_n;
+  const size_t msmem = static_cast<size_t>(pl.max_items) * 8 + static_cast<size_t>(sort_n) * 12 +
                        static_cast<size_t>(d) * 4 + 64;
   // one CTA per query, sized by the batch (see rescore.cuh)
   if (nq <= 64) LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));

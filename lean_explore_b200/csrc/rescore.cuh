@@ -47,6 +47,7 @@ struct MergeParams {
   double* flag_theta;  // [nq] lower bound of the true k-th best exact score
   int nq, k, kp, cap, lists, lvl_slots;
   int max_items;       // capacity of the shared-memory candidate pool
+  int sort_n;          // kp rounded up to a power of two (bitonic ranking of the re-scored rows)
 };
 
 // Exact inner products of R corpus rows with a query held in shared memory, computed by a full
@@ -138,9 +139,9 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   const int q = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint2* items = reinterpret_cast<uint2*>(msm);  // .x = ordered score key, .y = row
-  double* sel_score = reinterpret_cast<double*>(items + p.max_items);
-  unsigned* sel_row = reinterpret_cast<unsigned*>(sel_score + p.kp);
-  float* xq = reinterpret_cast<float*>(sel_row + p.kp);
+  double* sel_score = reinterpret_cast<double*>(items + p.max_items);  // [sort_n] (kp rounded up to a power of two)
+  unsigned* sel_row = reinterpret_cast<unsigned*>(sel_score + p.sort_n);
+  float* xq = reinterpret_cast<float*>(sel_row + p.sort_n);
   __shared__ int s_cnt[3], s_sel, s_m;
   __shared__ int s_len[kGroups * 148];  // list lengths (kGroups lists per slice, at most 148 slices)
   __shared__ uint32_t s_kmin, s_kmax, s_tkey, s_lvl;
@@ -355,20 +356,39 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
       if (lane == 0 && j0 + u < nsel) sel_score[j0 + u] = acc[u];
   }
   __syncthreads();
-  // rank by counting, emit the top k
+  // rank the re-scored rows by (score desc, row asc): bitonic sort in shared memory (padding
+  // entries sort last), then the first k are the answer
   const int k = p.k;
-  for (int j = tid; j < nsel; j += kMergeThreads) {
-    const double s = sel_score[j];
-    const unsigned r = sel_row[j];
-    int rank = 0;
-    for (int u = 0; u < nsel; ++u) rank += better(sel_score[u], sel_row[u], s, r) ? 1 : 0;
-    if (rank < k) {
-      p.out_d[static_cast<size_t>(q) * k + rank] = static_cast<float>(s);
-      p.out_i[static_cast<size_t>(q) * k + rank] = static_cast<long long>(r) + cv.row_offset;
-      if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + rank] = s;
-      if (rank == k - 1) s_kth = s;
+  for (int j = nsel + tid; j < p.sort_n; j += kMergeThreads) {
+    sel_score[j] = -CUDART_INF;
+    sel_row[j] = 0xFFFFFFFFu;
+  }
+  __syncthreads();
+  for (int size = 2; size <= p.sort_n; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = tid; i < (p.sort_n >> 1); i += kMergeThreads) {
+        const int lo = 2 * i - (i & (stride - 1));  // element whose `stride` bit is clear
+        const int hi = lo + stride;
+        const bool descending = (lo & size) == 0;
+        const double sl = sel_score[lo], sh = sel_score[hi];
+        const unsigned rl = sel_row[lo], rh = sel_row[hi];
+        if (better(sh, rh, sl, rl) == descending) {
+          sel_score[lo] = sh;
+          sel_score[hi] = sl;
+          sel_row[lo] = rh;
+          sel_row[hi] = rl;
+        }
+      }
+      __syncthreads();
     }
   }
+  for (int r = tid; r < min(k, nsel); r += kMergeThreads) {
+    const double sc = sel_score[r];
+    p.out_d[static_cast<size_t>(q) * k + r] = static_cast<float>(sc);
+    p.out_i[static_cast<size_t>(q) * k + r] = static_cast<long long>(sel_row[r]) + cv.row_offset;
+    if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + r] = sc;
+  }
+  if (tid == 0 && nsel >= k) s_kth = sel_score[k - 1];
   for (int r = nsel + tid; r < k; r += kMergeThreads) {  // fewer than k rows: FAISS pads -FLT_MAX / -1
     p.out_d[static_cast<size_t>(q) * k + r] = -FLT_MAX;
     p.out_i[static_cast<size_t>(q) * k + r] = -1;
