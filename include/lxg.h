@@ -167,6 +167,54 @@ int lxg_encoder_last_launches(const lxg_encoder* enc); /* kernels launched by th
 int lxg_encode(lxg_encoder* enc, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,
                int pool, float* out, void* stream);
 
+/* ---- Qwen3-class decoder backbone: embedding model and reranker ------------------------
+ * The two models the reference ships with share one backbone (RMSNorm, rotary positions,
+ * grouped-query causal attention with per-head q/k RMSNorm, SwiGLU):
+ *   lxg_decoder_embed  replaces SentenceTransformer("Qwen/Qwen3-Embedding-0.6B").encode inside
+ *                      EmbeddingClient.embed (src/lean_explore/util/embedding_client.py:58,88-101):
+ *                      transformer -> Pooling(lasttoken) -> Normalize; out [b, hidden] float32.
+ *   lxg_decoder_rerank replaces the AutoModelForCausalLM forward and the true/false softmax of
+ *                      RerankerClient._compute_scores_sync
+ *                      (src/lean_explore/util/reranker_client.py:110-141): scores [b] float32 =
+ *                      softmax([logit_false, logit_true])[1] of the LAST position's logits.
+ * ids / mask are [b, s] int32 (host or device), padded on the left as both reference clients
+ * do (padding_side="left"); right padding is handled too (the last position whose mask is set
+ * is used).  Positions are 0..s-1 over the padded sequence exactly as transformers.Qwen3Model
+ * assigns them when no position_ids are passed.
+ * Device pointers owned by the caller: matrices fp16 row-major [out, in] as nn.Linear stores
+ * them, vectors fp32.  head_dim must be 128, hidden a multiple of 128 and <= 1024, ffn a
+ * multiple of 64. */
+typedef struct lxg_qwen3_layer {
+  const void* ln1;      /* input_layernorm.weight [H] */
+  const void* wqkv;     /* [(heads + 2 kv_heads) * 128, H]: q_proj | k_proj | v_proj stacked */
+  const void* q_norm;   /* self_attn.q_norm.weight [128] */
+  const void* k_norm;   /* self_attn.k_norm.weight [128] */
+  const void* wo;       /* o_proj [H, heads * 128] */
+  const void* ln2;      /* post_attention_layernorm.weight [H] */
+  const void* wgu;      /* [2 F, H]: gate_proj / up_proj rows interleaved in groups of 32
+                           (rows 64 i .. 64 i + 31 = gate[32 i ..], rows 64 i + 32 .. = up[32 i ..]) */
+  const void* wdown;    /* down_proj [H, F] */
+} lxg_qwen3_layer;
+
+typedef struct lxg_qwen3_weights {
+  int32_t hidden, layers, heads, kv_heads, head_dim, ffn, vocab;
+  float rms_eps;
+  const void* tok_emb;    /* embed_tokens [vocab, H] fp16 */
+  const void* lm_head;    /* [vocab, H] fp16 (== tok_emb when tied); NULL for embedding-only use */
+  const void* final_norm; /* norm.weight [H] fp32 */
+  const void* inv_freq;   /* rotary inv_freq [64] fp32, as Qwen3RotaryEmbedding computes it */
+  const lxg_qwen3_layer* layer; /* host array of `layers` entries */
+} lxg_qwen3_weights;
+
+typedef struct lxg_decoder lxg_decoder;
+int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w);
+int lxg_decoder_destroy(lxg_decoder* dec);
+int lxg_decoder_last_launches(const lxg_decoder* dec);
+int lxg_decoder_embed(lxg_decoder* dec, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,
+                      float* out, void* stream);
+int lxg_decoder_rerank(lxg_decoder* dec, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,
+                       int32_t token_true, int32_t token_false, float* scores, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

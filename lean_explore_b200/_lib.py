@@ -59,6 +59,19 @@ class BertWeights(ctypes.Structure):
     ]
 
 
+class Qwen3Layer(ctypes.Structure):
+    _fields_ = [(n, c_void_p) for n in ("ln1", "wqkv", "q_norm", "k_norm", "wo", "ln2", "wgu", "wdown")]
+
+
+class Qwen3Weights(ctypes.Structure):
+    _fields_ = [
+        ("hidden", c_int32), ("layers", c_int32), ("heads", c_int32), ("kv_heads", c_int32),
+        ("head_dim", c_int32), ("ffn", c_int32), ("vocab", c_int32), ("rms_eps", c_float),
+        ("tok_emb", c_void_p), ("lm_head", c_void_p), ("final_norm", c_void_p), ("inv_freq", c_void_p),
+        ("layer", POINTER(Qwen3Layer)),
+    ]
+
+
 # name -> (restype, argtypes); mirrors include/lxg.h one to one (tests/test_abi.py checks it)
 SIGNATURES = {
     "lxg_init": (c_int, [c_int]),
@@ -84,6 +97,12 @@ SIGNATURES = {
     "lxg_encoder_destroy": (c_int, [c_void_p]),
     "lxg_encoder_last_launches": (c_int, [c_void_p]),
     "lxg_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int, c_void_p, c_void_p]),
+    "lxg_decoder_create": (c_int, [POINTER(c_void_p), POINTER(Qwen3Weights)]),
+    "lxg_decoder_destroy": (c_int, [c_void_p]),
+    "lxg_decoder_last_launches": (c_int, [c_void_p]),
+    "lxg_decoder_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "lxg_decoder_rerank": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                                   c_void_p]),
 }
 
 _lock = threading.Lock()

@@ -13,7 +13,7 @@ from pathlib import Path
 PKG_DIR = Path(__file__).resolve().parent
 CSRC = PKG_DIR / "csrc"
 LIB_PATH = PKG_DIR / "liblxg.so"
-SOURCES = ["lxg_search.cu", "lxg_encoder.cu"]
+SOURCES = ["lxg_search.cu", "lxg_encoder.cu", "lxg_decoder.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -1,0 +1,320 @@
+// Kernels of the Qwen3-class decoder backbone shared by the two models the reference ships with:
+// Qwen/Qwen3-Embedding-0.6B (EmbeddingClient, reference src/lean_explore/util/embedding_client.py:58,
+// 97-99: last-token pooling, L2 normalise) and Qwen/Qwen3-Reranker-0.6B (RerankerClient,
+// src/lean_explore/util/reranker_client.py:110-141: "true"/"false" logits of the last token).
+//   tok_emb -> L x [ RMSNorm, QKV GEMM, per-head q/k RMSNorm + RoPE, causal GQA attention,
+//   o_proj GEMM (+= residual), RMSNorm, gate|up GEMM + SwiGLU, down GEMM (+= residual) ] -> RMSNorm
+// exactly as transformers.Qwen3Model computes it (pre-norm, no biases, rotate_half RoPE with
+// position = index in the padded sequence, causal AND key-padding mask).  The residual stream is
+// fp32; GEMM operands are fp16, every norm / softmax / accumulation is fp32.  The GEMMs are
+// gemm_tc_kernel (encoder_kernels.cuh) with the kEpiStore / kEpiAccF32 / kEpiSwiGLU epilogues.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "encoder_kernels.cuh"
+
+namespace lxg {
+
+// ------------------------------------------------------------------ RMSNorm
+// One warp per token: out = x * rsqrt(mean(x^2) + eps) * w   (fp32 in, fp16 out).  With ids != NULL
+// the row is first gathered from the token-embedding table and written to the residual stream
+// (the first layer's input_layernorm fused with embed_tokens).
+static __global__ void __launch_bounds__(256)
+rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __half* __restrict__ tok_emb, int vocab,
+               int tokens, int hidden, const float* __restrict__ w, float eps, __half* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  constexpr int kMax = 16;  // hidden <= 1024
+  float2 v[kMax];
+  const int n2 = hidden >> 1;
+  float2* x2 = reinterpret_cast<float2*>(resid + static_cast<size_t>(t) * hidden);
+  float ss = 0.f;
+  if (ids != nullptr) {
+    int id = ids[t];
+    id = min(max(id, 0), vocab - 1);
+    const __half2* e2 = reinterpret_cast<const __half2*>(tok_emb + static_cast<size_t>(id) * hidden);
+#pragma unroll
+    for (int i = 0; i < kMax; ++i) {
+      const int j = i * 32 + lane;
+      v[i] = make_float2(0.f, 0.f);
+      if (j < n2) {
+        v[i] = __half22float2(e2[j]);
+        x2[j] = v[i];
+        ss += v[i].x * v[i].x + v[i].y * v[i].y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kMax; ++i) {
+      const int j = i * 32 + lane;
+      v[i] = make_float2(0.f, 0.f);
+      if (j < n2) {
+        v[i] = x2[j];
+        ss += v[i].x * v[i].x + v[i].y * v[i].y;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / hidden + eps);
+  __half2* o2 = reinterpret_cast<__half2*>(out + static_cast<size_t>(t) * hidden);
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n2) {
+      const float2 ww = reinterpret_cast<const float2*>(w)[j];
+      o2[j] = __floats2half2_rn(v[i].x * rstd * ww.x, v[i].y * rstd * ww.y);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ q/k head RMSNorm + RoPE
+// In place on the QKV projection [tokens, (heads + 2 kv_heads) * 128] (fp16): one warp per
+// (token, q or k head).  Lane l holds features l, l+32, l+64, l+96 so both rotate_half partners
+// (i, i+64) sit in the same lane.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
+// with HF's fp32 inv_freq table (Qwen3RotaryEmbedding).
+static __global__ void __launch_bounds__(256)
+qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, int kv_heads,
+                    const float* __restrict__ q_w, const float* __restrict__ k_w,
+                    const float* __restrict__ inv_freq, float eps) {
+  constexpr int DH = 128;
+  const int lane = threadIdx.x & 31;
+  const int nh = heads + kv_heads;
+  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= static_cast<long long>(tokens) * nh) return;
+  const int t = static_cast<int>(wid / nh), h = static_cast<int>(wid % nh);
+  const float* w = h < heads ? q_w : k_w;
+  __half* p = qkv + static_cast<size_t>(t) * (heads + 2 * kv_heads) * DH + static_cast<size_t>(h) * DH;
+  float x[4];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    x[i] = __half2float(p[lane + 32 * i]);
+    ss += x[i] * x[i];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / DH + eps);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = x[i] * rstd * w[lane + 32 * i];
+  const float pos = static_cast<float>(t % seq);
+  float s0, c0, s1, c1;
+  sincosf(pos * inv_freq[lane], &s0, &c0);
+  sincosf(pos * inv_freq[lane + 32], &s1, &c1);
+  p[lane] = __float2half_rn(x[0] * c0 - x[2] * s0);
+  p[lane + 64] = __float2half_rn(x[2] * c0 + x[0] * s0);
+  p[lane + 32] = __float2half_rn(x[1] * c1 - x[3] * s1);
+  p[lane + 96] = __float2half_rn(x[3] * c1 + x[1] * s1);
+}
+
+// ------------------------------------------------------------------ causal GQA attention
+// Flash-style: one CTA per (128 query rows, q head, sequence); warp w owns 16 query rows.  Keys and
+// values of the head's KV group are streamed through shared memory in chunks of 64 keys (both
+// row-major; the P.V operand is read transposed with ldmatrix.trans), scores and context run on
+// mma.sync m16n8k16 with an fp32 online softmax.  Key j is visible to query i iff j <= i and mask[j] != 0 (HF create_causal_mask with a
+// padding mask); rows with no visible key (left padding) yield 0 and are never read downstream.
+constexpr int kCausalRows = 128;
+constexpr int kCausalKeys = 64;
+
+template <int DH>
+__global__ void __launch_bounds__(256)
+attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int heads,
+                        int kv_heads, __half* __restrict__ ctx) {
+  constexpr int kKSteps = DH / 16;
+  constexpr int kOTiles = DH / 8;
+  constexpr int kKPitch = DH + 8;
+  __shared__ __align__(16) __half ks[kCausalKeys * kKPitch];
+  __shared__ __align__(16) __half vs[kCausalKeys * kKPitch];
+  __shared__ float bias[kCausalKeys];
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (heads / kv_heads);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t row_stride = static_cast<size_t>(heads + 2 * kv_heads) * DH;
+  const __half* base = qkv + static_cast<size_t>(b) * seq * row_stride;
+  const __half* qbase = base + static_cast<size_t>(h) * DH;
+  const __half* kbase = base + static_cast<size_t>(heads + kvh) * DH;
+  const __half* vbase = base + static_cast<size_t>(heads + kv_heads + kvh) * DH;
+  const int wrow0 = qb * kCausalRows + warp * 16;  // first query row of this warp
+  const int r0 = wrow0 + g, r1 = r0 + 8;
+  const bool active = wrow0 < seq;
+
+  uint32_t qa[kKSteps][4];
+#pragma unroll
+  for (int kk = 0; kk < kKSteps; ++kk) {
+    const int c = kk * 16 + 2 * t;
+    qa[kk][0] = (active && r0 < seq) ? *reinterpret_cast<const uint32_t*>(qbase + r0 * row_stride + c) : 0u;
+    qa[kk][1] = (active && r1 < seq) ? *reinterpret_cast<const uint32_t*>(qbase + r1 * row_stride + c) : 0u;
+    qa[kk][2] = (active && r0 < seq) ? *reinterpret_cast<const uint32_t*>(qbase + r0 * row_stride + c + 8) : 0u;
+    qa[kk][3] = (active && r1 < seq) ? *reinterpret_cast<const uint32_t*>(qbase + r1 * row_stride + c + 8) : 0u;
+  }
+  float o[kOTiles][4];
+#pragma unroll
+  for (int n = 0; n < kOTiles; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+  float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
+  const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // softmax in base 2
+  const uint32_t smem_vs = ptx::smem_u32(vs);
+
+  const int key_end = min(seq, (qb + 1) * kCausalRows);  // causal: no key beyond the block's last row
+  for (int kb0 = 0; kb0 < key_end; kb0 += kCausalKeys) {
+    __syncthreads();  // previous chunk fully consumed
+    for (int i = threadIdx.x; i < kCausalKeys * (DH / 8); i += blockDim.x) {
+      const int j = i / (DH / 8), c = i % (DH / 8);
+      uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
+      if (kb0 + j < seq) {
+        kk = *reinterpret_cast<const uint4*>(kbase + (kb0 + j) * row_stride + 8 * c);
+        vv = *reinterpret_cast<const uint4*>(vbase + (kb0 + j) * row_stride + 8 * c);
+      }
+      *reinterpret_cast<uint4*>(ks + j * kKPitch + 8 * c) = kk;
+      *reinterpret_cast<uint4*>(vs + j * kKPitch + 8 * c) = vv;
+    }
+    for (int j = threadIdx.x; j < kCausalKeys; j += blockDim.x)
+      bias[j] = (kb0 + j < seq && mask[b * seq + kb0 + j] != 0) ? 0.f : -CUDART_INF_F;
+    __syncthreads();
+    if (!active || kb0 > wrow0 + 15) continue;  // warp-uniform: chunk entirely in this warp's future
+
+    float sc[8][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
+      const __half* kr = ks + (j * 8 + g) * kKPitch + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < kKSteps; ++kk)
+        mma_m16n8k16(sc[j], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16),
+                     *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+    }
+    float bm0 = -CUDART_INF_F, bm1 = -CUDART_INF_F;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int key0 = kb0 + j * 8 + 2 * t;
+      const float b0 = bias[j * 8 + 2 * t], b1 = bias[j * 8 + 2 * t + 1];
+      sc[j][0] = key0 <= r0 ? sc[j][0] * scale + b0 : -CUDART_INF_F;
+      sc[j][1] = key0 + 1 <= r0 ? sc[j][1] * scale + b1 : -CUDART_INF_F;
+      sc[j][2] = key0 <= r1 ? sc[j][2] * scale + b0 : -CUDART_INF_F;
+      sc[j][3] = key0 + 1 <= r1 ? sc[j][3] * scale + b1 : -CUDART_INF_F;
+      bm0 = fmaxf(bm0, fmaxf(sc[j][0], sc[j][1]));
+      bm1 = fmaxf(bm1, fmaxf(sc[j][2], sc[j][3]));
+    }
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+    bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+    bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+    const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);
+    const float mu0 = mn0 == -CUDART_INF_F ? 0.f : mn0, mu1 = mn1 == -CUDART_INF_F ? 0.f : mn1;
+    const float corr0 = exp2f(m0 - mu0), corr1 = exp2f(m1 - mu1);
+    m0 = mn0;
+    m1 = mn1;
+    float s0 = 0.f, s1 = 0.f;
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float p0 = exp2f(sc[j][0] - mu0), p1 = exp2f(sc[j][1] - mu0);
+      const float p2 = exp2f(sc[j][2] - mu1), p3 = exp2f(sc[j][3] - mu1);
+      s0 += p0 + p1;
+      s1 += p2 + p3;
+      pa[j >> 1][(j & 1) * 2] = pack_half2(p0, p1);
+      pa[j >> 1][(j & 1) * 2 + 1] = pack_half2(p2, p3);
+    }
+    l0 = l0 * corr0 + s0;
+    l1 = l1 * corr1 + s1;
+#pragma unroll
+    for (int n = 0; n < kOTiles; ++n) {
+      o[n][0] *= corr0;
+      o[n][1] *= corr0;
+      o[n][2] *= corr1;
+      o[n][3] *= corr1;
+    }
+    // context += P . V: B fragments of two feature tiles per ldmatrix.x4.trans
+    // (lanes 0-15: keys kk*16 + lane of tile n, lanes 16-31: the same keys of tile n + 1)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const uint32_t vrow = smem_vs + static_cast<uint32_t>(((kk * 16 + (lane & 15)) * kKPitch + (lane >> 4) * 8) * 2);
+#pragma unroll
+      for (int n = 0; n < kOTiles; n += 2) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(vrow + n * 16));
+        mma_m16n8k16(o[n], pa[kk], b0, b1);
+        mma_m16n8k16(o[n + 1], pa[kk], b2, b3);
+      }
+    }
+  }
+  if (!active) return;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
+  const size_t ctx_stride = static_cast<size_t>(heads) * DH;
+  __half* out0 = ctx + (static_cast<size_t>(b) * seq + r0) * ctx_stride + h * DH + 2 * t;
+  __half* out1 = ctx + (static_cast<size_t>(b) * seq + r1) * ctx_stride + h * DH + 2 * t;
+#pragma unroll
+  for (int n = 0; n < kOTiles; ++n) {
+    if (r0 < seq) *reinterpret_cast<__half2*>(out0 + n * 8) = __floats2half2_rn(o[n][0] * inv0, o[n][1] * inv0);
+    if (r1 < seq) *reinterpret_cast<__half2*>(out1 + n * 8) = __floats2half2_rn(o[n][2] * inv1, o[n][3] * inv1);
+  }
+}
+
+// ------------------------------------------------------------------ heads on the last token
+// One CTA per sequence.  The last token is the last position whose mask is set (position S-1
+// under the left padding both reference clients use; the mask-based index also covers right
+// padding, as sentence-transformers' Pooling(lasttoken) does).  Final RMSNorm in fp32, then
+//   mode 0 (embedding): out[b, :] = x / max(||x||, 1e-12)       (Pooling(lasttoken) + Normalize)
+//   mode 1 (reranker) : out[b] = softmax([false, true] logits)[1] with logits = x . lm_head[token]
+//                       (reranker_client.py:127-139)
+static __global__ void __launch_bounds__(256)
+last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ mask, int seq, int hidden,
+                       const float* __restrict__ norm_w, float eps, int mode, const __half* __restrict__ lm_head,
+                       int token_true, int token_false, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  __shared__ float red[3][8];
+  __shared__ int s_last;
+  extern __shared__ float xs[];
+  if (threadIdx.x == 0) {
+    int last = seq - 1;
+    while (last > 0 && mask[b * seq + last] == 0) --last;
+    s_last = last;
+  }
+  __syncthreads();
+  const float* x = resid + (static_cast<size_t>(b) * seq + s_last) * hidden;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  auto block_sum = [&](float v, int slot) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[slot][warp] = v;
+    __syncthreads();
+    float tot = 0.f;
+    for (int w = 0; w < nwarps; ++w) tot += red[slot][w];
+    __syncthreads();
+    return tot;
+  };
+  float ss = 0.f;
+  for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+    const float v = x[c];
+    xs[c] = v;
+    ss += v * v;
+  }
+  const float rstd = rsqrtf(block_sum(ss, 0) / hidden + eps);
+  float n2 = 0.f, dt = 0.f, df = 0.f;
+  for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
+    const float v = xs[c] * rstd * norm_w[c];
+    xs[c] = v;
+    n2 += v * v;
+    if (mode == 1) {
+      dt += v * __half2float(lm_head[static_cast<size_t>(token_true) * hidden + c]);
+      df += v * __half2float(lm_head[static_cast<size_t>(token_false) * hidden + c]);
+    }
+  }
+  if (mode == 0) {
+    const float inv = 1.f / fmaxf(sqrtf(block_sum(n2, 0)), 1e-12f);
+    for (int c = threadIdx.x; c < hidden; c += blockDim.x) out[static_cast<size_t>(b) * hidden + c] = xs[c] * inv;
+  } else {
+    const float lt = block_sum(dt, 1), lf = block_sum(df, 2);
+    if (threadIdx.x == 0) out[b] = 1.f / (1.f + expf(lf - lt));
+  }
+}
+
+}  // namespace lxg

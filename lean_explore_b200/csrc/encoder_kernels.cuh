@@ -20,7 +20,7 @@ namespace lxg {
 
 // ------------------------------------------------------------------ embeddings + LayerNorm
 // One warp per token.  out = LN(word[id] + pos[s] + type[0]) * g + b   (fp16)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 embed_ln_kernel(const int* __restrict__ ids, int tokens, int seq, int hidden, int vocab,
                 const __half* __restrict__ word, const __half* __restrict__ pos,
                 const __half* __restrict__ type0, const float* __restrict__ g,
@@ -75,7 +75,7 @@ embed_ln_kernel(const int* __restrict__ ids, int tokens, int seq, int hidden, in
 }
 
 // ------------------------------------------------------------------ LayerNorm (fp32 in, fp16 out)
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int tokens, int hidden, const float* __restrict__ g,
                  const float* __restrict__ b, float eps, __half* __restrict__ out) {
   const int lane = threadIdx.x & 31;
@@ -121,12 +121,21 @@ layernorm_kernel(const float* __restrict__ x, int tokens, int hidden, const floa
   }
 }
 
+__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
+  const __half2 h = __floats2half2_rn(x, y);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 // ------------------------------------------------------------------ tcgen05 GEMM
 // C[M, N] = epi(A[M, K] . W[N, K]^T + bias[N])
 //   kEpiStore : fp16 out                     (QKV projection)
 //   kEpiGelu  : erf-GELU, fp16 out           (intermediate.dense)
 //   kEpiResid : + residual fp16 [M, N], fp32 out   (attention.output.dense / output.dense, pre-LN)
-enum GemmEpilogue { kEpiStore = 0, kEpiGelu = 1, kEpiResid = 2 };
+//   kEpiAccF32: out fp32 [M, N] += result    (decoder o_proj / down_proj onto the fp32 residual stream)
+//   kEpiSwiGLU: silu(gate) * up, fp16 out [M, N/2]; W rows interleaved per 128-row tile as
+//               gate[32] | up[32] | gate[32] | up[32] so one thread holds both halves of a column
+// bias may be NULL (decoder projections have none).
+enum GemmEpilogue { kEpiStore = 0, kEpiGelu = 1, kEpiResid = 2, kEpiAccF32 = 3, kEpiSwiGLU = 4 };
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 128;
@@ -264,55 +273,96 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m0 + (warp & 3) * 32 + lane;
       ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-#pragma unroll 1
-      for (int c = half * 2; c < half * 2 + 2; ++c) {
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + c * 32, r);
+      if constexpr (EPI == kEpiSwiGLU) {
+        uint32_t rg[32], ru[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + (half * 2) * 32, rg);
+        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + (half * 2 + 1) * 32, ru);
         ptx::tc_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (row < p.m && col0 < p.n) {
-          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+        if (row < p.m) {
+          const int ocol = (n0 >> 1) + half * 32;
+          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * (p.n >> 1) + ocol);
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = __ldg(b4 + j);
-            v[4 * j + 0] = __uint_as_float(r[4 * j + 0]) + bb.x;
-            v[4 * j + 1] = __uint_as_float(r[4 * j + 1]) + bb.y;
-            v[4 * j + 2] = __uint_as_float(r[4 * j + 2]) + bb.z;
-            v[4 * j + 3] = __uint_as_float(r[4 * j + 3]) + bb.w;
+          for (int j = 0; j < 32; ++j) {
+            const float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+            v[j] = fminf(fmaxf(g / (1.0f + __expf(-g)) * u, -65504.f), 65504.f);
           }
-          if constexpr (EPI == kEpiGelu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_half2(v[8 * j], v[8 * j + 1]);
+            o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+            o4[j] = o;
           }
-          if constexpr (EPI == kEpiResid) {
-            const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
-            float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const uint4 rr = __ldg(r4 + j);
-              const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
-              const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
-              const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
-              const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
-              o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
-              o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
+        }
+      } else {
+  #pragma unroll 1
+        for (int c = half * 2; c < half * 2 + 2; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + c * 32, r);
+          ptx::tc_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (row < p.m && col0 < p.n) {
+            float v[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias != nullptr) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 bb = __ldg(b4 + j);
+                v[4 * j + 0] += bb.x;
+                v[4 * j + 1] += bb.y;
+                v[4 * j + 2] += bb.z;
+                v[4 * j + 3] += bb.w;
+              }
             }
-          } else {
-            uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __half2 h;
-              h = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
-              o.x = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-              o.y = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-              o.z = *reinterpret_cast<uint32_t*>(&h);
-              h = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-              o.w = *reinterpret_cast<uint32_t*>(&h);
-              o4[j] = o;
+            if constexpr (EPI == kEpiGelu) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+            }
+            if constexpr (EPI == kEpiResid) {
+              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 rr = __ldg(r4 + j);
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+                const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
+                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
+                o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
+                o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
+              }
+            } else if constexpr (EPI == kEpiAccF32) {
+              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+  #pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 o = o4[j];
+                o.x += v[4 * j + 0];
+                o.y += v[4 * j + 1];
+                o.z += v[4 * j + 2];
+                o.w += v[4 * j + 3];
+                o4[j] = o;
+              }
+            } else {
+              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                __half2 h;
+                h = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
+                o.x = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+                o.y = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+                o.z = *reinterpret_cast<uint32_t*>(&h);
+                h = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
+                o.w = *reinterpret_cast<uint32_t*>(&h);
+                o4[j] = o;
+              }
             }
           }
         }
@@ -342,10 +392,6 @@ __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], const uint32_t (&a)[
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack_half2(float x, float y) {
-  const __half2 h = __floats2half2_rn(x, y);
-  return *reinterpret_cast<const uint32_t*>(&h);
 }
 
 template <int DH>
@@ -498,7 +544,7 @@ attention_mma_kernel(const __half* __restrict__ qkv, const int* __restrict__ mas
 // not a multiple of 16 (no shipped model).
 constexpr int kAttnThreads = 256;
 
-__global__ void __launch_bounds__(kAttnThreads)
+static __global__ void __launch_bounds__(kAttnThreads)
 attention_scalar_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int hidden,
                  int heads, __half* __restrict__ ctx) {
   extern __shared__ __align__(16) uint8_t asm_raw[];
@@ -579,7 +625,7 @@ attention_scalar_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
 // ------------------------------------------------------------------ pooling + L2 normalise
 // sentence-transformers Pooling (mean over unmasked tokens, clamp(sum_mask, 1e-9) / CLS) followed
 // by Normalize (x / max(||x||_2, 1e-12)).  One CTA per sequence, fp32 output.
-__global__ void __launch_bounds__(256)
+static __global__ void __launch_bounds__(256)
 pool_normalize_kernel(const __half* __restrict__ hs, const int* __restrict__ mask, int seq, int hidden,
                       int pool_cls, float* __restrict__ out) {
   const int b = blockIdx.x;

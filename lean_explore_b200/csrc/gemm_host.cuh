@@ -1,0 +1,43 @@
+// Host-side helpers shared by the encoder / decoder entry points: tensor maps of the GEMM
+// operands and the launch of gemm_tc_kernel.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/lxg.h"
+#include "common.h"
+#include "encoder_kernels.cuh"
+
+namespace lxg {
+
+inline int make_map(CUtensorMap* m, const void* base, int rows, int cols) {
+  // row-major fp16 [rows, cols]; box = 64 columns x 128 rows, 128-byte swizzle
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * sizeof(__half)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(kGemmBM)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = lxg::encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
+                                      box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LXG_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string(r));
+  return LXG_OK;
+}
+
+template <int EPI>
+inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int tiles = ((gp.m + kGemmBM - 1) / kGemmBM) * (gp.n / kGemmBN);
+  gemm_tc_kernel<EPI><<<std::min(tiles, std::max(1, lxg::num_sms())), kGemmThreads, kGemmSmem, st>>>(a, w, gp);
+  return cudaGetLastError();
+}
+
+}  // namespace lxg

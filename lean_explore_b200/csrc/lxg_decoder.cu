@@ -1,0 +1,307 @@
+// Qwen3-class decoder entry points of the C ABI (include/lxg.h): host logic only - workspace,
+// tensor maps, launch sequence, CUDA-graph replay.  lxg_decoder_embed replaces
+// SentenceTransformer.encode for the shipped Qwen/Qwen3-Embedding-0.6B (reference
+// src/lean_explore/util/embedding_client.py:58,88-101), lxg_decoder_rerank replaces the
+// AutoModelForCausalLM forward + true/false softmax of RerankerClient._compute_scores_sync
+// (src/lean_explore/util/reranker_client.py:110-141).
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lxg.h"
+#include "common.h"
+#include "decoder_kernels.cuh"
+#include "gemm_host.cuh"
+
+using namespace lxg;
+
+struct lxg_decoder {
+  lxg_qwen3_weights w{};
+  std::vector<lxg_qwen3_layer> layers;
+  std::mutex mu;
+  int cap_tokens = 0;
+  float* resid = nullptr;                                          // fp32 residual stream [cap, H]
+  __half *hn = nullptr, *qkv = nullptr, *ctx = nullptr, *act = nullptr;  // normed rows, QKV, context, SwiGLU output
+  int *ids = nullptr, *mask = nullptr;
+  CUtensorMap map_hn{}, map_ctx{}, map_act{};
+  std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
+  int launches = 0;
+  struct Graph {
+    int b, s, mode, tt, tf;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Graph> graphs;
+  bool use_graphs = true;
+  float* out_buf = nullptr;
+  size_t out_cap = 0;  // floats
+  cudaStream_t own = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+};
+
+namespace {
+
+constexpr int kHeadDim = 128;
+
+void drop_graphs(lxg_decoder* e) {
+  for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
+  e->graphs.clear();
+}
+
+void free_ws(lxg_decoder* e) {
+  drop_graphs(e);
+  cudaFree(e->resid);
+  cudaFree(e->hn);
+  cudaFree(e->qkv);
+  cudaFree(e->ctx);
+  cudaFree(e->act);
+  cudaFree(e->ids);
+  cudaFree(e->mask);
+  e->resid = nullptr;
+  e->hn = e->qkv = e->ctx = e->act = nullptr;
+  e->ids = e->mask = nullptr;
+  e->cap_tokens = 0;
+}
+
+int reserve_ws(lxg_decoder* e, int tokens) {
+  if (tokens <= e->cap_tokens) return LXG_OK;
+  free_ws(e);
+  const size_t cap = (static_cast<size_t>(std::max(tokens, 256)) + 127) / 128 * 128;
+  const size_t H = e->w.hidden, F = e->w.ffn;
+  const size_t QKV = static_cast<size_t>(e->w.heads + 2 * e->w.kv_heads) * kHeadDim, C = static_cast<size_t>(e->w.heads) * kHeadDim;
+  LXG_CUDA(cudaMalloc(&e->resid, cap * H * sizeof(float)));
+  LXG_CUDA(cudaMalloc(&e->hn, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->qkv, cap * QKV * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->ctx, cap * C * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->act, cap * F * sizeof(__half)));
+  LXG_CUDA(cudaMalloc(&e->ids, cap * sizeof(int)));
+  LXG_CUDA(cudaMalloc(&e->mask, cap * sizeof(int)));
+  // rows beyond the live tokens are read by TMA (never stored): keep them finite
+  LXG_CUDA(cudaMemset(e->hn, 0, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMemset(e->ctx, 0, cap * C * sizeof(__half)));
+  LXG_CUDA(cudaMemset(e->act, 0, cap * F * sizeof(__half)));
+  int rc;
+  if ((rc = make_map(&e->map_hn, e->hn, static_cast<int>(cap), static_cast<int>(H))) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_ctx, e->ctx, static_cast<int>(cap), static_cast<int>(C))) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_act, e->act, static_cast<int>(cap), static_cast<int>(F))) != LXG_OK) return rc;
+  e->cap_tokens = static_cast<int>(cap);
+  return LXG_OK;
+}
+
+// 1 + 8 * layers + 1 launches on `st`, workspace pointers only (graph-capturable).
+int launch_forward(lxg_decoder* e, int b, int s, int mode, int tt, int tf, cudaStream_t st) {
+  const int tokens = b * s;
+  const int H = e->w.hidden, F = e->w.ffn, heads = e->w.heads, kvh = e->w.kv_heads;
+  const int QKV = (heads + 2 * kvh) * kHeadDim, C = heads * kHeadDim;
+  const float eps = e->w.rms_eps;
+  int launches = 0;
+  const int row_blocks = (tokens + 7) / 8;
+  const long long rope_warps = static_cast<long long>(tokens) * (heads + kvh);
+  const int rope_blocks = static_cast<int>((rope_warps + 7) / 8);
+  const dim3 attn_grid((s + kCausalRows - 1) / kCausalRows, heads, b);
+  for (int l = 0; l < e->w.layers; ++l) {
+    const lxg_qwen3_layer& L = e->layers[l];
+    // input_layernorm (layer 0: fused with the embed_tokens gather)
+    rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, l == 0 ? e->ids : nullptr, reinterpret_cast<const __half*>(e->w.tok_emb),
+                                               e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn);
+    LXG_CUDA(cudaGetLastError());
+    GemmParams gp{};
+    gp.bias = nullptr;
+    gp.residual = nullptr;
+    gp.m = tokens;
+    // q_proj | k_proj | v_proj
+    gp.out = e->qkv;
+    gp.n = QKV;
+    gp.k = H;
+    LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st));
+    qk_norm_rope_kernel<<<rope_blocks, 256, 0, st>>>(e->qkv, tokens, s, heads, kvh, reinterpret_cast<const float*>(L.q_norm),
+                                                     reinterpret_cast<const float*>(L.k_norm),
+                                                     reinterpret_cast<const float*>(e->w.inv_freq), eps);
+    LXG_CUDA(cudaGetLastError());
+    attention_causal_kernel<kHeadDim><<<attn_grid, 256, 0, st>>>(e->qkv, e->mask, s, heads, kvh, e->ctx);
+    LXG_CUDA(cudaGetLastError());
+    // o_proj, accumulated onto the residual stream
+    gp.out = e->resid;
+    gp.n = H;
+    gp.k = C;
+    LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st));
+    rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, nullptr, nullptr, 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps,
+                                               e->hn);
+    LXG_CUDA(cudaGetLastError());
+    // gate_proj | up_proj (interleaved) + SwiGLU
+    gp.out = e->act;
+    gp.n = 2 * F;
+    gp.k = H;
+    LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st));
+    // down_proj, accumulated onto the residual stream
+    gp.out = e->resid;
+    gp.n = H;
+    gp.k = F;
+    LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st));
+    launches += 8;
+  }
+  last_token_head_kernel<<<b, 256, H * sizeof(float), st>>>(e->resid, e->mask, s, H, reinterpret_cast<const float*>(e->w.final_norm),
+                                                            eps, mode, reinterpret_cast<const __half*>(e->w.lm_head), tt, tf,
+                                                            e->out_buf);
+  LXG_CUDA(cudaGetLastError());
+  ++launches;
+  e->launches = launches;
+  return LXG_OK;
+}
+
+int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, int mode, int tt, int tf, float* out,
+        void* stream) {
+  if (!e || !ids || !mask || !out) return set_error(LXG_EINVAL, "NULL argument");
+  if (b < 0 || s <= 0) return set_error(LXG_EINVAL, "b must be >= 0 and s >= 1");
+  if (b > 65535) return set_error(LXG_EUNSUPPORTED, "more than 65535 sequences per call");
+  if (mode == 1) {
+    if (!e->w.lm_head) return set_error(LXG_EINVAL, "this decoder was created without lm_head weights");
+    if (tt < 0 || tt >= e->w.vocab || tf < 0 || tf >= e->w.vocab) return set_error(LXG_EINVAL, "true/false token id outside the vocabulary");
+  }
+  if (b == 0) return LXG_OK;
+  std::lock_guard<std::mutex> lock(e->mu);
+  cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
+  const long long tokens_ll = static_cast<long long>(b) * s;
+  if (tokens_ll > (1 << 20)) return set_error(LXG_EUNSUPPORTED, "more than 1M tokens per call");
+  const int tokens = static_cast<int>(tokens_ll);
+  int rc = reserve_ws(e, tokens);
+  if (rc != LXG_OK) return rc;
+  if (!e->own) {
+    LXG_CUDA(cudaStreamCreateWithFlags(&e->own, cudaStreamNonBlocking));
+    LXG_CUDA(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+    LXG_CUDA(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  }
+  cudaStream_t st = e->own;
+  LXG_CUDA(cudaEventRecord(e->ev_in, caller));
+  LXG_CUDA(cudaStreamWaitEvent(st, e->ev_in, 0));
+  const int H = e->w.hidden;
+  const bool ids_dev = is_device_ptr(ids), mask_dev = is_device_ptr(mask), out_dev = is_device_ptr(out);
+  LXG_CUDA(cudaMemcpyAsync(e->ids, ids, tokens * sizeof(int), ids_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  LXG_CUDA(cudaMemcpyAsync(e->mask, mask, tokens * sizeof(int), mask_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  const size_t out_floats = mode == 0 ? static_cast<size_t>(b) * H : static_cast<size_t>(b);
+  if (out_floats > e->out_cap) {
+    drop_graphs(e);
+    cudaFree(e->out_buf);
+    e->out_buf = nullptr;
+    e->out_cap = 0;
+    const size_t cap = std::max(out_floats, static_cast<size_t>(64) * H);
+    LXG_CUDA(cudaMalloc(&e->out_buf, cap * sizeof(float)));
+    e->out_cap = cap;
+  }
+  bool ran = false;
+  if (e->use_graphs) {
+    cudaGraphExec_t exec = nullptr;
+    for (auto& g : e->graphs)
+      if (g.b == b && g.s == s && g.mode == mode && g.tt == tt && g.tf == tf) exec = g.exec;
+    if (exec) {
+      LXG_CUDA(cudaGraphLaunch(exec, st));
+      ran = true;
+    } else {
+      // first call with this shape: run eagerly (sets kernel attributes), then capture for later calls
+      rc = launch_forward(e, b, s, mode, tt, tf, st);
+      if (rc != LXG_OK) return rc;
+      ran = true;
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc2 = launch_forward(e, b, s, mode, tt, tf, st);
+        const cudaError_t ce = cudaStreamEndCapture(st, &graph);
+        if (rc2 == LXG_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+          if (e->graphs.size() >= 64) drop_graphs(e);
+          e->graphs.push_back({b, s, mode, tt, tf, exec});
+        } else {
+          e->use_graphs = false;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+      } else {
+        cudaGetLastError();
+        e->use_graphs = false;
+      }
+    }
+  }
+  if (!ran) {
+    rc = launch_forward(e, b, s, mode, tt, tf, st);
+    if (rc != LXG_OK) return rc;
+  }
+  LXG_CUDA(cudaMemcpyAsync(out, e->out_buf, out_floats * sizeof(float), out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+  if (!out_dev) {
+    LXG_CUDA(cudaStreamSynchronize(st));
+  } else {
+    LXG_CUDA(cudaEventRecord(e->ev_out, st));
+    LXG_CUDA(cudaStreamWaitEvent(caller, e->ev_out, 0));
+  }
+  return LXG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
+  if (!out) return set_error(LXG_EINVAL, "out is NULL");
+  *out = nullptr;
+  if (!w || !w->layer) return set_error(LXG_EINVAL, "weights are NULL");
+  if (!lxg::encode_tensor_map_ready()) return set_error(LXG_EINVAL, "lxg_init has not been called");
+  if (w->head_dim != kHeadDim) return set_error(LXG_EUNSUPPORTED, "decoder geometry: head_dim must be 128 (every Qwen3 size)");
+  if (w->hidden <= 0 || w->hidden > 1024 || w->hidden % kGemmBN != 0 || w->ffn <= 0 || w->ffn % 64 != 0 || w->layers <= 0 ||
+      w->heads <= 0 || w->kv_heads <= 0 || w->heads % w->kv_heads != 0 || w->vocab <= 0)
+    return set_error(LXG_EUNSUPPORTED,
+                     "decoder geometry: hidden must be a multiple of 128 and <= 1024, ffn a multiple of 64, heads a multiple of kv_heads");
+  const void* globals[] = {w->tok_emb, w->final_norm, w->inv_freq};
+  for (const void* p : globals)
+    if (!p || !is_device_ptr(p)) return set_error(LXG_EINVAL, "tok_emb / final_norm / inv_freq must be device memory");
+  if (w->lm_head && !is_device_ptr(w->lm_head)) return set_error(LXG_EINVAL, "lm_head must be device memory");
+  lxg_decoder* e = new lxg_decoder();
+  e->w = *w;
+  e->layers.assign(w->layer, w->layer + w->layers);
+  e->w.layer = e->layers.data();
+  const int H = w->hidden, F = w->ffn, QKV = (w->heads + 2 * w->kv_heads) * kHeadDim, C = w->heads * kHeadDim;
+  e->map_wqkv.resize(w->layers);
+  e->map_wo.resize(w->layers);
+  e->map_wgu.resize(w->layers);
+  e->map_wdown.resize(w->layers);
+  for (int l = 0; l < w->layers; ++l) {
+    const lxg_qwen3_layer& L = e->layers[l];
+    const void* ptrs[] = {L.ln1, L.wqkv, L.q_norm, L.k_norm, L.wo, L.ln2, L.wgu, L.wdown};
+    for (const void* p : ptrs)
+      if (!p || !is_device_ptr(p)) {
+        delete e;
+        return set_error(LXG_EINVAL, "layer " + std::to_string(l) + ": weight pointer is not device memory");
+      }
+    int rc;
+    if ((rc = make_map(&e->map_wqkv[l], L.wqkv, QKV, H)) != LXG_OK || (rc = make_map(&e->map_wo[l], L.wo, H, C)) != LXG_OK ||
+        (rc = make_map(&e->map_wgu[l], L.wgu, 2 * F, H)) != LXG_OK || (rc = make_map(&e->map_wdown[l], L.wdown, H, F)) != LXG_OK) {
+      delete e;
+      return rc;
+    }
+  }
+  *out = e;
+  return LXG_OK;
+}
+
+int lxg_decoder_destroy(lxg_decoder* e) {
+  if (!e) return LXG_OK;
+  free_ws(e);
+  cudaFree(e->out_buf);
+  if (e->own) cudaStreamDestroy(e->own);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  delete e;
+  return LXG_OK;
+}
+
+int lxg_decoder_last_launches(const lxg_decoder* e) { return e ? e->launches : -1; }
+
+int lxg_decoder_embed(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, float* out, void* stream) {
+  return run(e, ids, mask, b, s, 0, 0, 0, out, stream);
+}
+
+int lxg_decoder_rerank(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, int32_t token_true,
+                       int32_t token_false, float* scores, void* stream) {
+  return run(e, ids, mask, b, s, 1, token_true, token_false, scores, stream);
+}
+
+}  // extern "C"

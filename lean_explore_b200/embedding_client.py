@@ -35,10 +35,14 @@ class GpuEmbeddingClient:
             raise RuntimeError("GpuEmbeddingClient runs on a B200 only (there is no CPU fallback)")
         self.max_length = max_length
         self.batch_size = batch_size or int(os.getenv("LEAN_EXPLORE_EMBEDDING_BATCH_SIZE", DEFAULT_BATCH_SIZE))
+        from .decoder import load_qwen3, model_type_of
         from .encoder import load_sentence_encoder
 
         logger.info("Loading embedding model %s on %s", model_name, self.device)
-        self.model = load_sentence_encoder(model_name, device=self.device, max_length=max_length)
+        if model_type_of(model_name) == "qwen3":  # the shipped Qwen/Qwen3-Embedding-0.6B (d = 1024)
+            self.model = load_qwen3(model_name, device=self.device, max_length=max_length, with_lm_head=False)
+        else:  # BERT-class sentence-transformers models (all-MiniLM-L6-v2, bge-base-en-v1.5)
+            self.model = load_sentence_encoder(model_name, device=self.device, max_length=max_length)
         if max_length is not None:
             logger.info("Set max sequence length to %d", max_length)
 
@@ -47,7 +51,7 @@ class GpuEmbeddingClient:
 
         def _encode():
             # BERT-class sentence-transformers models define no "query" prompt: is_query is a
-            # no-op for them; models that define one get it prepended.
+            # no-op for them; Qwen3-Embedding defines one and gets it prepended.
             return self.model.encode(texts, batch_size=self.batch_size, is_query=is_query)
 
         embeddings = await loop.run_in_executor(None, _encode)
