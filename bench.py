@@ -385,6 +385,10 @@ def main():
             out["extra"]["encoder"] = encoder_numbers(dev, cpu=not args.no_cpu_baseline)
         except Exception as exc:  # noqa: BLE001 - secondary numbers must not lose the headline line
             out["extra"]["encoder"] = {"error": repr(exc)}
+        try:
+            out["extra"]["qwen3"] = decoder_numbers(dev, cpu=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001
+            out["extra"]["qwen3"] = {"error": repr(exc)}
 
     if world > 1:
         dist.barrier()
@@ -491,6 +495,55 @@ def encoder_numbers(dev, cpu: bool):
             entry["cpu_baseline"]["kind"] = "HF BertModel fp32 (what sentence-transformers runs), torch %d threads" % torch.get_num_threads()
         res[name] = entry
         del enc, model
+    return res
+
+
+def decoder_numbers(dev, cpu: bool):
+    """The shipped models: Qwen3-Embedding-0.6B forward behind
+    EmbeddingClient.embed and Qwen3-Reranker-0.6B behind RerankerClient._compute_scores_sync, on
+    random-init weights of the real geometry (vocabulary cut to 4096 rows: it only feeds a gather),
+    synthetic left-padded token ids.  CPU leg: HF Qwen3ForCausalLM fp32 on the host cores through
+    oracle/qwen3_decoder.py."""
+    import torch
+
+    from lean_explore_b200.decoder import Qwen3Decoder
+    from oracle import qwen3_decoder as qd
+
+    model, cfg = qd.make_model("qwen3-0.6b", seed=0)
+    dec = Qwen3Decoder(model.state_dict(), hidden=cfg.hidden_size, layers=cfg.num_hidden_layers,
+                       heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads, ffn=cfg.intermediate_size,
+                       head_dim=cfg.head_dim, rms_eps=cfg.rms_norm_eps, rope_theta=1e6, device=dev.index or 0)
+    H, F, L = cfg.hidden_size, cfg.intermediate_size, cfg.num_hidden_layers
+    qkv, c = (cfg.num_attention_heads + 2 * cfg.num_key_value_heads) * 128, cfg.num_attention_heads * 128
+    flop_tok = 2.0 * L * (H * qkv + c * H + H * 2 * F + F * H)
+    res = {"geometry": "Qwen3-0.6B: L28 H1024 16q/8kv x128 FFN3072, vocab rows cut to 4096", "launches": None}
+    tt, tf = 1837, 3082
+    for label, mode, b, sl, iters in (("embed query B=1 S=24", 0, 1, 24, 100), ("embed bulk B=64 S=128", 0, 64, 128, 10),
+                                      ("rerank B=16 S=256 (reference CUDA batch)", 1, 16, 256, 10),
+                                      ("rerank B=50 S=256 (rerank_top=50 in one call)", 1, 50, 256, 10)):
+        ids_h, mask_h = qd.make_inputs(b, sl, seed=5, side="left")
+        call = (lambda: dec.embed_ids(ids_h, mask_h)) if mode == 0 else (lambda: dec.rerank_ids(ids_h, mask_h, tt, tf))
+        for _ in range(3):
+            call()
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            call()  # host ids in, host result out: H2D + forward + D2H + sync inside the timing
+        ms = (time.perf_counter() - t0) / iters * 1e3
+        res[label] = {"e2e_ms_per_call": round(ms, 4), "items_per_s": round(b / (ms / 1e3), 1),
+                      "gemm_tflops": round(flop_tok * b * sl / (ms / 1e3) / 1e12, 2)}
+    res["launches"] = dec.last_launches()
+    if cpu:
+        res["cpu_baseline"] = {"kind": "HF Qwen3ForCausalLM fp32, torch %d threads" % torch.get_num_threads()}
+        for label, mode, b, sl, reps in (("embed query B=1 S=24", 0, 1, 24, 3), ("rerank B=4 S=256", 1, 4, 256, 1)):
+            ids_c, mask_c = qd.make_inputs(b, sl, seed=6, side="left")
+            fn = (lambda: qd.embed(model, ids_c, mask_c)) if mode == 0 else (lambda: qd.rerank(model, ids_c, mask_c, tt, tf))
+            fn()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                fn()
+            dt = (time.perf_counter() - t0) / reps
+            res["cpu_baseline"][label] = {"ms_per_call": round(dt * 1e3, 2), "items_per_s": round(b / dt, 2)}
+    del dec, model
     return res
 
 

@@ -72,8 +72,8 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
 
 // ------------------------------------------------------------------ q/k head RMSNorm + RoPE
 // In place on the QKV projection [tokens, (heads + 2 kv_heads) * 128] (fp16): one warp per
-// (token, q or k head).  Lane l holds features l, l+32, l+64, l+96 so both rotate_half partners
-// (i, i+64) sit in the same lane.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
+// (token, q or k head).  Lane l holds features 2l, 2l+1, 2l+64, 2l+65 so both rotate_half partners
+// (i, i+64) sit in the same lane and every access is a half2.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
 // with HF's fp32 inv_freq table (Qwen3RotaryEmbedding).
 static __global__ void __launch_bounds__(256)
 qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, int kv_heads,
@@ -87,39 +87,40 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, in
   const int t = static_cast<int>(wid / nh), h = static_cast<int>(wid % nh);
   const float* w = h < heads ? q_w : k_w;
   __half* p = qkv + static_cast<size_t>(t) * (heads + 2 * kv_heads) * DH + static_cast<size_t>(h) * DH;
-  float x[4];
-  float ss = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    x[i] = __half2float(p[lane + 32 * i]);
-    ss += x[i] * x[i];
-  }
+  // lane l holds features 2l, 2l+1 (x[0], x[1]) and their rotate_half partners 2l+64, 2l+65 (x[2], x[3])
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(p + 2 * lane));
+  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(p + 64 + 2 * lane));
+  float x[4] = {lo.x, lo.y, hi.x, hi.y};
+  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rstd = rsqrtf(ss / DH + eps);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) x[i] = x[i] * rstd * w[lane + 32 * i];
+  const float2 wlo = *reinterpret_cast<const float2*>(w + 2 * lane), whi = *reinterpret_cast<const float2*>(w + 64 + 2 * lane);
+  x[0] *= rstd * wlo.x;
+  x[1] *= rstd * wlo.y;
+  x[2] *= rstd * whi.x;
+  x[3] *= rstd * whi.y;
   const float pos = static_cast<float>(t % seq);
+  const float2 f = *reinterpret_cast<const float2*>(inv_freq + 2 * lane);
   float s0, c0, s1, c1;
-  sincosf(pos * inv_freq[lane], &s0, &c0);
-  sincosf(pos * inv_freq[lane + 32], &s1, &c1);
-  p[lane] = __float2half_rn(x[0] * c0 - x[2] * s0);
-  p[lane + 64] = __float2half_rn(x[2] * c0 + x[0] * s0);
-  p[lane + 32] = __float2half_rn(x[1] * c1 - x[3] * s1);
-  p[lane + 96] = __float2half_rn(x[3] * c1 + x[1] * s1);
+  sincosf(pos * f.x, &s0, &c0);
+  sincosf(pos * f.y, &s1, &c1);
+  *reinterpret_cast<__half2*>(p + 2 * lane) = __floats2half2_rn(x[0] * c0 - x[2] * s0, x[1] * c1 - x[3] * s1);
+  *reinterpret_cast<__half2*>(p + 64 + 2 * lane) = __floats2half2_rn(x[2] * c0 + x[0] * s0, x[3] * c1 + x[1] * s1);
 }
 
 // ------------------------------------------------------------------ causal GQA attention
-// Flash-style: one CTA per (128 query rows, q head, sequence); warp w owns 16 query rows.  Keys and
+// Flash-style: one CTA (4 warps) per (64 query rows, q head, sequence); warp w owns 16 query rows;
+// three CTAs are resident per SM so one CTA's chunk loads overlap the others' MMAs.  Keys and
 // values of the head's KV group are streamed through shared memory in chunks of 64 keys (both
 // row-major; the P.V operand is read transposed with ldmatrix.trans), scores and context run on
 // mma.sync m16n8k16 with an fp32 online softmax.  Key j is visible to query i iff j <= i and mask[j] != 0 (HF create_causal_mask with a
 // padding mask); rows with no visible key (left padding) yield 0 and are never read downstream.
-constexpr int kCausalRows = 128;
+constexpr int kCausalRows = 64;
 constexpr int kCausalKeys = 64;
 
 template <int DH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kCausalRows * 2, 3)
 attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int heads,
                         int kv_heads, __half* __restrict__ ctx) {
   constexpr int kKSteps = DH / 16;

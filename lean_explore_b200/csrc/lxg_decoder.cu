@@ -121,7 +121,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int mode, int tt, int tf, cudaS
                                                      reinterpret_cast<const float*>(L.k_norm),
                                                      reinterpret_cast<const float*>(e->w.inv_freq), eps);
     LXG_CUDA(cudaGetLastError());
-    attention_causal_kernel<kHeadDim><<<attn_grid, 256, 0, st>>>(e->qkv, e->mask, s, heads, kvh, e->ctx);
+    attention_causal_kernel<kHeadDim><<<attn_grid, kCausalRows * 2, 0, st>>>(e->qkv, e->mask, s, heads, kvh, e->ctx);
     LXG_CUDA(cudaGetLastError());
     // o_proj, accumulated onto the residual stream
     gp.out = e->resid;

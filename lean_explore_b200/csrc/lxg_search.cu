@@ -31,6 +31,7 @@ static int g_device = -1;
 static int g_num_sms = 0;
 static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
 static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
+static bool g_asmem_768 = true;      // LXG_SCAN_ASMEM=0: 512 < d <= 768 falls back to 64-row tiles, all of A in tensor memory (A/B)
 static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -117,6 +118,7 @@ struct lxg_index {
   int scan_pitch = 0;      // elements
   int tile_rows = 0;       // N_T
   int num_kc = 0;
+  int a_smem_chunks = 0;    // k-chunks of the query block the scan keeps in shared memory (kASm)
   CUtensorMap tmap{};       // box = tile_rows rows   (one CTA per query block)
   CUtensorMap tmap_pair{};  // box = tile_rows/2 rows (CTA pairs, tcgen05 cta_group::2)
   std::mutex mu;
@@ -235,12 +237,12 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
   return pl;
 }
 
-template <int N_T, bool kPair>
+template <int N_T, bool kPair, int kASm = 0>
 cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, cudaStream_t st) {
   static bool attr_set = false;
-  const int smem = kStageRing + 1024;
+  const int smem = (kASm == 0 ? kStageRing : kScanSmemMax) + 1024;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<N_T, kPair>,
+    cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<N_T, kPair, kASm>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) return e;
     attr_set = true;
@@ -257,7 +259,7 @@ cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, c
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, scan_topk_kernel<N_T, kPair>, kPair ? ix->tmap_pair : ix->tmap, sp);
+  return cudaLaunchKernelEx(&cfg, scan_topk_kernel<N_T, kPair, kASm>, kPair ? ix->tmap_pair : ix->tmap, sp);
 }
 
 template <int THREADS>
@@ -311,6 +313,8 @@ int lxg_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   const char* fs = std::getenv("LXG_SCAN_SINGLE");
   g_force_single = fs && fs[0] == '1';
+  const char* am = std::getenv("LXG_SCAN_ASMEM");
+  g_asmem_768 = !(am && am[0] == '0');
   const char* nl = std::getenv("LXG_SCAN_NOLEVEL");
   g_no_level = nl && nl[0] == '1';
   const char* pm = std::getenv("LXG_SCAN_PERF_MODE");
@@ -335,9 +339,9 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
   if (n < 0 || d <= 0 || (dtype != LXG_F32 && dtype != LXG_F16))
     return set_error(LXG_EINVAL, "bad n / d / dtype");
   if (n >= (1ll << 31) - 256) return set_error(LXG_EUNSUPPORTED, "more than 2^31 rows per shard");
-  if (d > 768)
+  if (d > 1024)
     return set_error(LXG_EUNSUPPORTED,
-                     "d > 768: the fp16 query block must fit tensor memory next to two accumulators");
+                     "d > 1024: the fp16 query block must fit tensor memory + shared memory next to the corpus pipeline");
   if (n > 0 && (!corpus_dev || !is_device_ptr(corpus_dev)))
     return set_error(LXG_EINVAL, "corpus_dev must be device memory");
   lxg_index* ix = new lxg_index();
@@ -350,7 +354,12 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
   ix->cv.max_row_norm = 0.f;
   ix->cv.scan_scale = 1.f;
   ix->num_kc = (d + kKC - 1) / kKC;
-  ix->tile_rows = (ix->num_kc * 32 + 256 <= 512) ? 128 : 64;
+  // 128-row tiles throughout; the first 8 k-chunks (512 dims) of the query block live in tensor
+  // memory, the rest in shared memory: 4 chunks for d <= 768 (measured on cfg3, same box: 2.43 ms
+  // against 3.12 ms for the 64-row-tile variant that keeps all of A in tensor memory, which
+  // LXG_SCAN_ASMEM=0 still selects), 8 chunks for d <= 1024
+  ix->a_smem_chunks = ix->num_kc <= 8 ? 0 : (ix->num_kc > 12 ? 8 : (g_asmem_768 ? 4 : 0));
+  ix->tile_rows = (ix->num_kc <= 8 || ix->a_smem_chunks > 0) ? 128 : 64;
   const float sqrt_d = std::sqrt(static_cast<float>(d));
   const bool alias = dtype == LXG_F16 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(corpus_dev) % 16 == 0);
   if (n > 0) {
@@ -570,7 +579,13 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   LXG_CUDA(cudaGetLastError());
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
-  if (ix->tile_rows == 128) {
+  if (ix->a_smem_chunks == 8) {
+    if (pl.pair) LXG_CUDA((launch_scan<128, true, 8>(ix, sp, pl.grid_x, st)));
+    else LXG_CUDA((launch_scan<128, false, 8>(ix, sp, pl.grid_x, st)));
+  } else if (ix->a_smem_chunks == 4) {
+    if (pl.pair) LXG_CUDA((launch_scan<128, true, 4>(ix, sp, pl.grid_x, st)));
+    else LXG_CUDA((launch_scan<128, false, 4>(ix, sp, pl.grid_x, st)));
+  } else if (ix->tile_rows == 128) {
     if (pl.pair) LXG_CUDA((launch_scan<128, true>(ix, sp, pl.grid_x, st)));
     else LXG_CUDA((launch_scan<128, false>(ix, sp, pl.grid_x, st)));
   } else {

@@ -51,6 +51,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Cluster-scope acquire: pairs with mbar_arrive_cluster of the peer CTA (whose shared-memory
+// writes the waiter's MMAs go on to read).
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0, ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, P;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (!ok && ++spins == (1u << 27)) __trap();
+  }
+}
 // Spin on try_wait (each probe sleeps in hardware up to its time limit).  A protocol bug would
 // otherwise hang the GPU: after ~2^27 failed probes (many seconds) trap, so that the launch fails
 // with an error the host reports instead.
@@ -122,7 +137,7 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
   asm volatile(
       "{\n\t.reg .b32 remAddr32;\n\t"
       "mapa.shared::cluster.u32 remAddr32, %0, %1;\n\t"
-      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n\t}"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remAddr32];\n\t}"
       :
       : "r"(smem_u32(bar)), "r"(cta)
       : "memory");
@@ -254,6 +269,19 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uin
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T over a CTA pair: every CTA's shared memory holds its 128 rows of
+// A and N/2 rows of B at the descriptors' offsets.  Issued by the even CTA only.
+__device__ __forceinline__ void mma_f16_ss_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc,
+                                                uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       :
       : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");

@@ -42,7 +42,9 @@ constexpr int kEpiWarps = 4 * kGroups;    // four warps (the four TMEM lane quar
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kScanThreads = kEpiThreads + 64;  // + one TMA warp + one MMA warp
 constexpr int kKC = 64;            // fp16 elements per 128-byte swizzled row
-constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline
+constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline (kASm == 0)
+constexpr int kScanSmemMax = 229376;  // A chunks in shared memory + pipeline when kASm > 0
+constexpr int kAChunkBytes = 16384;   // one k-chunk of the query block: 128 rows x 128 bytes
 constexpr int kStageBytes = 32768; // one pipeline stage: N_T rows x (32768 / (128 N_T)) k-chunks
 constexpr int kQueryBlock = 128;   // queries per CTA == UMMA M
 constexpr int kTrack = 8;          // register tracker: best kTrack scores a list has seen
@@ -402,17 +404,26 @@ __device__ __forceinline__ void scan_chunk_careful(uint32_t taddr, ListState& ls
 
 // N_T: corpus rows per accumulator tile (UMMA N).  128 when the fp16 queries need <= 256 TMEM
 // columns (d <= 512), 64 when they need up to 384 (d <= 768): A + 2 accumulators <= 512 columns.
+// kASm: k-chunks (64 dims) of the query block kept in SHARED memory instead of tensor memory, for
+// d beyond what fits TMEM next to two N_T = 128 accumulators (8 chunks = 512 dims): chunks
+// 0..7 are TS MMAs (A from TMEM), chunks 8.. are SS MMAs (A from a 128B-swizzled K-major smem
+// image written by the epilogue threads).  kASm = 8 covers d <= 1024 (the shipped
+// Qwen3-Embedding-0.6B), kASm = 4 is an alternative to N_T = 64 for d <= 768.
 // kPair: two CTAs of a cluster (two adjacent blocks of 128 queries) run ONE tcgen05.mma
 // cta_group::2 stream (M = 256): each CTA stages only N_T/2 rows of every corpus tile, so a corpus
 // byte crosses L2 -> SM once per 256 queries instead of once per 128.
-template <int N_T, bool kPair>
+template <int N_T, bool kPair, int kASm = 0>
 __global__ void __launch_bounds__(kScanThreads, 1)
 scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
+  static_assert(kASm == 0 || N_T == 128, "shared-memory A chunks go with 128-row tiles");
+  constexpr int kTmChunks = (512 - 2 * N_T) / 32;        // A k-chunks that live in tensor memory
+  constexpr int kRingBytes = kASm == 0 ? kStageRing : kScanSmemMax - kASm * kAChunkBytes;
   constexpr int kBoxRows = kPair ? N_T / 2 : N_T;       // corpus rows this CTA stages per tile
   constexpr int kBoxBytes = kBoxRows * 128;             // one TMA box: kBoxRows rows x 64 fp16
   constexpr int kStageBytesT = kPair ? kStageBytes / 2 : kStageBytes;
   constexpr int kKcPerStage = kStageBytesT / kBoxBytes;  // k-chunks (boxes) per pipeline stage
-  constexpr int kStages = kStageRing / kStageBytesT;
+  constexpr int kStages = kRingBytes / kStageBytesT;
+  static_assert(kASm == 0 || kTmChunks % kKcPerStage == 0, "a stage is all-TS or all-SS");
   // Epilogue group g owns accumulator columns [g * kGroupCols, (g+1) * kGroupCols) of every tile,
   // read in chunks of kChunkCols columns.  (Computing every tile as N = N_T/2 halves with
   // per-group barriers was measured and dropped: N = 64 MMAs with A in tensor memory run at
@@ -442,9 +453,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   const int slice = blockIdx.y;
   const uint32_t rank = kPair ? ptx::cluster_ctarank() : 0u;  // position in the CTA pair
 
-  // 1024-byte aligned stage ring (SWIZZLE_128B atoms are 1024 bytes).
-  const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* ring = smem_raw + (ring_u32 - ptx::smem_u32(smem_raw));
+  // 1024-byte aligned: [A chunks kTmChunks.. (kASm x 16 KB)] [stage ring] (SWIZZLE_128B atoms are 1024 bytes).
+  const uint32_t asm_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t ring_u32 = asm_u32 + kASm * kAChunkBytes;
 
   const int tile_begin = slice * p.tiles_per_slice;
   const int tile_end = min(p.num_tiles, tile_begin + p.tiles_per_slice);
@@ -520,7 +531,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     // (warp-uniform loop, one elected lane issues: in divergent code every tcgen05 instruction
     // would be wrapped in its own elect loop)
     if (rank == 0) {
-      ptx::mbar_wait(&a_ready_bar, 0);
+      if constexpr (kPair && kASm > 0) ptx::mbar_wait_cluster(&a_ready_bar, 0); else ptx::mbar_wait(&a_ready_bar, 0);
       ptx::tc_fence_after();
       const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
       const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
@@ -530,6 +541,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       const uint32_t desc_lo0 = ptx::opaque(((ring_u32 & 0x3FFFFu) >> 4) | (1u << 16));
       constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t a_tmem0 = ptx::opaque(tmem_base + kACol0);
+      const uint32_t adesc_lo0 = ptx::opaque(((asm_u32 & 0x3FFFFu) >> 4) | (1u << 16));
       uint32_t stage = 0, phase = 0;
       for (int it = 0; it < my_tiles; ++it) {
         const uint32_t acc = it & 1;
@@ -542,21 +554,43 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           ptx::tc_fence_after();
           if (ptx::elect_one()) {
             const uint32_t lo = desc_lo0 + stage * (kStageBytesT >> 4);
-            const uint32_t a_kc = a_tmem0 + kc0 * 32;
+            if (kASm == 0 || kc0 < kTmChunks) {
+              const uint32_t a_kc = a_tmem0 + kc0 * 32;
 #pragma unroll
-            for (int b = 0; b < kKcPerStage; ++b) {
-              if (b < nb) {
+              for (int b = 0; b < kKcPerStage; ++b) {
+                if (b < nb) {
 #pragma unroll
-                for (int k4 = 0; k4 < 4; ++k4) {
-                  // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
-                  // 8 TMEM columns in A.
-                  const uint64_t bdesc =
-                      (static_cast<uint64_t>(kDescHi) << 32) | (lo + b * (kBoxBytes >> 4) + k4 * 2);
-                  const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
-                  if constexpr (kPair)
-                    ptx::mma_f16_ts_pair(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
-                  else
-                    ptx::mma_f16_ts(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    // K advances 16 fp16 = 32 bytes inside the swizzle atom (+2 in >>4 units) and
+                    // 8 TMEM columns in A.
+                    const uint64_t bdesc =
+                        (static_cast<uint64_t>(kDescHi) << 32) | (lo + b * (kBoxBytes >> 4) + k4 * 2);
+                    const uint32_t accum = (kc0 | b | k4) != 0 ? 1u : 0u;
+                    if constexpr (kPair)
+                      ptx::mma_f16_ts_pair(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
+                    else
+                      ptx::mma_f16_ts(d_tmem, a_kc + b * 32 + k4 * 8, bdesc, kIdesc, accum);
+                  }
+                }
+              }
+            } else {
+              // A from shared memory: chunk kc lives at asm + (kc - kTmChunks) * 16 KB, same
+              // K-major 128B-swizzled layout (and descriptor) as a corpus box
+              const uint32_t alo = adesc_lo0 + (kc0 - kTmChunks) * (kAChunkBytes >> 4);
+#pragma unroll
+              for (int b = 0; b < kKcPerStage; ++b) {
+                if (b < nb) {
+#pragma unroll
+                  for (int k4 = 0; k4 < 4; ++k4) {
+                    const uint64_t bdesc =
+                        (static_cast<uint64_t>(kDescHi) << 32) | (lo + b * (kBoxBytes >> 4) + k4 * 2);
+                    const uint64_t adesc =
+                        (static_cast<uint64_t>(kDescHi) << 32) | (alo + b * (kAChunkBytes >> 4) + k4 * 2);
+                    if constexpr (kPair)
+                      ptx::mma_f16_ss_pair(d_tmem, adesc, bdesc, kIdesc, 1u);
+                    else
+                      ptx::mma_f16_ss(d_tmem, adesc, bdesc, kIdesc, 1u);
+                  }
                 }
               }
             }
@@ -591,7 +625,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     // the 128-byte k-chunks of the row are dealt round robin to the groups
     {
       const uint4* xrow = reinterpret_cast<const uint4*>(p.xh + static_cast<size_t>(q) * p.dpad);
-      for (int kc = grp; kc < p.num_kc; kc += kGroups) {
+      for (int kc = grp; kc < min(p.num_kc, kASm > 0 ? kTmChunks : p.num_kc); kc += kGroups) {
         uint32_t r[32];
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
@@ -602,6 +636,21 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           r[4 * u + 3] = v.w;
         }
         ptx::tmem_st_32x32b_x32(tmem_base + lane_base + kACol0 + kc * 32, r);
+      }
+      if constexpr (kASm > 0) {
+        // chunks kTmChunks..: K-major rows of 128 bytes, 16-byte unit u of row t stored at unit
+        // u ^ (t & 7) (CU_TENSOR_MAP_SWIZZLE_128B, what the MMA descriptor expects)
+        for (int kc = kTmChunks + grp; kc < p.num_kc; kc += kGroups) {
+          const uint32_t rowaddr = asm_u32 + (kc - kTmChunks) * kAChunkBytes + t * 128;
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint4 v = __ldg(xrow + kc * 8 + u);
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowaddr + ((u ^ (t & 7)) << 4)), "r"(v.x), "r"(v.y),
+                         "r"(v.z), "r"(v.w)
+                         : "memory");
+          }
+        }
+        ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async proxy
       }
     }
     ptx::tc_wait_st();

@@ -43,7 +43,8 @@ def _check(corpus_np, x, k, normalize=True):
     return ix
 
 
-@pytest.mark.parametrize("n,d,nq", [(300, 64, 5), (1000, 384, 7), (1000, 768, 130), (1001, 128, 3)])
+@pytest.mark.parametrize("n,d,nq", [(300, 64, 5), (1000, 384, 7), (1000, 768, 130), (1001, 128, 3),
+                                     (1000, 1024, 130), (700, 1000, 5), (900, 840, 260)])
 def test_tensor_core_scores_match_reference(n, d, nq):
     """Raw pass-1 scores (TMA -> swizzled smem -> tcgen05.mma with A in TMEM -> tcgen05.ld)
     against an fp64 product of the same fp16-rounded operands."""
@@ -80,7 +81,8 @@ def test_reference_kat_one_hot_row_is_its_own_neighbour():
 
 
 @pytest.mark.parametrize("dtype", [np.float16, np.float32])
-@pytest.mark.parametrize("n,d,nq,k", [(4096, 384, 32, 10), (4096, 768, 32, 50), (20000, 384, 200, 50)])
+@pytest.mark.parametrize("n,d,nq,k", [(4096, 384, 32, 10), (4096, 768, 32, 50), (20000, 384, 200, 50),
+                                       (4096, 1024, 32, 50), (20000, 1024, 300, 50)])
 def test_topk_matches_oracle(n, d, nq, k, dtype):
     _check(make_corpus(n, d, dtype=dtype), make_queries(nq, d), k)
 
@@ -107,7 +109,7 @@ def test_k_larger_than_n_pads_like_faiss():
 
 
 def test_ragged_shapes():
-    for n, d, nq in [(1, 8, 1), (129, 72, 2), (257, 100, 129), (5000, 760, 3)]:
+    for n, d, nq in [(1, 8, 1), (129, 72, 2), (257, 100, 129), (5000, 760, 3), (5000, 1016, 3), (3000, 900, 140)]:
         _check(make_corpus(n, d), make_queries(nq, d), 5)
     _check(make_corpus(515, 100, dtype=np.float32), make_queries(4, 100), 5)
 
@@ -226,7 +228,7 @@ def test_every_scan_mode_returns_the_same_exact_result(scan_modes):
             assert np.array_equal(I, want[1]) and np.array_equal(D, want[0])
 
 
-@pytest.mark.parametrize("d", [64, 768])
+@pytest.mark.parametrize("d", [64, 768, 1024])
 def test_adversarial_row_order_overflows_the_lists(d):
     """Rows sorted by ascending score for the probe query: every tile beats everything seen before,
     thresholds always lag, the candidate lists overflow and are compacted exactly."""
@@ -240,6 +242,18 @@ def test_adversarial_row_order_overflows_the_lists(d):
     _check(corpus, q, 100)
     many = np.concatenate([q, make_queries(1198, d)])  # 10 query blocks: few long lists overflow
     _check(corpus, many, 10)
+
+
+def test_shipped_model_dimension_d1024_fp32_corpus():
+    """d = 1024 is what the shipped index holds (Qwen3-Embedding-0.6B): query chunks 8..15 of the
+    block live in shared memory (SS MMAs), fp32 corpus as the reference stores it, faiss_k = 1000."""
+    corpus = make_corpus(30000, 1024, dtype=np.float32)
+    _check(corpus, make_queries(1, 1024), 1000)
+    _check(corpus, make_queries(257, 1024), 10)
+    from lean_explore_b200 import _lib
+
+    with pytest.raises(_lib.LxgError):
+        _index(make_corpus(10, 1032))
 
 
 def test_large_k_with_many_query_blocks():
