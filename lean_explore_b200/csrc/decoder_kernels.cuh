@@ -71,9 +71,11 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
 }
 
 // ------------------------------------------------------------------ q/k head RMSNorm + RoPE
-// In place on the QKV projection [tokens, (heads + 2 kv_heads) * 128] (fp16): one warp per
-// (token, q or k head).  Lane l holds features 2l, 2l+1, 2l+64, 2l+65 so both rotate_half partners
-// (i, i+64) sit in the same lane and every access is a half2.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
+// In place on the QKV projection [tokens, (heads + 2 kv_heads) * 128] (fp16): one warp per token,
+// looping over its q and k heads (they share the position, so cos / sin are evaluated once per
+// token - the kernel was instruction bound on sincosf when every (token, head) had its own warp).
+// Lane l holds features 2l, 2l+1, 2l+64, 2l+65 so both rotate_half partners (i, i+64) sit in the
+// same lane and every access is a half2.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
 // with HF's fp32 inv_freq table (Qwen3RotaryEmbedding).
 static __global__ void __launch_bounds__(256)
 qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, int kv_heads,
@@ -81,32 +83,31 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, in
                     const float* __restrict__ inv_freq, float eps) {
   constexpr int DH = 128;
   const int lane = threadIdx.x & 31;
-  const int nh = heads + kv_heads;
-  const long long wid = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (wid >= static_cast<long long>(tokens) * nh) return;
-  const int t = static_cast<int>(wid / nh), h = static_cast<int>(wid % nh);
-  const float* w = h < heads ? q_w : k_w;
-  __half* p = qkv + static_cast<size_t>(t) * (heads + 2 * kv_heads) * DH + static_cast<size_t>(h) * DH;
-  // lane l holds features 2l, 2l+1 (x[0], x[1]) and their rotate_half partners 2l+64, 2l+65 (x[2], x[3])
-  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(p + 2 * lane));
-  const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(p + 64 + 2 * lane));
-  float x[4] = {lo.x, lo.y, hi.x, hi.y};
-  float ss = x[0] * x[0] + x[1] * x[1] + x[2] * x[2] + x[3] * x[3];
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-  const float rstd = rsqrtf(ss / DH + eps);
-  const float2 wlo = *reinterpret_cast<const float2*>(w + 2 * lane), whi = *reinterpret_cast<const float2*>(w + 64 + 2 * lane);
-  x[0] *= rstd * wlo.x;
-  x[1] *= rstd * wlo.y;
-  x[2] *= rstd * whi.x;
-  x[3] *= rstd * whi.y;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens) return;
   const float pos = static_cast<float>(t % seq);
   const float2 f = *reinterpret_cast<const float2*>(inv_freq + 2 * lane);
   float s0, c0, s1, c1;
   sincosf(pos * f.x, &s0, &c0);
   sincosf(pos * f.y, &s1, &c1);
-  *reinterpret_cast<__half2*>(p + 2 * lane) = __floats2half2_rn(x[0] * c0 - x[2] * s0, x[1] * c1 - x[3] * s1);
-  *reinterpret_cast<__half2*>(p + 64 + 2 * lane) = __floats2half2_rn(x[2] * c0 + x[0] * s0, x[3] * c1 + x[1] * s1);
+  const float2 qlo = *reinterpret_cast<const float2*>(q_w + 2 * lane), qhi = *reinterpret_cast<const float2*>(q_w + 64 + 2 * lane);
+  const float2 klo = *reinterpret_cast<const float2*>(k_w + 2 * lane), khi = *reinterpret_cast<const float2*>(k_w + 64 + 2 * lane);
+  __half* row = qkv + static_cast<size_t>(t) * (heads + 2 * kv_heads) * DH;
+  const int nh = heads + kv_heads;
+#pragma unroll 4
+  for (int h = 0; h < nh; ++h) {
+    __half* p = row + h * DH;
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(p + 2 * lane));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(p + 64 + 2 * lane));
+    float ss = lo.x * lo.x + lo.y * lo.y + hi.x * hi.x + hi.y * hi.y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    const float rstd = rsqrtf(ss / DH + eps);
+    const float2 wlo = h < heads ? qlo : klo, whi = h < heads ? qhi : khi;
+    const float x0 = lo.x * rstd * wlo.x, x1 = lo.y * rstd * wlo.y, x2 = hi.x * rstd * whi.x, x3 = hi.y * rstd * whi.y;
+    *reinterpret_cast<__half2*>(p + 2 * lane) = __floats2half2_rn(x0 * c0 - x2 * s0, x1 * c1 - x3 * s1);
+    *reinterpret_cast<__half2*>(p + 64 + 2 * lane) = __floats2half2_rn(x2 * c0 + x0 * s0, x3 * c1 + x1 * s1);
+  }
 }
 
 // ------------------------------------------------------------------ causal GQA attention

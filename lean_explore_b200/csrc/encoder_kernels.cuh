@@ -153,6 +153,105 @@ struct GemmParams {
   int m, n, k;
 };
 
+// Epilogue of one thread (= one output row) over `nchunks` 32-column chunks of an accumulator,
+// starting at chunk c0: taddr = TMEM address of the accumulator (lane field set), n0 = first
+// output column of the tile.  Shared by the single-CTA and the CTA-pair kernels.
+template <int EPI>
+__device__ __forceinline__ void gemm_epilogue_row(uint32_t taddr, int c0, int nchunks, int row, int n0, const GemmParams& p) {
+  if constexpr (EPI == kEpiSwiGLU) {
+#pragma unroll 1
+    for (int c = c0; c < c0 + nchunks; c += 2) {  // chunk c = gate, chunk c + 1 = up of the same 32 outputs
+      uint32_t rg[32], ru[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, rg);
+      ptx::tmem_ld_32x32b_x32(taddr + (c + 1) * 32, ru);
+      ptx::tc_wait_ld();
+      if (row < p.m) {
+        const int ocol = (n0 >> 1) + (c >> 1) * 32;
+        uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * (p.n >> 1) + ocol);
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
+          v[j] = fminf(fmaxf(__fdividef(g, 1.0f + __expf(-g)) * u, -65504.f), 65504.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 o;
+          o.x = pack_half2(v[8 * j], v[8 * j + 1]);
+          o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+          o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+          o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+          o4[j] = o;
+        }
+      }
+    }
+  } else {
+#pragma unroll 1
+    for (int c = c0; c < c0 + nchunks; ++c) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+      ptx::tc_wait_ld();
+      const int col0 = n0 + c * 32;
+      if (row < p.m && col0 < p.n) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            v[4 * j + 0] += bb.x;
+            v[4 * j + 1] += bb.y;
+            v[4 * j + 2] += bb.z;
+            v[4 * j + 3] += bb.w;
+          }
+        }
+        if constexpr (EPI == kEpiGelu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
+        }
+        if constexpr (EPI == kEpiResid) {
+          const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
+          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 rr = __ldg(r4 + j);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
+            const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
+            const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
+            o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
+            o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
+          }
+        } else if constexpr (EPI == kEpiAccF32) {
+          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4 o = o4[j];
+            o.x += v[4 * j + 0];
+            o.y += v[4 * j + 1];
+            o.z += v[4 * j + 2];
+            o.w += v[4 * j + 3];
+            o4[j] = o;
+          }
+        } else {
+          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_half2(v[8 * j], v[8 * j + 1]);
+            o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
+            o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
+            o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
+            o4[j] = o;
+          }
+        }
+      }
+    }
+  }
+}
+
 // Persistent, warp-specialised: grid = min(#tiles, #SMs), every CTA walks tiles
 // t = blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so concurrently running CTAs share a W
 // tile in L2).  Warp 8 streams A / W k-blocks through a 6-stage TMA ring, warp 9 issues
@@ -273,100 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int row = m0 + (warp & 3) * 32 + lane;
       ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-      if constexpr (EPI == kEpiSwiGLU) {
-        uint32_t rg[32], ru[32];
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + (half * 2) * 32, rg);
-        ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + (half * 2 + 1) * 32, ru);
-        ptx::tc_wait_ld();
-        if (row < p.m) {
-          const int ocol = (n0 >> 1) + half * 32;
-          uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * (p.n >> 1) + ocol);
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float g = __uint_as_float(rg[j]), u = __uint_as_float(ru[j]);
-            v[j] = fminf(fmaxf(g / (1.0f + __expf(-g)) * u, -65504.f), 65504.f);
-          }
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_half2(v[8 * j], v[8 * j + 1]);
-            o.y = pack_half2(v[8 * j + 2], v[8 * j + 3]);
-            o.z = pack_half2(v[8 * j + 4], v[8 * j + 5]);
-            o.w = pack_half2(v[8 * j + 6], v[8 * j + 7]);
-            o4[j] = o;
-          }
-        }
-      } else {
-  #pragma unroll 1
-        for (int c = half * 2; c < half * 2 + 2; ++c) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * kGemmBN + c * 32, r);
-          ptx::tc_wait_ld();
-          const int col0 = n0 + c * 32;
-          if (row < p.m && col0 < p.n) {
-            float v[32];
-  #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-            if (p.bias != nullptr) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
-  #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                const float4 bb = __ldg(b4 + j);
-                v[4 * j + 0] += bb.x;
-                v[4 * j + 1] += bb.y;
-                v[4 * j + 2] += bb.z;
-                v[4 * j + 3] += bb.w;
-              }
-            }
-            if constexpr (EPI == kEpiGelu) {
-  #pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.5f * v[j] * (1.0f + erff(v[j] * 0.70710678118654752f));
-            }
-            if constexpr (EPI == kEpiResid) {
-              const uint4* r4 = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(row) * p.n + col0);
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
-  #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 rr = __ldg(r4 + j);
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rr.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rr.y));
-                const float2 cc = __half22float2(*reinterpret_cast<const __half2*>(&rr.z));
-                const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&rr.w));
-                o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
-                o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
-              }
-            } else if constexpr (EPI == kEpiAccF32) {
-              float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
-  #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float4 o = o4[j];
-                o.x += v[4 * j + 0];
-                o.y += v[4 * j + 1];
-                o.z += v[4 * j + 2];
-                o.w += v[4 * j + 3];
-                o4[j] = o;
-              }
-            } else {
-              uint4* o4 = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + static_cast<size_t>(row) * p.n + col0);
-  #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                __half2 h;
-                h = __floats2half2_rn(v[8 * j], v[8 * j + 1]);
-                o.x = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
-                o.y = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
-                o.z = *reinterpret_cast<uint32_t*>(&h);
-                h = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
-                o.w = *reinterpret_cast<uint32_t*>(&h);
-                o4[j] = o;
-              }
-            }
-          }
-        }
-      }
+      gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kGemmBN, half * 2, 2, row, n0, p);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);
@@ -377,6 +383,156 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == kTmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 2 * kGemmBN);
+  }
+}
+
+// ------------------------------------------------------------------ tcgen05 GEMM, CTA pairs
+// Same contract as gemm_tc_kernel for N % 256 == 0, on 256 x 256 output tiles computed by a
+// cluster of two CTAs with ONE tcgen05.mma.cta_group::2 stream (M = 256, N = 256, K = 16) issued
+// by the even CTA.  Each CTA stages its own 128 rows of A and 128 of the tile's 256 rows of W per
+// k-block (32 KB per stage, six stages) and drains its own 128 accumulator lanes.  Why: an SS MMA
+// of a 128 x 128 tile reads 8 KB of operands from shared memory per 64 tensor-core clocks while TMA
+// writes the next 8 KB - twice what the 128 B/clk shared-memory port delivers, which is where the
+// single-CTA kernel saturates (~50 % of the tensor peak).  The pair tile reads and writes 8 KB per
+// 128 clocks per SM.
+constexpr int kPairBN = 256;
+constexpr int kPairStageBytes = (kGemmBM + kPairBN / 2) * kGemmBK * 2;  // 32 KB per CTA
+constexpr int kPairStages = 6;
+constexpr int kPairSmem = kPairStages * kPairStageBytes + 1024;
+constexpr int kPairEpiWarps = 16;  // 4 per TMEM lane quarter (64 columns each): the epilogue is latency bound, more warps hide it
+constexpr int kPairThreads = (kPairEpiWarps + 2) * 32;
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
+gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                 const GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[kPairStages];
+  __shared__ __align__(8) uint64_t empty_bar[kPairStages];
+  __shared__ __align__(8) uint64_t acc_full_bar[2];
+  __shared__ __align__(8) uint64_t acc_empty_bar[2];
+  __shared__ uint32_t tmem_base_holder;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+  const int tiles_m = (p.m + 2 * kGemmBM - 1) / (2 * kGemmBM);
+  const int tiles = tiles_m * (p.n / kPairBN);
+  const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
+  const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kGemmBM, kPairBN);
+  constexpr int kTmaWarp = kPairEpiWarps, kMmaWarp = kPairEpiWarps + 1;
+
+  if (warp == kMmaWarp && lane == 0) {
+    for (int s = 0; s < kPairStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full_bar[a], 1);
+      ptx::mbar_init(&acc_empty_bar[a], 2 * kPairEpiWarps);  // both CTAs' epilogue warps
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == kTmaWarp) {
+    if (lane == 0) {
+      ptx::prefetch_tensormap(&tmap_a);
+      ptx::prefetch_tensormap(&tmap_w);
+    }
+    ptx::tmem_alloc_pair(&tmem_base_holder, 2 * kPairBN);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_base_holder;
+
+  if (warp == kTmaWarp) {
+    // both CTAs load their halves; all bytes are counted on the even CTA's full barrier
+    const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
+    const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
+    const uint32_t ring0 = ptx::opaque(ring_u32);
+    uint32_t stage = 0, phase = 0;
+    for (int t = cluster; t < tiles; t += nclusters) {
+      const int m0 = (t % tiles_m) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
+      const int n0 = (t / tiles_m) * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
+        if (ptx::elect_one()) {
+          const uint32_t fb = full0 + stage * 8;
+          if (rank == 0) ptx::mbar_arrive_expect_tx_a(fb, 2 * kPairStageBytes);
+          const uint32_t dst = ring0 + stage * kPairStageBytes;
+          ptx::tma_load_2d_pair_a(dst, &tmap_a, kb * kGemmBK, m0, fb, ptx::kEvictNormal);
+          ptx::tma_load_2d_pair_a(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, fb, ptx::kEvictLast);
+        }
+        __syncwarp();
+        if (++stage == kPairStages) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    if (rank == 0) {
+      const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
+      const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
+      const uint32_t afull0 = ptx::opaque(ptx::smem_u32(&acc_full_bar[0]));
+      const uint32_t aempty0 = ptx::opaque(ptx::smem_u32(&acc_empty_bar[0]));
+      const uint32_t desc_lo0 = ptx::opaque(((ring_u32 & 0x3FFFFu) >> 4) | (1u << 16));
+      constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int t = cluster; t < tiles; t += nclusters, ++it) {
+        const uint32_t acc = it & 1;
+        ptx::mbar_wait_a(aempty0 + acc * 8, ((it >> 1) & 1) ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kPairBN;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          ptx::mbar_wait_a(full0 + stage * 8, phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t lo = desc_lo0 + stage * (kPairStageBytes >> 4);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (lo + k4 * 2);
+              const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (lo + ((kGemmBM * kGemmBK * 2) >> 4) + k4 * 2);
+              ptx::mma_f16_ss_pair(d_tmem, adesc, bdesc, kIdesc, (kb | k4) != 0 ? 1u : 0u);
+            }
+            ptx::tc_commit_pair_a(empty0 + stage * 8, 3);
+            if (kb == num_kb - 1) ptx::tc_commit_pair_a(afull0 + acc * 8, 3);
+          }
+          __syncwarp();
+          if (++stage == kPairStages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+      }
+    }
+  } else {
+    // epilogue: thread = output row of this CTA's half of the tile, warp >> 2 = which 64 columns
+    const int quarter = warp >> 2;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t afull0 = ptx::opaque(ptx::smem_u32(&acc_full_bar[0]));
+    int it = 0;
+    for (int t = cluster; t < tiles; t += nclusters, ++it) {
+      const uint32_t acc = it & 1;
+      const int m0 = (t % tiles_m) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM, n0 = (t / tiles_m) * kPairBN;
+      const int row = m0 + (warp & 3) * 32 + lane;
+      ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
+      ptx::tc_fence_after();
+      gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kPairBN, quarter * 2, 2, row, n0, p);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+    }
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  if (warp == kTmaWarp) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, 2 * kPairBN);
   }
 }
 

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <string>
 
 #include "../../include/lxg.h"
@@ -27,8 +28,30 @@ inline int make_map(CUtensorMap* m, const void* base, int rows, int cols) {
   return LXG_OK;
 }
 
+// LXG_GEMM_SINGLE=1 keeps every GEMM on the single-CTA kernel (A/B measurements)
+inline bool gemm_pairs_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("LXG_GEMM_SINGLE");
+    return !(e && e[0] == '1');
+  }();
+  return on;
+}
+
 template <int EPI>
 inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st) {
+  // more than one row tile and N a multiple of 256: 256 x 256 tiles on CTA pairs
+  if (gp.m > kGemmBM && gp.n % kPairBN == 0 && gemm_pairs_enabled()) {
+    static bool pair_attr_set = false;
+    if (!pair_attr_set) {
+      cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+      if (e != cudaSuccess) return e;
+      pair_attr_set = true;
+    }
+    const int tiles = ((gp.m + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (gp.n / kPairBN);
+    const int clusters = std::min(tiles, std::max(1, lxg::num_sms() / 2));
+    gemm_pair_kernel<EPI><<<2 * clusters, kPairThreads, kPairSmem, st>>>(a, w, gp);
+    return cudaGetLastError();
+  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);

@@ -99,8 +99,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int mode, int tt, int tf, cudaS
   const float eps = e->w.rms_eps;
   int launches = 0;
   const int row_blocks = (tokens + 7) / 8;
-  const long long rope_warps = static_cast<long long>(tokens) * (heads + kvh);
-  const int rope_blocks = static_cast<int>((rope_warps + 7) / 8);
+  const int rope_blocks = row_blocks;  // one warp per token
   const dim3 attn_grid((s + kCausalRows - 1) / kCausalRows, heads, b);
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];

@@ -38,7 +38,7 @@ def _compare(got, want):
 @pytest.mark.parametrize("geom,b,s,pool", [
     ("tiny", 5, 19, "mean"), ("tiny", 3, 8, "cls"), ("tiny", 1, 1, "mean"),
     ("minilm-l6", 4, 24, "mean"), ("minilm-l6", 9, 33, "mean"), ("minilm-l6", 3, 130, "cls"),
-    ("bge-base", 4, 24, "cls"), ("bge-base", 2, 17, "mean"),
+    ("bge-base", 4, 24, "cls"), ("bge-base", 2, 17, "mean"), ("bge-base", 6, 40, "cls"),
 ])
 def test_encoder_matches_hf_oracle(geom, b, s, pool):
     model, cfg = be.make_model(geom, seed=0)
