@@ -502,7 +502,7 @@ def decoder_numbers(dev, cpu: bool):
     """The shipped models: Qwen3-Embedding-0.6B forward behind
     EmbeddingClient.embed and Qwen3-Reranker-0.6B behind RerankerClient._compute_scores_sync, on
     random-init weights of the real geometry (vocabulary cut to 4096 rows: it only feeds a gather),
-    synthetic left-padded token ids.  CPU leg: HF Qwen3ForCausalLM fp32 on the host cores through
+    synthetic left-padded token ids with ragged lengths (uniform in [S/4, S]).  CPU leg: HF Qwen3ForCausalLM fp32 on the host cores through
     oracle/qwen3_decoder.py."""
     import torch
 
@@ -529,8 +529,10 @@ def decoder_numbers(dev, cpu: bool):
         for _ in range(iters):
             call()  # host ids in, host result out: H2D + forward + D2H + sync inside the timing
         ms = (time.perf_counter() - t0) / iters * 1e3
+        computed = dec.last_tokens()  # host batches are packed: padding tokens never enter the layers
         res[label] = {"e2e_ms_per_call": round(ms, 4), "items_per_s": round(b / (ms / 1e3), 1),
-                      "gemm_tflops": round(flop_tok * b * sl / (ms / 1e3) / 1e12, 2)}
+                      "tokens_padded": b * sl, "tokens_computed": computed,
+                      "gemm_tflops": round(flop_tok * computed / (ms / 1e3) / 1e12, 2)}
     res["launches"] = dec.last_launches()
     if cpu:
         res["cpu_baseline"] = {"kind": "HF Qwen3ForCausalLM fp32, torch %d threads" % torch.get_num_threads()}

@@ -100,6 +100,7 @@ SIGNATURES = {
     "lxg_decoder_create": (c_int, [POINTER(c_void_p), POINTER(Qwen3Weights)]),
     "lxg_decoder_destroy": (c_int, [c_void_p]),
     "lxg_decoder_last_launches": (c_int, [c_void_p]),
+    "lxg_decoder_last_tokens": (c_int, [c_void_p]),
     "lxg_decoder_embed": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "lxg_decoder_rerank": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p,
                                    c_void_p]),

@@ -78,14 +78,15 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
 // same lane and every access is a half2.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
 // with HF's fp32 inv_freq table (Qwen3RotaryEmbedding).
 static __global__ void __launch_bounds__(256)
-qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, int kv_heads,
+qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __restrict__ pos_of, int heads, int kv_heads,
                     const float* __restrict__ q_w, const float* __restrict__ k_w,
                     const float* __restrict__ inv_freq, float eps) {
   constexpr int DH = 128;
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
-  const float pos = static_cast<float>(t % seq);
+  // packed batches carry the position of every token; padded ones use the column index
+  const float pos = static_cast<float>(pos_of != nullptr ? pos_of[t] : t % seq);
   const float2 f = *reinterpret_cast<const float2*>(inv_freq + 2 * lane);
   float s0, c0, s1, c1;
   sincosf(pos * f.x, &s0, &c0);
@@ -117,12 +118,13 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, int heads, in
 // row-major; the P.V operand is read transposed with ldmatrix.trans), scores and context run on
 // mma.sync m16n8k16 with an fp32 online softmax.  Key j is visible to query i iff j <= i and mask[j] != 0 (HF create_causal_mask with a
 // padding mask); rows with no visible key (left padding) yield 0 and are never read downstream.
+// Packed batches (cu != NULL, no padding tokens at all) give sequence b the tokens [cu[b], cu[b+1]).
 constexpr int kCausalRows = 64;
 constexpr int kCausalKeys = 64;
 
 template <int DH>
 __global__ void __launch_bounds__(kCausalRows * 2, 3)
-attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int heads,
+attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, const int* __restrict__ cu, int seq, int heads,
                         int kv_heads, __half* __restrict__ ctx) {
   constexpr int kKSteps = DH / 16;
   constexpr int kOTiles = DH / 8;
@@ -131,11 +133,15 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
   __shared__ __align__(16) __half vs[kCausalKeys * kKPitch];
   __shared__ float bias[kCausalKeys];
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  // packed batch (cu != NULL): sequence b is tokens [cu[b], cu[b+1]), every key is real
+  const int tok0 = cu != nullptr ? cu[b] : b * seq;
+  if (cu != nullptr) seq = cu[b + 1] - tok0;
+  if (qb * kCausalRows >= seq) return;  // whole CTA, before any barrier
   const int kvh = h / (heads / kv_heads);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, t = lane & 3;
   const size_t row_stride = static_cast<size_t>(heads + 2 * kv_heads) * DH;
-  const __half* base = qkv + static_cast<size_t>(b) * seq * row_stride;
+  const __half* base = qkv + static_cast<size_t>(tok0) * row_stride;
   const __half* qbase = base + static_cast<size_t>(h) * DH;
   const __half* kbase = base + static_cast<size_t>(heads + kvh) * DH;
   const __half* vbase = base + static_cast<size_t>(heads + kv_heads + kvh) * DH;
@@ -173,7 +179,7 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
       *reinterpret_cast<uint4*>(vs + j * kKPitch + 8 * c) = vv;
     }
     for (int j = threadIdx.x; j < kCausalKeys; j += blockDim.x)
-      bias[j] = (kb0 + j < seq && mask[b * seq + kb0 + j] != 0) ? 0.f : -CUDART_INF_F;
+      bias[j] = (kb0 + j < seq && (cu != nullptr || mask[tok0 + kb0 + j] != 0)) ? 0.f : -CUDART_INF_F;
     __syncthreads();
     if (!active || kb0 > wrow0 + 15) continue;  // warp-uniform: chunk entirely in this warp's future
 
@@ -251,8 +257,8 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float inv0 = l0 > 0.f ? 1.f / l0 : 0.f, inv1 = l1 > 0.f ? 1.f / l1 : 0.f;
   const size_t ctx_stride = static_cast<size_t>(heads) * DH;
-  __half* out0 = ctx + (static_cast<size_t>(b) * seq + r0) * ctx_stride + h * DH + 2 * t;
-  __half* out1 = ctx + (static_cast<size_t>(b) * seq + r1) * ctx_stride + h * DH + 2 * t;
+  __half* out0 = ctx + (static_cast<size_t>(tok0) + r0) * ctx_stride + h * DH + 2 * t;
+  __half* out1 = ctx + (static_cast<size_t>(tok0) + r1) * ctx_stride + h * DH + 2 * t;
 #pragma unroll
   for (int n = 0; n < kOTiles; ++n) {
     if (r0 < seq) *reinterpret_cast<__half2*>(out0 + n * 8) = __floats2half2_rn(o[n][0] * inv0, o[n][1] * inv0);
@@ -268,7 +274,7 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
 //   mode 1 (reranker) : out[b] = softmax([false, true] logits)[1] with logits = x . lm_head[token]
 //                       (reranker_client.py:127-139)
 static __global__ void __launch_bounds__(256)
-last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ mask, int seq, int hidden,
+last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ mask, const int* __restrict__ cu, int seq, int hidden,
                        const float* __restrict__ norm_w, float eps, int mode, const __half* __restrict__ lm_head,
                        int token_true, int token_false, float* __restrict__ out) {
   const int b = blockIdx.x;
@@ -276,12 +282,16 @@ last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ 
   __shared__ int s_last;
   extern __shared__ float xs[];
   if (threadIdx.x == 0) {
-    int last = seq - 1;
-    while (last > 0 && mask[b * seq + last] == 0) --last;
-    s_last = last;
+    if (cu != nullptr) {
+      s_last = cu[b + 1] - 1;  // packed: absolute index of the sequence's last token
+    } else {
+      int last = seq - 1;
+      while (last > 0 && mask[b * seq + last] == 0) --last;
+      s_last = b * seq + last;
+    }
   }
   __syncthreads();
-  const float* x = resid + (static_cast<size_t>(b) * seq + s_last) * hidden;
+  const float* x = resid + static_cast<size_t>(s_last) * hidden;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
   auto block_sum = [&](float v, int slot) {
 #pragma unroll

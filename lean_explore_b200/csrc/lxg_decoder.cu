@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -27,9 +28,15 @@ struct lxg_decoder {
   float* resid = nullptr;                                          // fp32 residual stream [cap, H]
   __half *hn = nullptr, *qkv = nullptr, *ctx = nullptr, *act = nullptr;  // normed rows, QKV, context, SwiGLU output
   int *ids = nullptr, *mask = nullptr;
+  int *pos = nullptr, *cu = nullptr;   // packed batches: position of every token, sequence offsets [b + 1]
+  int cu_cap = 0;
+  int* stage = nullptr;                // pinned host staging: packed ids | pos | cu
+  size_t stage_cap = 0;                // ints
+  bool pack = true;                    // LXG_DECODER_PACK=0: always compute the padded rectangle
   CUtensorMap map_hn{}, map_ctx{}, map_act{};
   std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
   int launches = 0;
+  int last_tokens = 0;  // tokens the last forward actually computed (after packing)
   struct Graph {
     int b, s, mode, tt, tf;
     cudaGraphExec_t exec;
@@ -60,6 +67,8 @@ void free_ws(lxg_decoder* e) {
   cudaFree(e->act);
   cudaFree(e->ids);
   cudaFree(e->mask);
+  cudaFree(e->pos);
+  e->pos = nullptr;
   e->resid = nullptr;
   e->hn = e->qkv = e->ctx = e->act = nullptr;
   e->ids = e->mask = nullptr;
@@ -79,6 +88,7 @@ int reserve_ws(lxg_decoder* e, int tokens) {
   LXG_CUDA(cudaMalloc(&e->act, cap * F * sizeof(__half)));
   LXG_CUDA(cudaMalloc(&e->ids, cap * sizeof(int)));
   LXG_CUDA(cudaMalloc(&e->mask, cap * sizeof(int)));
+  LXG_CUDA(cudaMalloc(&e->pos, cap * sizeof(int)));
   // rows beyond the live tokens are read by TMA (never stored): keep them finite
   LXG_CUDA(cudaMemset(e->hn, 0, cap * H * sizeof(__half)));
   LXG_CUDA(cudaMemset(e->ctx, 0, cap * C * sizeof(__half)));
@@ -92,8 +102,11 @@ int reserve_ws(lxg_decoder* e, int tokens) {
 }
 
 // 1 + 8 * layers + 1 launches on `st`, workspace pointers only (graph-capturable).
-int launch_forward(lxg_decoder* e, int b, int s, int mode, int tt, int tf, cudaStream_t st) {
-  const int tokens = b * s;
+// Padded: tokens = b * s, `s` columns per sequence, key mask from e->mask.  Packed: `tokens` real
+// tokens back to back, sequence i = [cu[i], cu[i+1]), `s` = the longest sequence.
+int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mode, int tt, int tf, cudaStream_t st) {
+  const int* pos_of = packed ? e->pos : nullptr;
+  const int* cu = packed ? e->cu : nullptr;
   const int H = e->w.hidden, F = e->w.ffn, heads = e->w.heads, kvh = e->w.kv_heads;
   const int QKV = (heads + 2 * kvh) * kHeadDim, C = heads * kHeadDim;
   const float eps = e->w.rms_eps;
@@ -116,11 +129,11 @@ int launch_forward(lxg_decoder* e, int b, int s, int mode, int tt, int tf, cudaS
     gp.n = QKV;
     gp.k = H;
     LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st));
-    qk_norm_rope_kernel<<<rope_blocks, 256, 0, st>>>(e->qkv, tokens, s, heads, kvh, reinterpret_cast<const float*>(L.q_norm),
+    qk_norm_rope_kernel<<<rope_blocks, 256, 0, st>>>(e->qkv, tokens, s, pos_of, heads, kvh, reinterpret_cast<const float*>(L.q_norm),
                                                      reinterpret_cast<const float*>(L.k_norm),
                                                      reinterpret_cast<const float*>(e->w.inv_freq), eps);
     LXG_CUDA(cudaGetLastError());
-    attention_causal_kernel<kHeadDim><<<attn_grid, kCausalRows * 2, 0, st>>>(e->qkv, e->mask, s, heads, kvh, e->ctx);
+    attention_causal_kernel<kHeadDim><<<attn_grid, kCausalRows * 2, 0, st>>>(e->qkv, e->mask, cu, s, heads, kvh, e->ctx);
     LXG_CUDA(cudaGetLastError());
     // o_proj, accumulated onto the residual stream
     gp.out = e->resid;
@@ -142,7 +155,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int mode, int tt, int tf, cudaS
     LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st));
     launches += 8;
   }
-  last_token_head_kernel<<<b, 256, H * sizeof(float), st>>>(e->resid, e->mask, s, H, reinterpret_cast<const float*>(e->w.final_norm),
+  last_token_head_kernel<<<b, 256, H * sizeof(float), st>>>(e->resid, e->mask, cu, s, H, reinterpret_cast<const float*>(e->w.final_norm),
                                                             eps, mode, reinterpret_cast<const __half*>(e->w.lm_head), tt, tf,
                                                             e->out_buf);
   LXG_CUDA(cudaGetLastError());
@@ -178,8 +191,72 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
   LXG_CUDA(cudaStreamWaitEvent(st, e->ev_in, 0));
   const int H = e->w.hidden;
   const bool ids_dev = is_device_ptr(ids), mask_dev = is_device_ptr(mask), out_dev = is_device_ptr(out);
-  LXG_CUDA(cudaMemcpyAsync(e->ids, ids, tokens * sizeof(int), ids_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
-  LXG_CUDA(cudaMemcpyAsync(e->mask, mask, tokens * sizeof(int), mask_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  // ---- packing: with host inputs and more than one sequence, padding tokens are dropped on the
+  // host (every mask row must be one contiguous run of ones - what a tokenizer's left / right
+  // padding produces) and only the real tokens go through the layers.  RoPE is relative and pad
+  // keys are masked in the padded formulation, so both compute the same function.
+  int live_tokens = tokens, max_len = s;
+  bool packed = false;
+  if (e->pack && b > 1 && !ids_dev && !mask_dev) {
+    const size_t need = static_cast<size_t>(2) * tokens + b + 1;
+    if (need > e->stage_cap) {
+      if (e->stage) cudaFreeHost(e->stage);
+      e->stage = nullptr;
+      e->stage_cap = 0;
+      LXG_CUDA(cudaMallocHost(&e->stage, need * sizeof(int)));
+      e->stage_cap = need;
+    }
+    if (b + 1 > e->cu_cap) {
+      cudaFree(e->cu);
+      e->cu = nullptr;
+      e->cu_cap = 0;
+      LXG_CUDA(cudaMalloc(&e->cu, static_cast<size_t>(b + 1) * sizeof(int)));
+      e->cu_cap = b + 1;
+    }
+    // the previous call's H2D copies from the staging buffer must have drained
+    LXG_CUDA(cudaStreamSynchronize(st));
+    int* pid = e->stage;
+    int* ppos = e->stage + tokens;
+    int* pcu = e->stage + 2 * static_cast<size_t>(tokens);
+    int n = 0, longest = 1;
+    bool ok = true;
+    for (int i = 0; i < b && ok; ++i) {
+      const int32_t* mrow = mask + static_cast<size_t>(i) * s;
+      const int32_t* irow = ids + static_cast<size_t>(i) * s;
+      int first = 0;
+      while (first < s && mrow[first] == 0) ++first;
+      int last = s - 1;
+      while (last >= first && mrow[last] == 0) --last;
+      for (int j = first; j <= last; ++j) ok = ok && mrow[j] != 0;
+      pcu[i] = n;
+      if (last < first) {  // no token at all: keep one (padding) token so the row stays defined
+        pid[n] = irow[s - 1];
+        ppos[n] = 0;
+        ++n;
+        continue;
+      }
+      for (int j = first; j <= last; ++j) {
+        pid[n] = irow[j];
+        ppos[n] = j - first;
+        ++n;
+      }
+      longest = std::max(longest, last - first + 1);
+    }
+    pcu[b] = n;
+    if (ok) {
+      packed = true;
+      live_tokens = n;
+      max_len = longest;
+      LXG_CUDA(cudaMemcpyAsync(e->ids, pid, n * sizeof(int), cudaMemcpyHostToDevice, st));
+      LXG_CUDA(cudaMemcpyAsync(e->pos, ppos, n * sizeof(int), cudaMemcpyHostToDevice, st));
+      LXG_CUDA(cudaMemcpyAsync(e->cu, pcu, (b + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+  }
+  if (!packed) {
+    LXG_CUDA(cudaMemcpyAsync(e->ids, ids, tokens * sizeof(int), ids_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    LXG_CUDA(cudaMemcpyAsync(e->mask, mask, tokens * sizeof(int), mask_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+  }
+  e->last_tokens = live_tokens;
   const size_t out_floats = mode == 0 ? static_cast<size_t>(b) * H : static_cast<size_t>(b);
   if (out_floats > e->out_cap) {
     drop_graphs(e);
@@ -191,7 +268,12 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
     e->out_cap = cap;
   }
   bool ran = false;
-  if (e->use_graphs) {
+  if (packed) {
+    // ragged shapes rarely repeat and a bulk forward is not launch bound: plain launches
+    rc = launch_forward(e, b, max_len, live_tokens, true, mode, tt, tf, st);
+    if (rc != LXG_OK) return rc;
+    ran = true;
+  } else if (e->use_graphs) {
     cudaGraphExec_t exec = nullptr;
     for (auto& g : e->graphs)
       if (g.b == b && g.s == s && g.mode == mode && g.tt == tt && g.tf == tf) exec = g.exec;
@@ -200,12 +282,12 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
       ran = true;
     } else {
       // first call with this shape: run eagerly (sets kernel attributes), then capture for later calls
-      rc = launch_forward(e, b, s, mode, tt, tf, st);
+      rc = launch_forward(e, b, s, tokens, false, mode, tt, tf, st);
       if (rc != LXG_OK) return rc;
       ran = true;
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-        const int rc2 = launch_forward(e, b, s, mode, tt, tf, st);
+        const int rc2 = launch_forward(e, b, s, tokens, false, mode, tt, tf, st);
         const cudaError_t ce = cudaStreamEndCapture(st, &graph);
         if (rc2 == LXG_OK && ce == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
           if (e->graphs.size() >= 64) drop_graphs(e);
@@ -222,7 +304,7 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
     }
   }
   if (!ran) {
-    rc = launch_forward(e, b, s, mode, tt, tf, st);
+    rc = launch_forward(e, b, s, tokens, false, mode, tt, tf, st);
     if (rc != LXG_OK) return rc;
   }
   LXG_CUDA(cudaMemcpyAsync(out, e->out_buf, out_floats * sizeof(float), out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
@@ -277,6 +359,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
       return rc;
     }
   }
+  const char* pk = std::getenv("LXG_DECODER_PACK");
+  e->pack = !(pk && pk[0] == '0');
   *out = e;
   return LXG_OK;
 }
@@ -285,6 +369,8 @@ int lxg_decoder_destroy(lxg_decoder* e) {
   if (!e) return LXG_OK;
   free_ws(e);
   cudaFree(e->out_buf);
+  cudaFree(e->cu);
+  if (e->stage) cudaFreeHost(e->stage);
   if (e->own) cudaStreamDestroy(e->own);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -293,6 +379,7 @@ int lxg_decoder_destroy(lxg_decoder* e) {
 }
 
 int lxg_decoder_last_launches(const lxg_decoder* e) { return e ? e->launches : -1; }
+int lxg_decoder_last_tokens(const lxg_decoder* e) { return e ? e->last_tokens : -1; }
 
 int lxg_decoder_embed(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, float* out, void* stream) {
   return run(e, ids, mask, b, s, 0, 0, 0, out, stream);

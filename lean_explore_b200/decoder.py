@@ -106,6 +106,10 @@ class Qwen3Decoder:
     def last_launches(self) -> int:
         return int(self._lib.lxg_decoder_last_launches(self._handle))
 
+    def last_tokens(self) -> int:
+        """Tokens the last forward computed (padding tokens are dropped for host batches)."""
+        return int(self._lib.lxg_decoder_last_tokens(self._handle))
+
     @staticmethod
     def _prep(input_ids, attention_mask):
         ids = np.ascontiguousarray(input_ids, dtype=np.int32)

@@ -102,15 +102,48 @@ def test_padding_content_graph_replay_and_device_io():
     assert (a == b).all()
     ids2 = np.where(mask == 1, ids, 777).astype(np.int32)
     assert np.abs(dec.embed_ids(ids2, mask) - a).max() < 1e-6
-    got = dec.embed_ids_torch(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda())
+    assert dec.last_tokens() == int(mask.sum())  # host batch: padding tokens were dropped before layer 0
+    want = qd.embed(model, ids, mask)
+    got = dec.embed_ids_torch(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda())  # device ids: padded rectangle
     torch.cuda.synchronize()
-    assert (got.cpu().numpy() == a).all()
-    _compare_emb(a, qd.embed(model, ids, mask))
+    assert dec.last_tokens() == ids.size
+    _compare_emb(got.cpu().numpy(), want)
+    got2 = dec.embed_ids_torch(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda())  # graph replay
+    torch.cuda.synchronize()
+    assert (got2 == got).all()
+    assert np.abs(got.cpu().numpy() - a).max() < TOL_EMB  # packed and padded formulations agree
+    _compare_emb(a, want)
     # left padding == the same sequences without padding, one by one (positions shift, RoPE is relative)
     for i in (1, 5):
         n = int(mask[i].sum())
         solo = dec.embed_ids(ids[i : i + 1, 48 - n :], np.ones((1, n), np.int32))
         assert np.abs(solo[0] - a[i]).max() < TOL_EMB
+
+
+def test_packed_and_padded_paths_agree_and_holes_fall_back(monkeypatch):
+    """LXG_DECODER_PACK=0 keeps the padded rectangle for host batches too; a mask with a hole is not
+    a padding pattern, so it takes the padded path (HF semantics: positions keep counting, the
+    hole is only masked as a key)."""
+    from lean_explore_b200.decoder import Qwen3Decoder
+
+    model, cfg, dec = _pair("tiny")
+    monkeypatch.setenv("LXG_DECODER_PACK", "0")
+    padded = Qwen3Decoder(model.state_dict(), hidden=cfg.hidden_size, layers=cfg.num_hidden_layers,
+                          heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads, ffn=cfg.intermediate_size,
+                          head_dim=cfg.head_dim, rms_eps=cfg.rms_norm_eps, rope_theta=1e6)
+    for side in ("left", "right"):
+        ids, mask = qd.make_inputs(9, 90, seed=21, side=side)
+        a, b = dec.embed_ids(ids, mask), padded.embed_ids(ids, mask)
+        assert dec.last_tokens() == int(mask.sum()) and padded.last_tokens() == ids.size
+        assert np.abs(a - b).max() < TOL_EMB
+        _compare_emb(a, qd.embed(model, ids, mask))
+    ids, mask = qd.make_inputs(4, 30, seed=22, side="left")
+    mask[2, 20] = 0  # a hole
+    got = dec.embed_ids(ids, mask)
+    assert dec.last_tokens() == ids.size
+    _compare_emb(got, qd.embed(model, ids, mask))
+    sc = dec.rerank_ids(ids, mask, TOKEN_TRUE, TOKEN_FALSE)
+    _compare_scores(sc, qd.rerank(model, ids, mask, TOKEN_TRUE, TOKEN_FALSE))
 
 
 def test_argument_errors():
