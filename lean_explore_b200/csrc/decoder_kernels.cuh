@@ -19,10 +19,12 @@ namespace lxg {
 // ------------------------------------------------------------------ RMSNorm
 // One warp per token: out = x * rsqrt(mean(x^2) + eps) * w   (fp32 in, fp16 out).  With ids != NULL
 // the row is first gathered from the token-embedding table and written to the residual stream
-// (the first layer's input_layernorm fused with embed_tokens).
+// (the first layer's input_layernorm fused with embed_tokens).  With nsplit > 0 the row first
+// absorbs the split-K partial sums of the preceding projection.
 static __global__ void __launch_bounds__(256)
 rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __half* __restrict__ tok_emb, int vocab,
-               int tokens, int hidden, const float* __restrict__ w, float eps, __half* __restrict__ out) {
+               int tokens, int hidden, const float* __restrict__ w, float eps, __half* __restrict__ out,
+               const float* __restrict__ partial, int nsplit, size_t split_stride) {
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
@@ -52,6 +54,17 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
       v[i] = make_float2(0.f, 0.f);
       if (j < n2) {
         v[i] = x2[j];
+        if (nsplit > 0) {
+          // split-K partial sums of the preceding o_proj / down_proj (skinny path): added here in
+          // slab order, and the residual stream is updated in passing
+          const float2* p2 = reinterpret_cast<const float2*>(partial + static_cast<size_t>(t) * hidden) + j;
+          for (int sidx = 0; sidx < nsplit; ++sidx) {
+            const float2 a = p2[sidx * (split_stride >> 1)];
+            v[i].x += a.x;
+            v[i].y += a.y;
+          }
+          x2[j] = v[i];
+        }
         ss += v[i].x * v[i].x + v[i].y * v[i].y;
       }
     }
@@ -70,6 +83,59 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
   }
 }
 
+// Skinny path (<= 128 tokens): one CTA per token.  Adds the split-K partial slabs of the preceding
+// o_proj / down_proj to the residual row (slab order, so the sum is reproducible), writes the row
+// back and normalises it.  All slab loads of a thread are independent and in flight together - a
+// warp per token (rmsnorm_kernel) would walk them as one long dependent chain.
+static __global__ void __launch_bounds__(256)
+rmsnorm_partial_kernel(float* __restrict__ resid, int hidden, const float* __restrict__ w, float eps,
+                       __half* __restrict__ out, const float* __restrict__ partial, int nsplit, size_t split_stride) {
+  constexpr int kMaxSplit = 16;
+  const int t = blockIdx.x;
+  const int n2 = hidden >> 1;
+  __shared__ float red[8];
+  float2* x2 = reinterpret_cast<float2*>(resid + static_cast<size_t>(t) * hidden);
+  const float2* p2 = reinterpret_cast<const float2*>(partial + static_cast<size_t>(t) * hidden);
+  float2 v[2];
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {  // hidden <= 1024: two float2 per thread
+    const int j = i * 256 + threadIdx.x;
+    v[i] = make_float2(0.f, 0.f);
+    if (j < n2) {
+      float2 a[kMaxSplit];
+#pragma unroll
+      for (int sidx = 0; sidx < kMaxSplit; ++sidx)
+        a[sidx] = sidx < nsplit ? p2[sidx * (split_stride >> 1) + j] : make_float2(0.f, 0.f);
+      v[i] = x2[j];
+#pragma unroll
+      for (int sidx = 0; sidx < kMaxSplit; ++sidx) {
+        v[i].x += a[sidx].x;
+        v[i].y += a[sidx].y;
+      }
+      x2[j] = v[i];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) tot += red[k];
+  const float rstd = rsqrtf(tot / hidden + eps);
+  __half2* o2 = reinterpret_cast<__half2*>(out + static_cast<size_t>(t) * hidden);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int j = i * 256 + threadIdx.x;
+    if (j < n2) {
+      const float2 ww = reinterpret_cast<const float2*>(w)[j];
+      o2[j] = __floats2half2_rn(v[i].x * rstd * ww.x, v[i].y * rstd * ww.y);
+    }
+  }
+}
+
 // ------------------------------------------------------------------ q/k head RMSNorm + RoPE
 // In place on the QKV projection [tokens, (heads + 2 kv_heads) * 128] (fp16): one warp per token,
 // looping over its q and k heads (they share the position, so cos / sin are evaluated once per
@@ -78,13 +144,18 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
 // same lane and every access is a half2.  cos/sin are evaluated in fp32 on angle = pos * inv_freq[i]
 // with HF's fp32 inv_freq table (Qwen3RotaryEmbedding).
 static __global__ void __launch_bounds__(256)
-qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __restrict__ pos_of, int heads, int kv_heads,
+qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __restrict__ pos_of, int heads, int kv_heads, int hgroup,
                     const float* __restrict__ q_w, const float* __restrict__ k_w,
                     const float* __restrict__ inv_freq, float eps) {
   constexpr int DH = 128;
   const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (t >= tokens) return;
+  // a warp owns `hgroup` consecutive heads of one token: all of them for bulk batches (cos / sin
+  // once per token), one for a handful of tokens (more warps, shorter dependent chains)
+  const int nh = heads + kv_heads;
+  const int groups = (nh + hgroup - 1) / hgroup;
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= tokens * groups) return;
+  const int t = wid / groups, h_begin = (wid % groups) * hgroup, h_end = min(nh, h_begin + hgroup);
   // packed batches carry the position of every token; padded ones use the column index
   const float pos = static_cast<float>(pos_of != nullptr ? pos_of[t] : t % seq);
   const float2 f = *reinterpret_cast<const float2*>(inv_freq + 2 * lane);
@@ -94,9 +165,8 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __
   const float2 qlo = *reinterpret_cast<const float2*>(q_w + 2 * lane), qhi = *reinterpret_cast<const float2*>(q_w + 64 + 2 * lane);
   const float2 klo = *reinterpret_cast<const float2*>(k_w + 2 * lane), khi = *reinterpret_cast<const float2*>(k_w + 64 + 2 * lane);
   __half* row = qkv + static_cast<size_t>(t) * (heads + 2 * kv_heads) * DH;
-  const int nh = heads + kv_heads;
 #pragma unroll 4
-  for (int h = 0; h < nh; ++h) {
+  for (int h = h_begin; h < h_end; ++h) {
     __half* p = row + h * DH;
     const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(p + 2 * lane));
     const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(p + 64 + 2 * lane));
@@ -276,7 +346,8 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
 static __global__ void __launch_bounds__(256)
 last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ mask, const int* __restrict__ cu, int seq, int hidden,
                        const float* __restrict__ norm_w, float eps, int mode, const __half* __restrict__ lm_head,
-                       int token_true, int token_false, float* __restrict__ out) {
+                       int token_true, int token_false, float* __restrict__ out,
+                       const float* __restrict__ partial, int nsplit, size_t split_stride) {
   const int b = blockIdx.x;
   __shared__ float red[3][8];
   __shared__ int s_last;
@@ -305,7 +376,9 @@ last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ 
   };
   float ss = 0.f;
   for (int c = threadIdx.x; c < hidden; c += blockDim.x) {
-    const float v = x[c];
+    float v = x[c];
+    for (int sidx = 0; sidx < nsplit; ++sidx)  // split-K partials of the last down_proj
+      v += partial[static_cast<size_t>(sidx) * split_stride + static_cast<size_t>(s_last) * hidden + c];
     xs[c] = v;
     ss += v * v;
   }

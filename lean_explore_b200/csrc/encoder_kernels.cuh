@@ -135,7 +135,9 @@ __device__ __forceinline__ uint32_t pack_half2(float x, float y) {
 //   kEpiSwiGLU: silu(gate) * up, fp16 out [M, N/2]; W rows interleaved per 128-row tile as
 //               gate[32] | up[32] | gate[32] | up[32] so one thread holds both halves of a column
 // bias may be NULL (decoder projections have none).
-enum GemmEpilogue { kEpiStore = 0, kEpiGelu = 1, kEpiResid = 2, kEpiAccF32 = 3, kEpiSwiGLU = 4 };
+//   kEpiPartial: fp32 out [ksplit][M, N] - split-K partial sums of a skinny GEMM (M <= 128): the
+//               consumer (RMSNorm / head kernel) adds the slabs to the residual stream in a fixed order
+enum GemmEpilogue { kEpiStore = 0, kEpiGelu = 1, kEpiResid = 2, kEpiAccF32 = 3, kEpiSwiGLU = 4, kEpiPartial = 5 };
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBN = 128;
@@ -151,6 +153,8 @@ struct GemmParams {
   const __half* residual;  // [M, N] (kEpiResid)
   void* out;               // fp16 [M, N] or fp32 [M, N]
   int m, n, k;
+  int ksplit;              // single-CTA kernel only: K is cut into ksplit ranges, one tile each (0 / 1 = off)
+  size_t split_stride;     // kEpiPartial: elements between the partial slabs
 };
 
 // Epilogue of one thread (= one output row) over `nchunks` 32-column chunks of an accumulator,
@@ -224,6 +228,10 @@ __device__ __forceinline__ void gemm_epilogue_row(uint32_t taddr, int c0, int nc
             o4[2 * j] = make_float4(v[8 * j] + a.x, v[8 * j + 1] + a.y, v[8 * j + 2] + b.x, v[8 * j + 3] + b.y);
             o4[2 * j + 1] = make_float4(v[8 * j + 4] + cc.x, v[8 * j + 5] + cc.y, v[8 * j + 6] + d.x, v[8 * j + 7] + d.y);
           }
+        } else if constexpr (EPI == kEpiPartial) {
+          float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
         } else if constexpr (EPI == kEpiAccF32) {
           float4* o4 = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + static_cast<size_t>(row) * p.n + col0);
 #pragma unroll
@@ -272,7 +280,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (p.m + kGemmBM - 1) / kGemmBM;
-  const int tiles = tiles_m * (p.n / kGemmBN);
+  const int tiles_mn = tiles_m * (p.n / kGemmBN);
+  const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
+  const int tiles = tiles_mn * ksplit;  // tile t: k range t / tiles_mn, output tile t % tiles_mn
   const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
   const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kGemmBM, kGemmBN);
@@ -308,8 +318,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const uint32_t ring0 = ptx::opaque(ring_u32);
     uint32_t stage = 0, phase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
-      const int m0 = (t % tiles_m) * kGemmBM, n0 = (t / tiles_m) * kGemmBN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int ks = t / tiles_mn, tt = t % tiles_mn;
+      const int m0 = (tt % tiles_m) * kGemmBM, n0 = (tt / tiles_m) * kGemmBN;
+      const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t fb = full0 + stage * 8;
@@ -339,7 +351,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::mbar_wait_a(aempty0 + acc * 8, ((it >> 1) & 1) ^ 1u);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * kGemmBN;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      const int ks = t / tiles_mn;
+      const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
+      for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait_a(full0 + stage * 8, phase);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
@@ -348,10 +362,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           for (int k4 = 0; k4 < 4; ++k4) {
             const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (lo + k4 * 2);
             const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (lo + ((kGemmBM * kGemmBK * 2) >> 4) + k4 * 2);
-            ptx::mma_f16_ss(d_tmem, adesc, bdesc, kIdesc, (kb | k4) != 0 ? 1u : 0u);
+            ptx::mma_f16_ss(d_tmem, adesc, bdesc, kIdesc, ((kb - kb0) | k4) != 0 ? 1u : 0u);
           }
           ptx::tc_commit_a(empty0 + stage * 8);
-          if (kb == num_kb - 1) ptx::tc_commit_a(afull0 + acc * 8);
+          if (kb == kb1 - 1) ptx::tc_commit_a(afull0 + acc * 8);
         }
         __syncwarp();
         if (++stage == kGemmStages) {
@@ -368,11 +382,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int it = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
-      const int m0 = (t % tiles_m) * kGemmBM, n0 = (t / tiles_m) * kGemmBN;
+      const int ks = t / tiles_mn, tt = t % tiles_mn;
+      const int m0 = (tt % tiles_m) * kGemmBM, n0 = (tt / tiles_m) * kGemmBN;
       const int row = m0 + (warp & 3) * 32 + lane;
       ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-      gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kGemmBN, half * 2, 2, row, n0, p);
+      if constexpr (EPI == kEpiPartial) {
+        GemmParams ps = p;  // this k range's slab
+        ps.out = reinterpret_cast<float*>(p.out) + static_cast<size_t>(ks) * p.split_stride;
+        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kGemmBN, half * 2, 2, row, n0, ps);
+      } else {
+        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kGemmBN, half * 2, 2, row, n0, p);
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty_bar[acc]);

@@ -58,7 +58,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  const int tiles = ((gp.m + kGemmBM - 1) / kGemmBM) * (gp.n / kGemmBN);
+  const int tiles = ((gp.m + kGemmBM - 1) / kGemmBM) * (gp.n / kGemmBN) * std::max(1, gp.ksplit);
   gemm_tc_kernel<EPI><<<std::min(tiles, std::max(1, lxg::num_sms())), kGemmThreads, kGemmSmem, st>>>(a, w, gp);
   return cudaGetLastError();
 }

@@ -26,6 +26,7 @@ struct lxg_decoder {
   std::mutex mu;
   int cap_tokens = 0;
   float* resid = nullptr;                                          // fp32 residual stream [cap, H]
+  float* partial = nullptr;                                        // skinny path: split-K slabs [kSkinnySplits][128, H]
   __half *hn = nullptr, *qkv = nullptr, *ctx = nullptr, *act = nullptr;  // normed rows, QKV, context, SwiGLU output
   int *ids = nullptr, *mask = nullptr;
   int *pos = nullptr, *cu = nullptr;   // packed batches: position of every token, sequence offsets [b + 1]
@@ -52,6 +53,8 @@ struct lxg_decoder {
 namespace {
 
 constexpr int kHeadDim = 128;
+constexpr int kSkinnyRows = 128;    // up to one row tile the o_proj / down_proj GEMMs are split along K ...
+constexpr int kSkinnySplits = 16;   // ... into this many ranges (8 output tiles x 16 = 128 CTAs instead of 8)
 
 void drop_graphs(lxg_decoder* e) {
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
@@ -61,6 +64,8 @@ void drop_graphs(lxg_decoder* e) {
 void free_ws(lxg_decoder* e) {
   drop_graphs(e);
   cudaFree(e->resid);
+  cudaFree(e->partial);
+  e->partial = nullptr;
   cudaFree(e->hn);
   cudaFree(e->qkv);
   cudaFree(e->ctx);
@@ -82,6 +87,7 @@ int reserve_ws(lxg_decoder* e, int tokens) {
   const size_t H = e->w.hidden, F = e->w.ffn;
   const size_t QKV = static_cast<size_t>(e->w.heads + 2 * e->w.kv_heads) * kHeadDim, C = static_cast<size_t>(e->w.heads) * kHeadDim;
   LXG_CUDA(cudaMalloc(&e->resid, cap * H * sizeof(float)));
+  LXG_CUDA(cudaMalloc(&e->partial, static_cast<size_t>(kSkinnySplits) * kSkinnyRows * H * sizeof(float)));
   LXG_CUDA(cudaMalloc(&e->hn, cap * H * sizeof(__half)));
   LXG_CUDA(cudaMalloc(&e->qkv, cap * QKV * sizeof(__half)));
   LXG_CUDA(cudaMalloc(&e->ctx, cap * C * sizeof(__half)));
@@ -112,14 +118,25 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   const float eps = e->w.rms_eps;
   int launches = 0;
   const int row_blocks = (tokens + 7) / 8;
-  const int rope_blocks = row_blocks;  // one warp per token
+  // skinny path (one row tile): o_proj / down_proj have only H / 128 output tiles, so K is split
+  // and the partial slabs are added to the residual stream by the kernel that reads it next
+  const bool skinny = tokens <= kSkinnyRows;
+  const size_t slab = static_cast<size_t>(kSkinnyRows) * H;
+  int pending = 0;  // slabs waiting to be absorbed by the next RMSNorm / the head kernel
+  const int hgroup = tokens >= 2048 ? heads + kvh : 1;
+  const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
   const dim3 attn_grid((s + kCausalRows - 1) / kCausalRows, heads, b);
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     // input_layernorm (layer 0: fused with the embed_tokens gather)
-    rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, l == 0 ? e->ids : nullptr, reinterpret_cast<const __half*>(e->w.tok_emb),
-                                               e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn);
+    if (pending > 0)
+      rmsnorm_partial_kernel<<<tokens, 256, 0, st>>>(e->resid, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn, e->partial, pending,
+                                                     slab);
+    else
+      rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, l == 0 ? e->ids : nullptr, reinterpret_cast<const __half*>(e->w.tok_emb),
+                                                 e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn, nullptr, 0, 0);
     LXG_CUDA(cudaGetLastError());
+    pending = 0;
     GemmParams gp{};
     gp.bias = nullptr;
     gp.residual = nullptr;
@@ -129,35 +146,58 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     gp.n = QKV;
     gp.k = H;
     LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st));
-    qk_norm_rope_kernel<<<rope_blocks, 256, 0, st>>>(e->qkv, tokens, s, pos_of, heads, kvh, reinterpret_cast<const float*>(L.q_norm),
+    qk_norm_rope_kernel<<<rope_blocks, 256, 0, st>>>(e->qkv, tokens, s, pos_of, heads, kvh, hgroup, reinterpret_cast<const float*>(L.q_norm),
                                                      reinterpret_cast<const float*>(L.k_norm),
                                                      reinterpret_cast<const float*>(e->w.inv_freq), eps);
     LXG_CUDA(cudaGetLastError());
     attention_causal_kernel<kHeadDim><<<attn_grid, kCausalRows * 2, 0, st>>>(e->qkv, e->mask, cu, s, heads, kvh, e->ctx);
     LXG_CUDA(cudaGetLastError());
     // o_proj, accumulated onto the residual stream
-    gp.out = e->resid;
     gp.n = H;
     gp.k = C;
-    LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st));
-    rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, nullptr, nullptr, 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps,
-                                               e->hn);
+    if (skinny) {
+      gp.out = e->partial;
+      gp.ksplit = std::min(kSkinnySplits, C / kGemmBK);
+      gp.split_stride = slab;
+      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_ctx, e->map_wo[l], gp, st));
+      pending = gp.ksplit;
+      gp.ksplit = 0;
+    } else {
+      gp.out = e->resid;
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st));
+    }
+    if (pending > 0)
+      rmsnorm_partial_kernel<<<tokens, 256, 0, st>>>(e->resid, H, reinterpret_cast<const float*>(L.ln2), eps, e->hn, e->partial, pending,
+                                                     slab);
+    else
+      rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, nullptr, nullptr, 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps,
+                                                 e->hn, nullptr, 0, 0);
     LXG_CUDA(cudaGetLastError());
+    pending = 0;
     // gate_proj | up_proj (interleaved) + SwiGLU
     gp.out = e->act;
     gp.n = 2 * F;
     gp.k = H;
     LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st));
     // down_proj, accumulated onto the residual stream
-    gp.out = e->resid;
     gp.n = H;
     gp.k = F;
-    LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st));
+    if (skinny) {
+      gp.out = e->partial;
+      gp.ksplit = std::min(kSkinnySplits, F / kGemmBK);
+      gp.split_stride = slab;
+      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_act, e->map_wdown[l], gp, st));
+      pending = gp.ksplit;
+      gp.ksplit = 0;
+    } else {
+      gp.out = e->resid;
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st));
+    }
     launches += 8;
   }
   last_token_head_kernel<<<b, 256, H * sizeof(float), st>>>(e->resid, e->mask, cu, s, H, reinterpret_cast<const float*>(e->w.final_norm),
                                                             eps, mode, reinterpret_cast<const __half*>(e->w.lm_head), tt, tf,
-                                                            e->out_buf);
+                                                            e->out_buf, e->partial, pending, slab);
   LXG_CUDA(cudaGetLastError());
   ++launches;
   e->launches = launches;
