@@ -18,6 +18,23 @@ CUresult encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t 
                            CUtensorMapL2promotion l2, CUtensorMapFloatOOBfill oob);
 }  // namespace lxg
 
+// Kernel launch with optional programmatic dependent launch (see ptx::pdl_wait).
+template <typename... KArgs, typename... Args>
+inline cudaError_t lxg_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 #define LXG_CUDA(call)                                                                          \
   do {                                                                                          \
     cudaError_t lxg_e_ = (call);                                                                \

@@ -25,6 +25,8 @@ static __global__ void __launch_bounds__(256)
 rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __half* __restrict__ tok_emb, int vocab,
                int tokens, int hidden, const float* __restrict__ w, float eps, __half* __restrict__ out,
                const float* __restrict__ partial, int nsplit, size_t split_stride) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
@@ -91,6 +93,8 @@ static __global__ void __launch_bounds__(256)
 rmsnorm_partial_kernel(float* __restrict__ resid, int hidden, const float* __restrict__ w, float eps,
                        __half* __restrict__ out, const float* __restrict__ partial, int nsplit, size_t split_stride) {
   constexpr int kMaxSplit = 16;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int t = blockIdx.x;
   const int n2 = hidden >> 1;
   __shared__ float red[8];
@@ -148,6 +152,8 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __
                     const float* __restrict__ q_w, const float* __restrict__ k_w,
                     const float* __restrict__ inv_freq, float eps) {
   constexpr int DH = 128;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   // a warp owns `hgroup` consecutive heads of one token: all of them for bulk batches (cos / sin
   // once per token), one for a handful of tokens (more warps, shorter dependent chains)
@@ -202,6 +208,8 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
   __shared__ __align__(16) __half ks[kCausalKeys * kKPitch];
   __shared__ __align__(16) __half vs[kCausalKeys * kKPitch];
   __shared__ float bias[kCausalKeys];
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   // packed batch (cu != NULL): sequence b is tokens [cu[b], cu[b+1]), every key is real
   const int tok0 = cu != nullptr ? cu[b] : b * seq;
@@ -348,6 +356,7 @@ last_token_head_kernel(const float* __restrict__ resid, const int* __restrict__ 
                        const float* __restrict__ norm_w, float eps, int mode, const __half* __restrict__ lm_head,
                        int token_true, int token_false, float* __restrict__ out,
                        const float* __restrict__ partial, int nsplit, size_t split_stride) {
+  ptx::pdl_wait();
   const int b = blockIdx.x;
   __shared__ float red[3][8];
   __shared__ int s_last;

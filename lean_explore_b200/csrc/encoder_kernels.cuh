@@ -311,6 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  ptx::pdl_wait();  // everything above overlapped the previous kernel's tail (programmatic dependent launch)
+  ptx::pdl_launch_dependents();
 
   if (warp == kTmaWarp) {
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
@@ -468,6 +470,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
 
   if (warp == kTmaWarp) {
     // both CTAs load their halves; all bytes are counted on the even CTA's full barrier

@@ -38,7 +38,7 @@ inline bool gemm_pairs_enabled() {
 }
 
 template <int EPI>
-inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st) {
+inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st, bool pdl = false) {
   // more than one row tile and N a multiple of 256: 256 x 256 tiles on CTA pairs
   if (gp.m > kGemmBM && gp.n % kPairBN == 0 && gemm_pairs_enabled()) {
     static bool pair_attr_set = false;
@@ -49,8 +49,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const
     }
     const int tiles = ((gp.m + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (gp.n / kPairBN);
     const int clusters = std::min(tiles, std::max(1, lxg::num_sms() / 2));
-    gemm_pair_kernel<EPI><<<2 * clusters, kPairThreads, kPairSmem, st>>>(a, w, gp);
-    return cudaGetLastError();
+    return lxg_launch(gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(kPairThreads), kPairSmem, st, pdl, a, w, gp);
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -59,8 +58,7 @@ inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const
     attr_set = true;
   }
   const int tiles = ((gp.m + kGemmBM - 1) / kGemmBM) * (gp.n / kGemmBN) * std::max(1, gp.ksplit);
-  gemm_tc_kernel<EPI><<<std::min(tiles, std::max(1, lxg::num_sms())), kGemmThreads, kGemmSmem, st>>>(a, w, gp);
-  return cudaGetLastError();
+  return lxg_launch(gemm_tc_kernel<EPI>, dim3(std::min(tiles, std::max(1, lxg::num_sms()))), dim3(kGemmThreads), kGemmSmem, st, pdl, a, w, gp);
 }
 
 }  // namespace lxg

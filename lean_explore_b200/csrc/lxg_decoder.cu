@@ -34,6 +34,7 @@ struct lxg_decoder {
   int* stage = nullptr;                // pinned host staging: packed ids | pos | cu
   size_t stage_cap = 0;                // ints
   bool pack = true;                    // LXG_DECODER_PACK=0: always compute the padded rectangle
+  bool pdl = true;                     // LXG_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
   CUtensorMap map_hn{}, map_ctx{}, map_act{};
   std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
   int launches = 0;
@@ -122,6 +123,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   // and the partial slabs are added to the residual stream by the kernel that reads it next
   const bool skinny = tokens <= kSkinnyRows;
   const size_t slab = static_cast<size_t>(kSkinnyRows) * H;
+  const bool pdl = e->pdl;
   int pending = 0;  // slabs waiting to be absorbed by the next RMSNorm / the head kernel
   const int hgroup = tokens >= 2048 ? heads + kvh : 1;
   const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
@@ -129,13 +131,15 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     // input_layernorm (layer 0: fused with the embed_tokens gather)
+    // every kernel but the first (it follows the input copies) is a programmatic dependent launch:
+    // its prologue overlaps the previous kernel's tail
     if (pending > 0)
-      rmsnorm_partial_kernel<<<tokens, 256, 0, st>>>(e->resid, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn, e->partial, pending,
-                                                     slab);
+      LXG_CUDA(lxg_launch(rmsnorm_partial_kernel, dim3(tokens), dim3(256), 0, st, pdl, e->resid, H, reinterpret_cast<const float*>(L.ln1), eps,
+                          e->hn, static_cast<const float*>(e->partial), pending, slab));
     else
-      rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, l == 0 ? e->ids : nullptr, reinterpret_cast<const __half*>(e->w.tok_emb),
-                                                 e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn, nullptr, 0, 0);
-    LXG_CUDA(cudaGetLastError());
+      LXG_CUDA(lxg_launch(rmsnorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl && l > 0, e->resid, static_cast<const int*>(l == 0 ? e->ids : nullptr),
+                          reinterpret_cast<const __half*>(e->w.tok_emb), e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn,
+                          static_cast<const float*>(nullptr), 0, static_cast<size_t>(0)));
     pending = 0;
     GemmParams gp{};
     gp.bias = nullptr;
@@ -145,13 +149,12 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     gp.out = e->qkv;
     gp.n = QKV;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st));
-    qk_norm_rope_kernel<<<rope_blocks, 256, 0, st>>>(e->qkv, tokens, s, pos_of, heads, kvh, hgroup, reinterpret_cast<const float*>(L.q_norm),
-                                                     reinterpret_cast<const float*>(L.k_norm),
-                                                     reinterpret_cast<const float*>(e->w.inv_freq), eps);
-    LXG_CUDA(cudaGetLastError());
-    attention_causal_kernel<kHeadDim><<<attn_grid, kCausalRows * 2, 0, st>>>(e->qkv, e->mask, cu, s, heads, kvh, e->ctx);
-    LXG_CUDA(cudaGetLastError());
+    LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st, pdl));
+    LXG_CUDA(lxg_launch(qk_norm_rope_kernel, dim3(rope_blocks), dim3(256), 0, st, pdl, e->qkv, tokens, s, pos_of, heads, kvh, hgroup,
+                        reinterpret_cast<const float*>(L.q_norm), reinterpret_cast<const float*>(L.k_norm),
+                        reinterpret_cast<const float*>(e->w.inv_freq), eps));
+    LXG_CUDA(lxg_launch(attention_causal_kernel<kHeadDim>, attn_grid, dim3(kCausalRows * 2), 0, st, pdl, static_cast<const __half*>(e->qkv),
+                        static_cast<const int*>(e->mask), cu, s, heads, kvh, e->ctx));
     // o_proj, accumulated onto the residual stream
     gp.n = H;
     gp.k = C;
@@ -159,26 +162,26 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.out = e->partial;
       gp.ksplit = std::min(kSkinnySplits, C / kGemmBK);
       gp.split_stride = slab;
-      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_ctx, e->map_wo[l], gp, st));
+      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_ctx, e->map_wo[l], gp, st, pdl));
       pending = gp.ksplit;
       gp.ksplit = 0;
     } else {
       gp.out = e->resid;
-      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st));
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st, pdl));
     }
     if (pending > 0)
-      rmsnorm_partial_kernel<<<tokens, 256, 0, st>>>(e->resid, H, reinterpret_cast<const float*>(L.ln2), eps, e->hn, e->partial, pending,
-                                                     slab);
+      LXG_CUDA(lxg_launch(rmsnorm_partial_kernel, dim3(tokens), dim3(256), 0, st, pdl, e->resid, H, reinterpret_cast<const float*>(L.ln2), eps,
+                          e->hn, static_cast<const float*>(e->partial), pending, slab));
     else
-      rmsnorm_kernel<<<row_blocks, 256, 0, st>>>(e->resid, nullptr, nullptr, 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps,
-                                                 e->hn, nullptr, 0, 0);
-    LXG_CUDA(cudaGetLastError());
+      LXG_CUDA(lxg_launch(rmsnorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, e->resid, static_cast<const int*>(nullptr),
+                          static_cast<const __half*>(nullptr), 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps, e->hn,
+                          static_cast<const float*>(nullptr), 0, static_cast<size_t>(0)));
     pending = 0;
     // gate_proj | up_proj (interleaved) + SwiGLU
     gp.out = e->act;
     gp.n = 2 * F;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st));
+    LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st, pdl));
     // down_proj, accumulated onto the residual stream
     gp.n = H;
     gp.k = F;
@@ -186,19 +189,18 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.out = e->partial;
       gp.ksplit = std::min(kSkinnySplits, F / kGemmBK);
       gp.split_stride = slab;
-      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_act, e->map_wdown[l], gp, st));
+      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_act, e->map_wdown[l], gp, st, pdl));
       pending = gp.ksplit;
       gp.ksplit = 0;
     } else {
       gp.out = e->resid;
-      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st));
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st, pdl));
     }
     launches += 8;
   }
-  last_token_head_kernel<<<b, 256, H * sizeof(float), st>>>(e->resid, e->mask, cu, s, H, reinterpret_cast<const float*>(e->w.final_norm),
-                                                            eps, mode, reinterpret_cast<const __half*>(e->w.lm_head), tt, tf,
-                                                            e->out_buf, e->partial, pending, slab);
-  LXG_CUDA(cudaGetLastError());
+  LXG_CUDA(lxg_launch(last_token_head_kernel, dim3(b), dim3(256), H * sizeof(float), st, pdl, static_cast<const float*>(e->resid),
+                      static_cast<const int*>(e->mask), cu, s, H, reinterpret_cast<const float*>(e->w.final_norm), eps, mode,
+                      reinterpret_cast<const __half*>(e->w.lm_head), tt, tf, e->out_buf, static_cast<const float*>(e->partial), pending, slab));
   ++launches;
   e->launches = launches;
   return LXG_OK;
@@ -401,6 +403,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   }
   const char* pk = std::getenv("LXG_DECODER_PACK");
   e->pack = !(pk && pk[0] == '0');
+  const char* pd = std::getenv("LXG_PDL");
+  e->pdl = !(pd && pd[0] == '0');
   *out = e;
   return LXG_OK;
 }

@@ -143,6 +143,14 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start (and run its
+// prologue) before the preceding kernel on the stream has finished; pdl_wait() blocks until that
+// kernel has completed and its writes are visible (a no-op for a normal launch).
+// pdl_launch_dependents() lets the NEXT kernel's CTAs be scheduled from here on.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------------------ cluster
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
