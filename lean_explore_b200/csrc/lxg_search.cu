@@ -355,8 +355,8 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
   ix->cv.scan_scale = 1.f;
   ix->num_kc = (d + kKC - 1) / kKC;
   // 128-row tiles throughout; the first 8 k-chunks (512 dims) of the query block live in tensor
-  // memory, the rest in shared memory: 4 chunks for d <= 768 (measured on cfg3, same box: 2.43 ms
-  // against 3.12 ms for the 64-row-tile variant that keeps all of A in tensor memory, which
+  // memory, the rest in shared memory: 4 chunks for d <= 768 (measured on cfg3, same box: 2.21 ms
+  // against 2.62 ms for the 64-row-tile variant that keeps all of A in tensor memory, which
   // LXG_SCAN_ASMEM=0 still selects), 8 chunks for d <= 1024
   ix->a_smem_chunks = ix->num_kc <= 8 ? 0 : (ix->num_kc > 12 ? 8 : (g_asmem_768 ? 4 : 0));
   ix->tile_rows = (ix->num_kc <= 8 || ix->a_smem_chunks > 0) ? 128 : 64;

@@ -657,7 +657,9 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     ptx::tc_fence_before();
     __syncwarp();
     if (lane == 0) {
-      if constexpr (kPair) ptx::mbar_arrive_cluster(&a_ready_bar, 0); else ptx::mbar_arrive(&a_ready_bar);
+      if constexpr (kPair && kASm > 0) ptx::mbar_arrive_cluster_release(&a_ready_bar, 0);  // orders the A image in shared memory
+      else if constexpr (kPair) ptx::mbar_arrive_cluster(&a_ready_bar, 0);
+      else ptx::mbar_arrive(&a_ready_bar);
     }
 
     // ---- threshold scan
