@@ -210,8 +210,9 @@ typedef struct lxg_decoder lxg_decoder;
 int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w);
 int lxg_decoder_destroy(lxg_decoder* dec);
 int lxg_decoder_last_launches(const lxg_decoder* dec);
-/* tokens the last forward computed: with host ids / mask and b > 1 the padding tokens are dropped
- * before the first layer (sequences are packed back to back), so this is sum(mask), not b * s */
+/* tokens the last forward computed: for a host batch of >= 512 padded tokens of which >= 10 % are
+ * padding, the padding tokens are dropped before the first layer (sequences are packed back to
+ * back), so this is sum(mask), not b * s */
 int lxg_decoder_last_tokens(const lxg_decoder* dec);
 int lxg_decoder_embed(lxg_decoder* dec, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,
                       float* out, void* stream);

@@ -285,7 +285,9 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
       longest = std::max(longest, last - first + 1);
     }
     pcu[b] = n;
-    if (ok) {
+    // worth it only for a bulk batch that is at least 10 % padding: a packed forward is launched
+    // kernel by kernel, small rectangular batches are better served by the captured graph
+    if (ok && tokens >= 512 && static_cast<long long>(n) * 10 <= static_cast<long long>(tokens) * 9) {
       packed = true;
       live_tokens = n;
       max_len = longest;
