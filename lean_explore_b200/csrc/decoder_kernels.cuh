@@ -19,12 +19,10 @@ namespace lxg {
 // ------------------------------------------------------------------ RMSNorm
 // One warp per token: out = x * rsqrt(mean(x^2) + eps) * w   (fp32 in, fp16 out).  With ids != NULL
 // the row is first gathered from the token-embedding table and written to the residual stream
-// (the first layer's input_layernorm fused with embed_tokens).  With nsplit > 0 the row first
-// absorbs the split-K partial sums of the preceding projection.
+// (the first layer's input_layernorm fused with embed_tokens).
 static __global__ void __launch_bounds__(256)
 rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __half* __restrict__ tok_emb, int vocab,
-               int tokens, int hidden, const float* __restrict__ w, float eps, __half* __restrict__ out,
-               const float* __restrict__ partial, int nsplit, size_t split_stride) {
+               int tokens, int hidden, const float* __restrict__ w, float eps, __half* __restrict__ out) {
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
@@ -56,17 +54,6 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
       v[i] = make_float2(0.f, 0.f);
       if (j < n2) {
         v[i] = x2[j];
-        if (nsplit > 0) {
-          // split-K partial sums of the preceding o_proj / down_proj (skinny path): added here in
-          // slab order, and the residual stream is updated in passing
-          const float2* p2 = reinterpret_cast<const float2*>(partial + static_cast<size_t>(t) * hidden) + j;
-          for (int sidx = 0; sidx < nsplit; ++sidx) {
-            const float2 a = p2[sidx * (split_stride >> 1)];
-            v[i].x += a.x;
-            v[i].y += a.y;
-          }
-          x2[j] = v[i];
-        }
         ss += v[i].x * v[i].x + v[i].y * v[i].y;
       }
     }
@@ -155,8 +142,8 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
-  // a warp owns `hgroup` consecutive heads of one token: all of them for bulk batches (cos / sin
-  // once per token), one for a handful of tokens (more warps, shorter dependent chains)
+  // a warp owns `hgroup` consecutive heads of one token: several for bulk batches (cos / sin once
+  // per warp), one for a handful of tokens (more warps, shorter dependent chains)
   const int nh = heads + kv_heads;
   const int groups = (nh + hgroup - 1) / hgroup;
   const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -197,6 +184,8 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __
 // Packed batches (cu != NULL, no padding tokens at all) give sequence b the tokens [cu[b], cu[b+1]).
 constexpr int kCausalRows = 64;
 constexpr int kCausalKeys = 64;
+// two buffers x (K chunk + V chunk) of 64 rows x (128 + 8) halves, + bias[2][64]
+constexpr int kCausalSmem = 4 * kCausalKeys * (128 + 8) * 2 + 2 * kCausalKeys * 4;
 
 template <int DH>
 __global__ void __launch_bounds__(kCausalRows * 2, 3)
@@ -205,9 +194,10 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
   constexpr int kKSteps = DH / 16;
   constexpr int kOTiles = DH / 8;
   constexpr int kKPitch = DH + 8;
-  __shared__ __align__(16) __half ks[kCausalKeys * kKPitch];
-  __shared__ __align__(16) __half vs[kCausalKeys * kKPitch];
-  __shared__ float bias[kCausalKeys];
+  constexpr int kTile = kCausalKeys * kKPitch;  // halves per K (or V) chunk
+  extern __shared__ __align__(16) uint8_t attn_smem[];  // [2 buffers][K chunk | V chunk] + bias[2][64]
+  __half* const kv_sm = reinterpret_cast<__half*>(attn_smem);
+  float* const bias_sm = reinterpret_cast<float*>(attn_smem + static_cast<size_t>(4) * kTile * sizeof(__half));
   ptx::pdl_wait();
   ptx::pdl_launch_dependents();
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -241,35 +231,59 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
   for (int n = 0; n < kOTiles; ++n) o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
   float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, l0 = 0.f, l1 = 0.f;
   const float scale = rsqrtf(static_cast<float>(DH)) * 1.4426950408889634f;  // softmax in base 2
-  const uint32_t smem_vs = ptx::smem_u32(vs);
 
   const int key_end = min(seq, (qb + 1) * kCausalRows);  // causal: no key beyond the block's last row
-  for (int kb0 = 0; kb0 < key_end; kb0 += kCausalKeys) {
-    __syncthreads();  // previous chunk fully consumed
+  const int nchunks = (key_end + kCausalKeys - 1) / kCausalKeys;
+  const uint32_t smem_kv = ptx::smem_u32(kv_sm);
+  // chunk c -> buffer c & 1, staged with cp.async (rows past the sequence are zero filled) one
+  // chunk ahead of the MMAs
+  auto stage_chunk = [&](int c) {
+    const int kb = c * kCausalKeys;
+    const uint32_t dst0 = smem_kv + static_cast<uint32_t>((c & 1) * 2 * kTile * 2);
     for (int i = threadIdx.x; i < kCausalKeys * (DH / 8); i += blockDim.x) {
-      const int j = i / (DH / 8), c = i % (DH / 8);
-      uint4 kk = make_uint4(0u, 0u, 0u, 0u), vv = kk;
-      if (kb0 + j < seq) {
-        kk = *reinterpret_cast<const uint4*>(kbase + (kb0 + j) * row_stride + 8 * c);
-        vv = *reinterpret_cast<const uint4*>(vbase + (kb0 + j) * row_stride + 8 * c);
-      }
-      *reinterpret_cast<uint4*>(ks + j * kKPitch + 8 * c) = kk;
-      *reinterpret_cast<uint4*>(vs + j * kKPitch + 8 * c) = vv;
+      const int j = i / (DH / 8), cc = i % (DH / 8);
+      const bool in = kb + j < seq;
+      const size_t row = static_cast<size_t>(in ? kb + j : 0) * row_stride + 8 * cc;
+      const uint32_t dst = dst0 + static_cast<uint32_t>((j * kKPitch + 8 * cc) * 2);
+      const uint32_t bytes = in ? 16u : 0u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(kbase + row), "r"(bytes) : "memory");
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst + kTile * 2), "l"(vbase + row), "r"(bytes) : "memory");
     }
     for (int j = threadIdx.x; j < kCausalKeys; j += blockDim.x)
-      bias[j] = (kb0 + j < seq && (cu != nullptr || mask[tok0 + kb0 + j] != 0)) ? 0.f : -CUDART_INF_F;
-    __syncthreads();
-    if (!active || kb0 > wrow0 + 15) continue;  // warp-uniform: chunk entirely in this warp's future
+      bias_sm[(c & 1) * kCausalKeys + j] = (kb + j < seq && (cu != nullptr || mask[tok0 + kb + j] != 0)) ? 0.f : -CUDART_INF_F;
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  stage_chunk(0);
+  for (int c = 0; c < nchunks; ++c) {
+    const int kb0 = c * kCausalKeys;
+    if (c + 1 < nchunks) {
+      stage_chunk(c + 1);  // its buffer was released by the barrier that ended iteration c - 1
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    __syncthreads();  // chunk c (every thread's copies + bias) is visible
+    const float* bias = bias_sm + (c & 1) * kCausalKeys;
+    const uint32_t smem_ks = smem_kv + static_cast<uint32_t>((c & 1) * 2 * kTile * 2);
+    const uint32_t smem_vs = smem_ks + kTile * 2;
+    if (active && kb0 <= wrow0 + 15) {  // warp-uniform: else the chunk lies entirely in this warp's future
 
     float sc[8][4];
+    // B fragments of Q.K^T with ldmatrix.x4: matrices = 8 keys x dims [32 kk2 + 8 m, +8), m = 0..3
+    // -> (b0, b1) of k-steps 2 kk2 and 2 kk2 + 1
+    const uint32_t krow = smem_ks + static_cast<uint32_t>(((lane & 7) * kKPitch + (lane >> 3) * 8) * 2);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       sc[j][0] = sc[j][1] = sc[j][2] = sc[j][3] = 0.f;
-      const __half* kr = ks + (j * 8 + g) * kKPitch + 2 * t;
 #pragma unroll
-      for (int kk = 0; kk < kKSteps; ++kk)
-        mma_m16n8k16(sc[j], qa[kk], *reinterpret_cast<const uint32_t*>(kr + kk * 16),
-                     *reinterpret_cast<const uint32_t*>(kr + kk * 16 + 8));
+      for (int kk2 = 0; kk2 < kKSteps / 2; ++kk2) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3)
+                     : "r"(krow + static_cast<uint32_t>((j * 8 * kKPitch + kk2 * 32) * 2)));
+        mma_m16n8k16(sc[j], qa[2 * kk2], b0, b1);
+        mma_m16n8k16(sc[j], qa[2 * kk2 + 1], b2, b3);
+      }
     }
     float bm0 = -CUDART_INF_F, bm1 = -CUDART_INF_F;
 #pragma unroll
@@ -327,6 +341,8 @@ attention_causal_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
         mma_m16n8k16(o[n + 1], pa[kk], b2, b3);
       }
     }
+    }  // active
+    __syncthreads();  // buffer c & 1 may be overwritten by the copies of chunk c + 2
   }
   if (!active) return;
   l0 += __shfl_xor_sync(0xffffffffu, l0, 1);

@@ -125,9 +125,14 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   const size_t slab = static_cast<size_t>(kSkinnyRows) * H;
   const bool pdl = e->pdl;
   int pending = 0;  // slabs waiting to be absorbed by the next RMSNorm / the head kernel
-  const int hgroup = tokens >= 2048 ? heads + kvh : 1;
+  const int hgroup = tokens >= 2048 ? 4 : 1;  // heads per RoPE warp (cos / sin are evaluated once per warp)
   const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
   const dim3 attn_grid((s + kCausalRows - 1) / kCausalRows, heads, b);
+  static bool attn_attr_set = false;
+  if (!attn_attr_set) {
+    LXG_CUDA(cudaFuncSetAttribute(attention_causal_kernel<kHeadDim>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCausalSmem));
+    attn_attr_set = true;
+  }
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     // input_layernorm (layer 0: fused with the embed_tokens gather)
@@ -138,8 +143,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
                           e->hn, static_cast<const float*>(e->partial), pending, slab));
     else
       LXG_CUDA(lxg_launch(rmsnorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl && l > 0, e->resid, static_cast<const int*>(l == 0 ? e->ids : nullptr),
-                          reinterpret_cast<const __half*>(e->w.tok_emb), e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn,
-                          static_cast<const float*>(nullptr), 0, static_cast<size_t>(0)));
+                          reinterpret_cast<const __half*>(e->w.tok_emb), e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn));
     pending = 0;
     GemmParams gp{};
     gp.bias = nullptr;
@@ -153,7 +157,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     LXG_CUDA(lxg_launch(qk_norm_rope_kernel, dim3(rope_blocks), dim3(256), 0, st, pdl, e->qkv, tokens, s, pos_of, heads, kvh, hgroup,
                         reinterpret_cast<const float*>(L.q_norm), reinterpret_cast<const float*>(L.k_norm),
                         reinterpret_cast<const float*>(e->w.inv_freq), eps));
-    LXG_CUDA(lxg_launch(attention_causal_kernel<kHeadDim>, attn_grid, dim3(kCausalRows * 2), 0, st, pdl, static_cast<const __half*>(e->qkv),
+    LXG_CUDA(lxg_launch(attention_causal_kernel<kHeadDim>, attn_grid, dim3(kCausalRows * 2), kCausalSmem, st, pdl, static_cast<const __half*>(e->qkv),
                         static_cast<const int*>(e->mask), cu, s, heads, kvh, e->ctx));
     // o_proj, accumulated onto the residual stream
     gp.n = H;
@@ -174,8 +178,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
                           e->hn, static_cast<const float*>(e->partial), pending, slab));
     else
       LXG_CUDA(lxg_launch(rmsnorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, e->resid, static_cast<const int*>(nullptr),
-                          static_cast<const __half*>(nullptr), 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps, e->hn,
-                          static_cast<const float*>(nullptr), 0, static_cast<size_t>(0)));
+                          static_cast<const __half*>(nullptr), 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps, e->hn));
     pending = 0;
     // gate_proj | up_proj (interleaved) + SwiGLU
     gp.out = e->act;
