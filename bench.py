@@ -498,6 +498,29 @@ def encoder_numbers(dev, cpu: bool):
     return res
 
 
+def qwen3_random_model(seed: int = 0, vocab_size: int = 4096):
+    """Random-init HF Qwen3ForCausalLM of the 0.6B geometry (no checkpoints exist offline); only its
+    state_dict is used on the GPU leg."""
+    import torch
+    from transformers import Qwen3Config, Qwen3ForCausalLM
+
+    cfg = Qwen3Config(vocab_size=vocab_size, head_dim=128, max_position_embeddings=32768, rope_theta=1e6, rms_norm_eps=1e-6,
+                      tie_word_embeddings=True, initializer_range=0.05, attention_bias=False, hidden_size=1024,
+                      num_hidden_layers=28, num_attention_heads=16, num_key_value_heads=8, intermediate_size=3072)
+    torch.manual_seed(seed)
+    return Qwen3ForCausalLM(cfg).eval(), cfg
+
+
+def ragged_left_padded_ids(batch: int, seq: int, vocab_size: int = 4096, seed: int = 0):
+    """Synthetic token ids, lengths uniform in [seq/4, seq] (first row full), padded on the left."""
+    rng = np.random.default_rng(seed)
+    ids = rng.integers(10, vocab_size, size=(batch, seq)).astype(np.int32)
+    lens = rng.integers(min(seq, max(1, seq // 4)), seq + 1, size=batch)
+    lens[0] = seq
+    mask = (np.arange(seq)[None, :] >= seq - lens[:, None]).astype(np.int32)
+    return np.where(mask == 1, ids, 0).astype(np.int32), mask
+
+
 def decoder_numbers(dev, cpu: bool):
     """The shipped models: Qwen3-Embedding-0.6B forward behind
     EmbeddingClient.embed and Qwen3-Reranker-0.6B behind RerankerClient._compute_scores_sync, on
@@ -507,9 +530,8 @@ def decoder_numbers(dev, cpu: bool):
     import torch
 
     from lean_explore_b200.decoder import Qwen3Decoder
-    from oracle import qwen3_decoder as qd
 
-    model, cfg = qd.make_model("qwen3-0.6b", seed=0)
+    model, cfg = qwen3_random_model()
     dec = Qwen3Decoder(model.state_dict(), hidden=cfg.hidden_size, layers=cfg.num_hidden_layers,
                        heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads, ffn=cfg.intermediate_size,
                        head_dim=cfg.head_dim, rms_eps=cfg.rms_norm_eps, rope_theta=1e6, device=dev.index or 0)
@@ -521,7 +543,7 @@ def decoder_numbers(dev, cpu: bool):
     for label, mode, b, sl, iters in (("embed query B=1 S=24", 0, 1, 24, 100), ("embed bulk B=64 S=128", 0, 64, 128, 10),
                                       ("rerank B=16 S=256 (reference CUDA batch)", 1, 16, 256, 10),
                                       ("rerank B=50 S=256 (rerank_top=50 in one call)", 1, 50, 256, 10)):
-        ids_h, mask_h = qd.make_inputs(b, sl, seed=5, side="left")
+        ids_h, mask_h = ragged_left_padded_ids(b, sl, seed=5)
         call = (lambda: dec.embed_ids(ids_h, mask_h)) if mode == 0 else (lambda: dec.rerank_ids(ids_h, mask_h, tt, tf))
         for _ in range(3):
             call()
@@ -535,9 +557,11 @@ def decoder_numbers(dev, cpu: bool):
                       "gemm_tflops": round(flop_tok * computed / (ms / 1e3) / 1e12, 2)}
     res["launches"] = dec.last_launches()
     if cpu:
+        from oracle import qwen3_decoder as qd  # the CPU leg is the only place the oracle runs
+
         res["cpu_baseline"] = {"kind": "HF Qwen3ForCausalLM fp32, torch %d threads" % torch.get_num_threads()}
         for label, mode, b, sl, reps in (("embed query B=1 S=24", 0, 1, 24, 3), ("rerank B=4 S=256", 1, 4, 256, 1)):
-            ids_c, mask_c = qd.make_inputs(b, sl, seed=6, side="left")
+            ids_c, mask_c = ragged_left_padded_ids(b, sl, seed=6)
             fn = (lambda: qd.embed(model, ids_c, mask_c)) if mode == 0 else (lambda: qd.rerank(model, ids_c, mask_c, tt, tf))
             fn()
             t0 = time.perf_counter()
