@@ -319,21 +319,24 @@ __device__ __forceinline__ void track_insert(float (&t)[kTrack], float v, bool t
 
 // Cross-list level: min over the lists of the published r-th best, for the
 // `nlive` queries q0.. of this warp (query q0 + lane gets its value).  lvl is query-major
-// [nq][lists]: the warp reads one query's levels with coalesced loads, 8 queries in flight.
+// [nq][lists]: the warp reads one query's levels with coalesced loads, 16 queries in flight.
 __device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int q0, int nlive, int lane) {
+  // kBatch queries' loads are in flight together: a refresh is a chain of dependent L2 round trips
+  // (~0.7 us each), and the tile that follows cannot be released before it returns
+  constexpr int kBatch = 16;
   const int lists = p.lvl_slots;
   uint32_t mine = kLvlNone;
-  for (int b = 0; b < nlive; b += 8) {  // warp-uniform
-    uint32_t lo[8];
+  for (int b = 0; b < nlive; b += kBatch) {  // warp-uniform
+    uint32_t lo[kBatch];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) lo[u] = kLvlSkip;
+    for (int u = 0; u < kBatch; ++u) lo[u] = kLvlSkip;
     for (int s = lane; s < lists; s += 32) {
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
+      for (int u = 0; u < kBatch; ++u)
         if (b + u < nlive) lo[u] = min(lo[u], __ldcg(p.lvl + static_cast<size_t>(q0 + b + u) * lists + s));
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < kBatch; ++u) {
       const uint32_t v = __reduce_min_sync(0xffffffffu, lo[u]);
       if (lane == b + u) mine = v;
     }
