@@ -148,9 +148,19 @@ int build_tensor_map(lxg_index* ix) {
   return LXG_OK;
 }
 
-int candidates_per_slice(int k) {
-  // kp = k plus a margin (so that the exactness certificate almost always holds), rounded to 32
-  const int margin = std::max(14, k / 4);
+int candidates_per_slice(int k, float rel_err, int d, long long n) {
+  // kp = k plus a margin (so that the exactness certificate almost always holds), rounded to 32.
+  // The certificate needs exact score(rank k) - tensor score(rank kp) > eps = rel_err |c| |q|.  For
+  // isotropic rows the scores near rank r sit ~ sigma ln(kp / k) / sqrt(2 ln(n / k)) apart with
+  // sigma = |c| |q| / sqrt(d), so the margin that keeps that gap at 3 eps is
+  // ln(kp / k) = 3 rel_err sqrt(d) sqrt(2 ln(n / k)).  It only exceeds the k / 4 floor for fp32
+  // corpora at large d (rel_err doubles: the scan copy is rounded too) - the shipped 1024-d index,
+  // where k' = 64 left ~20 % of a 1024-query batch to the exhaustive exact path (10 ms).
+  int margin = std::max(14, k / 4);
+  if (n > 4LL * k) {
+    const double g = 3.0 * rel_err * std::sqrt(static_cast<double>(d)) * std::sqrt(2.0 * std::log(static_cast<double>(n) / k));
+    margin = std::max(margin, static_cast<int>(std::ceil(k * (std::exp(std::min(g, 1.0)) - 1.0))));
+  }
   return ((k + margin + 31) / 32) * 32;
 }
 
@@ -190,7 +200,7 @@ int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_
 Plan make_plan(const lxg_index* ix, int nq, int k) {
   Plan pl;
   const int nt = ix->tile_rows;
-  pl.kp = candidates_per_slice(k);
+  pl.kp = candidates_per_slice(k, ix->cv.rel_err, ix->cv.d, ix->cv.n);
   pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
   pl.num_tiles = static_cast<int>((ix->cv.n + nt - 1) / nt);
   pl.pair = pl.qblocks >= 2 && !g_force_single;

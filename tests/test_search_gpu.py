@@ -250,6 +250,13 @@ def test_shipped_model_dimension_d1024_fp32_corpus():
     corpus = make_corpus(30000, 1024, dtype=np.float32)
     _check(corpus, make_queries(1, 1024), 1000)
     _check(corpus, make_queries(257, 1024), 10)
+    # fp32 corpus at d = 1024: the scan copy is rounded too, so the certificate's eps doubles while
+    # the scores concentrate (sigma = 1/32); the candidate margin k' - k grows with rel_err sqrt(d)
+    # so that a batch does not fall back to the exhaustive exact path
+    big = make_corpus(100000, 1024, dtype=np.float32)
+    ix = _check(big, make_queries(256, 1024), 50)
+    st = ix.last_stats()
+    assert st["kp"] >= 96 and 0 <= st["uncertified"] <= 2, st
     from lean_explore_b200 import _lib
 
     with pytest.raises(_lib.LxgError):
