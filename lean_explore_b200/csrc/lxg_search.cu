@@ -561,7 +561,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.lvl_slots = pl.lvl_slots;
   sp.perf_mode = g_perf_mode;
   // exact-path workspace (its counters are cleared by the prep kernel as well)
-  const int nflag_max = std::min(nq, 256);
+  // one list per query: however many queries of a batch end up uncertified (a corpus full of exact
+  // duplicates), none can be left without its exact pass - also when the caller reads the results
+  // asynchronously and nobody looks at the flag count.  192 KB of workspace per query, reserved once.
+  const int nflag_max = nq;
   const size_t ex_bytes = static_cast<size_t>(nflag_max) * kExactListCap * (sizeof(double) + sizeof(unsigned)) +
                           static_cast<size_t>(nflag_max) * sizeof(int) + 256;
   LXG_CUDA(ix->ws_exact.reserve(ex_bytes));
@@ -681,8 +684,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
     LXG_CUDA(cudaMemcpyAsync(h, flag_count, sizeof(h), cudaMemcpyDeviceToHost, st));
     LXG_CUDA(cudaStreamSynchronize(st));
     ix->stats.uncertified = h[0];
-    if (h[0] > nflag_max)
-      return set_error(LXG_ETIES, "more than 256 queries of one batch needed the exact path");
+    if (h[0] > nflag_max) return set_error(LXG_ECUDA, "internal: more flagged queries than queries");
     if (h[1])
       return set_error(LXG_ETIES, "more than 16384 corpus rows tie with the k-th best score of a query");
   }

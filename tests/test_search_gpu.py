@@ -281,6 +281,23 @@ def test_near_duplicate_heavy_corpus_goes_through_the_exact_path():
     assert ix.last_stats()["uncertified"] >= 1
 
 
+def test_hundreds_of_uncertified_queries_in_one_batch_also_asynchronously():
+    """A corpus full of exact duplicates: more than 256 queries of ONE batch need the exact path
+    (round 1 capped that at 256 and returned LXG_ETIES; with device outputs nobody even read the
+    count).  Every query gets its own exact list now - host and asynchronous device results."""
+    base, copies = 320, 80  # more copies than k' = 64: the cut falls inside the run of equal scores
+    corpus = make_corpus(30000, 64)
+    for j in range(base):
+        corpus[base + j * copies : base + (j + 1) * copies] = corpus[j]  # 80 more copies of rows 0..319
+    x = corpus[:base].astype(np.float32)
+    ix = _check(corpus, x, 25)
+    assert ix.last_stats()["uncertified"] > 256
+    D, I = ix.search(x, 25, normalize=True)
+    Dt, It = ix.search_torch(torch.from_numpy(x).cuda(), 25, normalize=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(It.cpu().numpy(), I) and np.array_equal(Dt.cpu().numpy(), D)
+
+
 def test_more_queries_than_one_launch_holds():
     """nq > 148 * 128: lxg_search splits the batch over several launches."""
     corpus = make_corpus(3000, 64)
