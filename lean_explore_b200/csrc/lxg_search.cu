@@ -233,6 +233,10 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     // typical survivors: 2-3 k' when every list publishes, ~stride/2 times more when only every
     // stride-th does (the level then bounds a sample of the corpus); overflow is tightened exactly
     pl.max_items = std::max(2048, 4 * pl.kp) * (pl.lvl_stride > 1 ? 3 : 1);
+    // a handful of queries (the 1024-thread merge CTA has an SM's shared memory to itself): room for
+    // 12 k' entries - with k' = 1408 (faiss_k = 1000) and ~290 lists publishing their 5th best, 4 k'
+    // overflowed and a third of the merge went into tightening the level over global memory
+    if (nq <= 64) pl.max_items = std::min(20480, std::max(pl.max_items, 12 * pl.kp));
   } else {
     // thresholds come from compacting full lists: pass 2 holds lists * kp keys in shared memory
     slice_up(std::min(pl.slices, std::max(1, 24576 / kGroups / pl.kp)));
