@@ -1,5 +1,5 @@
 set -x
-T=${TAG:-r1F}
+T=${TAG:-r1Z}
 timeout 1500 python -m pytest tests -m gpu -q --timeout 600 2>&1 | tail -30 > gpurun_out/${T}_pytest_gpu.log
 tail -5 gpurun_out/${T}_pytest_gpu.log
 timeout 900 python bench.py --steps 200 --warmup 10 > gpurun_out/${T}_bench_cfg2.json 2> gpurun_out/${T}_bench_cfg2.err
