@@ -32,6 +32,8 @@ static int g_num_sms = 0;
 static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
 static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
 static bool g_asmem_768 = true;      // LXG_SCAN_ASMEM=0: 512 < d <= 768 falls back to 64-row tiles, all of A in tensor memory (A/B)
+static int g_sync_mb = 28;           // LXG_SCAN_SYNC_MB: L2 megabytes the readers' spread may cover (all slices together)
+static bool g_sync_readers = true;   // LXG_SCAN_SYNC=0: the readers of a corpus slice are not kept in step (A/B)
 static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -327,6 +329,10 @@ int lxg_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   const char* fs = std::getenv("LXG_SCAN_SINGLE");
   g_force_single = fs && fs[0] == '1';
+  const char* sr = std::getenv("LXG_SCAN_SYNC");
+  g_sync_readers = !(sr && sr[0] == '0');
+  const char* smb = std::getenv("LXG_SCAN_SYNC_MB");
+  if (smb && std::atoi(smb) > 0) g_sync_mb = std::atoi(smb);
   const char* am = std::getenv("LXG_SCAN_ASMEM");
   g_asmem_768 = !(am && am[0] == '0');
   const char* nl = std::getenv("LXG_SCAN_NOLEVEL");
@@ -529,7 +535,10 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   const size_t o_qnorm = take(nq * sizeof(float));
   const size_t o_flist = take(nq * sizeof(int));
   const size_t o_theta = take(nq * sizeof(double));
-  const size_t o_flags = take(256);  // cleared together with the levels right behind it (prep kernel)
+  // flag_count, overflow, padding (64 words), then the scan's reader-progress counters (1024 words);
+  // cleared together with the levels right behind them (prep kernel)
+  constexpr int kProgWords = 1024;
+  const size_t o_flags = take(256 + kProgWords * sizeof(int));
   const size_t o_lvl = take(lists * sizeof(uint32_t));
   LXG_CUDA(ix->ws_small.reserve(off));
   // normalised fp32 queries, then the prepared fp16 query blocks
@@ -564,6 +573,18 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.lvl_stride = pl.lvl_stride;
   sp.lvl_slots = pl.lvl_slots;
   sp.perf_mode = g_perf_mode;
+  {
+    // readers of a slice are kept within ~half an L2 share of each other (see the TMA producer)
+    const int readers = pl.grid_x / (pl.pair ? 2 : 1);
+    const size_t tile_bytes = static_cast<size_t>(ix->tile_rows) * dpad * sizeof(__half);
+    const size_t corpus_bytes = static_cast<size_t>(pl.num_tiles) * tile_bytes;
+    sp.progress = nullptr;
+    if (g_sync_readers && readers > 1 && readers <= 32 && pl.slices * readers <= kProgWords && corpus_bytes > (96u << 20)) {
+      sp.progress = flag_count + 64;
+      const size_t share = (static_cast<size_t>(g_sync_mb) << 20) / static_cast<size_t>(pl.slices);
+      sp.sync_window = static_cast<int>(std::min<size_t>(64, std::max<size_t>(2, share / tile_bytes)));
+    }
+  }
   // exact-path workspace (its counters are cleared by the prep kernel as well)
   // one list per query: however many queries of a batch end up uncertified (a corpus full of exact
   // duplicates), none can be left without its exact pass - also when the caller reads the results
@@ -592,7 +613,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
   prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(
       x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize, reinterpret_cast<uint32_t*>(flag_count),
-      64 + (sp.lvl_r > 0 ? static_cast<int>(lists) : 0), reinterpret_cast<uint32_t*>(ex_count), nflag_max);
+      64 + kProgWords + (sp.lvl_r > 0 ? static_cast<int>(lists) : 0), reinterpret_cast<uint32_t*>(ex_count), nflag_max);
   LXG_CUDA(cudaGetLastError());
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));

@@ -65,6 +65,8 @@ struct ScanParams {
   int n;
   int num_tiles, slices, tiles_per_slice;
   int kp, cap, keep_max;
+  int* progress;      // [slices, readers] tiles issued by every reader (CTA or CTA pair) of a slice, or nullptr
+  int sync_window;    // a reader does not run more than this many tiles ahead of the slowest one
   int perf_mode;      // measurements only (LXG_SCAN_PERF_MODE): 1 = epilogue releases tiles unread, 2 = no candidate ever passes, 3 = TMEM reads only
 };
 
@@ -502,7 +504,30 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
       const uint32_t ring0 = ptx::opaque(ring_u32);
       uint32_t stage = 0, phase = 0;
+      // Every reader of a slice (the query blocks / pairs with the same blockIdx.y) streams the same
+      // corpus rows; DRAM serves them once only while the readers stay within the L2's reach of each
+      // other.  The leader therefore publishes its tile count every few tiles and holds its loads
+      // while the slowest reader is more than sync_window tiles behind (bounded wait; all CTAs of a
+      // launch are co-resident).  Measured on cfg3: without it the four pairs of a slice drift apart
+      // and the corpus is read twice from DRAM.
+      const int readers = static_cast<int>(gridDim.x) / (kPair ? 2 : 1);
+      const int reader = static_cast<int>(blockIdx.x) / (kPair ? 2 : 1);
+      int* const prog = (p.progress != nullptr && readers > 1 && rank == 0) ? p.progress + slice * readers : nullptr;
+      const int check_every = max(1, p.sync_window >> 1);
       for (int t = tile_begin; t < tile_end; ++t) {
+        if (prog != nullptr && (t - tile_begin) % check_every == 0) {
+          const int mine = t - tile_begin;
+          if (lane == 0) __stcg(prog + reader, mine);
+          if (mine > p.sync_window) {
+            const unsigned long long t0 = global_timer_ns();
+            for (;;) {
+              int v = lane < readers ? __ldcg(prog + lane) : 0x7fffffff;
+              v = __reduce_min_sync(0xffffffffu, v);
+              if (v + p.sync_window >= mine || global_timer_ns() - t0 > 20000ull) break;
+              __nanosleep(200);
+            }
+          }
+        }
         const int row = t * N_T + static_cast<int>(rank) * kBoxRows;
         for (int kc0 = 0; kc0 < p.num_kc; kc0 += kKcPerStage) {
           const int nb = min(kKcPerStage, p.num_kc - kc0);
@@ -528,6 +553,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           }
         }
       }
+      if (prog != nullptr && lane == 0) __stcg(prog + reader, 0x3fffffff);  // done: never the slowest
     }
   } else if (warp == kMmaWarp) {
     // -------------------------------------------------------------- MMA issuer
