@@ -359,7 +359,7 @@ def main():
                    if n * d * 2 > 126e6 else "inputs fit L2 (config as specified by BASELINE.json)"},
         "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": q * d * 4,
                 "d2h_bytes_per_step": q * k * 12, "api": "GpuIndexFlatIP.search(numpy) -> lxg_search",
-                "host_buffers": "pinned"},
+                "host_buffers": "pinned; read / written in place by the kernels over PCIe (no staging copies)"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "clocks": sampler.summary(),

@@ -33,6 +33,7 @@ static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level
 static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
 static bool g_asmem_768 = true;      // LXG_SCAN_ASMEM=0: 512 < d <= 768 falls back to 64-row tiles, all of A in tensor memory (A/B)
 static int g_sync_mb = 28;           // LXG_SCAN_SYNC_MB: L2 megabytes the readers' spread may cover (all slices together)
+static bool g_zero_copy = true;      // LXG_ZERO_COPY=0: pinned host queries / results go through staging copies
 static bool g_sync_readers = true;   // LXG_SCAN_SYNC=0: the readers of a corpus slice are not kept in step (A/B)
 static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -68,6 +69,18 @@ bool is_pinned_host_ptr(const void* p) {
     return false;
   }
   return a.type == cudaMemoryTypeHost;
+}
+
+// Device-side alias of page-locked, mapped host memory (what cudaHostAlloc / torch's pin_memory give
+// under unified addressing), or nullptr.  Kernels can read the queries from it and write the results
+// into it directly: no staging copies, and the flag read-back is the call's only synchronisation.
+void* mapped_host_alias(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
 }
 
 // One growable device allocation.
@@ -329,6 +342,8 @@ int lxg_init(int device) {
   g_num_sms = prop.multiProcessorCount;
   const char* fs = std::getenv("LXG_SCAN_SINGLE");
   g_force_single = fs && fs[0] == '1';
+  const char* zc = std::getenv("LXG_ZERO_COPY");
+  g_zero_copy = !(zc && zc[0] == '0');
   const char* sr = std::getenv("LXG_SCAN_SYNC");
   g_sync_readers = !(sr && sr[0] == '0');
   const char* smb = std::getenv("LXG_SCAN_SYNC_MB");
@@ -758,7 +773,10 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   LXG_CUDA(ix->ws_out.reserve(stage_bytes));
   uint8_t* stg = reinterpret_cast<uint8_t*>(ix->ws_out.p);
   const float* xd = x;
-  if (!x_dev) {
+  void* const x_alias = (!x_dev && g_zero_copy) ? mapped_host_alias(x) : nullptr;
+  if (x_alias != nullptr) {
+    xd = reinterpret_cast<const float*>(x_alias);  // the preparation kernel reads the pinned queries over PCIe
+  } else if (!x_dev) {
     const void* src = x;
     if (!is_pinned_host_ptr(x)) {  // pageable caller memory: bounce through the pinned stage
       LXG_CUDA(ix->h_stage.reserve(std::max(x_bytes, out_elems * 12)));
@@ -771,7 +789,13 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   }
   float* Dd = D_out;
   long long* Id = reinterpret_cast<long long*>(I_out);
-  if (!out_dev) {
+  void* const d_alias = (!out_dev && g_zero_copy) ? mapped_host_alias(D_out) : nullptr;
+  void* const i_alias = (!out_dev && g_zero_copy) ? mapped_host_alias(I_out) : nullptr;
+  const bool out_zero_copy = d_alias != nullptr && i_alias != nullptr;
+  if (out_zero_copy) {  // the merge / exact kernels write the pinned result buffers directly
+    Dd = reinterpret_cast<float*>(d_alias);
+    Id = reinterpret_cast<long long*>(i_alias);
+  } else if (!out_dev) {
     Id = reinterpret_cast<long long*>(stg);
     Dd = reinterpret_cast<float*>(stg + out_elems * 8);
   }
@@ -791,7 +815,9 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   ix->stats.kernel_launches = total_launches;
   if (!out_dev) {
     ix->stats.uncertified = total_flag;
-    if (is_pinned_host_ptr(D_out) && is_pinned_host_ptr(I_out)) {
+    if (out_zero_copy) {
+      // nothing to copy; every search_device call above ended with the flag read-back's synchronise
+    } else if (is_pinned_host_ptr(D_out) && is_pinned_host_ptr(I_out)) {
       LXG_CUDA(cudaMemcpyAsync(I_out, Id, out_elems * 8, cudaMemcpyDeviceToHost, st));
       LXG_CUDA(cudaMemcpyAsync(D_out, Dd, out_elems * 4, cudaMemcpyDeviceToHost, st));
       LXG_CUDA(cudaStreamSynchronize(st));

@@ -298,6 +298,20 @@ def test_hundreds_of_uncertified_queries_in_one_batch_also_asynchronously():
     assert np.array_equal(It.cpu().numpy(), I) and np.array_equal(Dt.cpu().numpy(), D)
 
 
+def test_pinned_host_queries_are_read_in_place():
+    """Page-locked queries (and the page-locked result arrays GpuIndexFlatIP.search allocates) are
+    read / written by the kernels directly over PCIe - same bits as the staged path."""
+    corpus = make_corpus(30000, 384)
+    ix = _index(corpus)
+    x = make_queries(300, 384)
+    D, I = ix.search(x, 50, normalize=True)                       # pageable queries: staged copy
+    xp = torch.from_numpy(x).pin_memory().numpy()
+    Dp, Ip = ix.search(xp, 50, normalize=True)                    # pinned queries: zero copy
+    assert np.array_equal(I, Ip) and np.array_equal(D, Dp)
+    assert np.array_equal(xp, x)                                  # queries are not modified
+    _check(corpus, xp, 50)
+
+
 def test_more_queries_than_one_launch_holds():
     """nq > 148 * 128: lxg_search splits the batch over several launches."""
     corpus = make_corpus(3000, 64)
