@@ -298,6 +298,15 @@ def test_hundreds_of_uncertified_queries_in_one_batch_also_asynchronously():
     assert np.array_equal(It.cpu().numpy(), I) and np.array_equal(Dt.cpu().numpy(), D)
 
 
+def test_corpus_larger_than_l2_with_several_readers_per_slice():
+    """230 MB corpus, 3 query blocks: the readers of a corpus slice are kept in step through the
+    progress counters (ScanParams.progress, only enabled beyond the L2's size) - results unchanged."""
+    corpus = make_corpus(300000, 384)
+    ix = _check(corpus, make_queries(300, 384), 10)
+    st = ix.last_stats()
+    assert st["query_blocks"] == 3 and st["slices"] >= 30
+
+
 def test_pinned_host_queries_are_read_in_place():
     """Page-locked queries (and the page-locked result arrays GpuIndexFlatIP.search allocates) are
     read / written by the kernels directly over PCIe - same bits as the staged path."""
