@@ -85,3 +85,20 @@ def test_product_package_never_imports_the_oracle():
     for path in (ROOT / "lean_explore_b200" / "csrc").iterdir():
         if path.suffix in (".cu", ".cuh", ".h"):
             assert "oracle/" not in path.read_text().replace("oracle/faiss_flat.py)", ""), path
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/lxg.h is the whole boundary: it must compile as C99 on its own (no C++, no CUDA, no
+    torch types) and every handle / struct it declares must be usable from C."""
+    src = tmp_path / "use_lxg.c"
+    src.write_text(
+        '#include "lxg.h"\n'
+        "int probe(void) {\n"
+        "  lxg_index* ix = 0; lxg_encoder* enc = 0; lxg_decoder* dec = 0;\n"
+        "  lxg_search_stats st; lxg_timing tm; lxg_bert_weights bw; lxg_qwen3_weights qw; lxg_qwen3_layer ql;\n"
+        "  (void)ix; (void)enc; (void)dec; (void)st; (void)tm; (void)bw; (void)qw; (void)ql;\n"
+        "  return LXG_OK + LXG_F16 + LXG_POOL_CLS + (int)sizeof(lxg_bert_layer);\n"
+        "}\n")
+    out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                          "-I", str(HEADER.parent), str(src)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
