@@ -65,6 +65,7 @@ __device__ __forceinline__ void warp_exact_dots(const CorpusView& cv, const long
   if (cv.dtype == 1) {
     const __half* base = reinterpret_cast<const __half*>(cv.rows);
     const bool vec = (cv.pitch % 4 == 0) && (reinterpret_cast<uintptr_t>(base) % 8 == 0);
+#pragma unroll 2
     for (int i = 4 * lane; i < d; i += 128) {
       float v[R][4];
       if (vec && i + 3 < d) {
@@ -91,6 +92,7 @@ __device__ __forceinline__ void warp_exact_dots(const CorpusView& cv, const long
   } else {
     const float* base = reinterpret_cast<const float*>(cv.rows);
     const bool vec = (cv.pitch % 4 == 0) && (reinterpret_cast<uintptr_t>(base) % 16 == 0);
+#pragma unroll 2
     for (int i = 4 * lane; i < d; i += 128) {
       float v[R][4];
       if (vec && i + 3 < d) {
