@@ -25,6 +25,8 @@ embed_ln_kernel(const int* __restrict__ ids, int tokens, int seq, int hidden, in
                 const __half* __restrict__ word, const __half* __restrict__ pos,
                 const __half* __restrict__ type0, const float* __restrict__ g,
                 const float* __restrict__ b, float eps, __half* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
@@ -78,6 +80,8 @@ embed_ln_kernel(const int* __restrict__ ids, int tokens, int seq, int hidden, in
 static __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* __restrict__ x, int tokens, int hidden, const float* __restrict__ g,
                  const float* __restrict__ b, float eps, __half* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (t >= tokens) return;
@@ -583,6 +587,8 @@ attention_mma_kernel(const __half* __restrict__ qkv, const int* __restrict__ mas
   constexpr int kOTiles = DH / 8;    // n-tiles of the context
   constexpr int kKPitch = DH + 8;    // halves; (DH+8)/2 words = 4 * odd: conflict-free fragment loads
   extern __shared__ __align__(16) uint8_t asm_raw[];
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int seq_pad = (seq + 15) & ~15;
   const int vpitch = seq_pad + 8;
@@ -729,6 +735,8 @@ static __global__ void __launch_bounds__(kAttnThreads)
 attention_scalar_kernel(const __half* __restrict__ qkv, const int* __restrict__ mask, int seq, int hidden,
                  int heads, __half* __restrict__ ctx) {
   extern __shared__ __align__(16) uint8_t asm_raw[];
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
   const int dh = hidden / heads;
   const int b = blockIdx.x / heads, h = blockIdx.x % heads;
   const int kpitch = dh + 2;  // fp16 elements; odd word pitch -> conflict-free key-strided reads
@@ -809,6 +817,7 @@ attention_scalar_kernel(const __half* __restrict__ qkv, const int* __restrict__ 
 static __global__ void __launch_bounds__(256)
 pool_normalize_kernel(const __half* __restrict__ hs, const int* __restrict__ mask, int seq, int hidden,
                       int pool_cls, float* __restrict__ out) {
+  ptx::pdl_wait();
   const int b = blockIdx.x;
   __shared__ float red[8];
   __shared__ float s_cnt;

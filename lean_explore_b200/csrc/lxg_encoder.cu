@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -100,12 +101,16 @@ int launch_forward(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
   int launches = 0;
   const int warps_per_block = 8;
   const int row_blocks = (tokens + warps_per_block - 1) / warps_per_block;
-  embed_ln_kernel<<<row_blocks, 256, 0, st>>>(e->ids, tokens, s, H, e->w.vocab, reinterpret_cast<const __half*>(e->w.word_emb),
-                                              reinterpret_cast<const __half*>(e->w.pos_emb),
-                                              reinterpret_cast<const __half*>(e->w.type_emb),
-                                              reinterpret_cast<const float*>(e->w.emb_ln_g),
-                                              reinterpret_cast<const float*>(e->w.emb_ln_b), e->w.ln_eps, e->h);
-  LXG_CUDA(cudaGetLastError());
+  // the first kernel follows the input copies; every later one is a programmatic dependent launch
+  // (its prologue overlaps the previous kernel's tail, also inside the captured graph; LXG_PDL=0 disables)
+  static const bool pdl = [] {
+    const char* v = std::getenv("LXG_PDL");
+    return !(v && v[0] == '0');
+  }();
+  LXG_CUDA(lxg_launch(embed_ln_kernel, dim3(row_blocks), dim3(256), 0, st, false, static_cast<const int*>(e->ids), tokens, s, H, e->w.vocab,
+                      reinterpret_cast<const __half*>(e->w.word_emb), reinterpret_cast<const __half*>(e->w.pos_emb),
+                      reinterpret_cast<const __half*>(e->w.type_emb), reinterpret_cast<const float*>(e->w.emb_ln_g),
+                      reinterpret_cast<const float*>(e->w.emb_ln_b), e->w.ln_eps, e->h));
   ++launches;
   // attention: tensor-core kernel for head sizes 32 / 64 (every shipped model), scalar fallback otherwise
   const bool attn_mma = dh == 32 || dh == 64;
@@ -137,45 +142,44 @@ int launch_forward(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
     gp.m = tokens;
     gp.n = 3 * H;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiStore>(e->map_h, e->map_wqkv[l], gp, st));
+    LXG_CUDA(launch_gemm<kEpiStore>(e->map_h, e->map_wqkv[l], gp, st, pdl));
+    const __half* qkv_c = e->qkv;
+    const int* mask_c = e->mask;
     if (attn_which == 1)
-      attention_mma_kernel<32><<<b * heads, attn_warps * 32, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
+      LXG_CUDA(lxg_launch(attention_mma_kernel<32>, dim3(b * heads), dim3(attn_warps * 32), attn_smem, st, pdl, qkv_c, mask_c, s, H, heads, e->ctx));
     else if (attn_which == 2)
-      attention_mma_kernel<64><<<b * heads, attn_warps * 32, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
+      LXG_CUDA(lxg_launch(attention_mma_kernel<64>, dim3(b * heads), dim3(attn_warps * 32), attn_smem, st, pdl, qkv_c, mask_c, s, H, heads, e->ctx));
     else
-      attention_scalar_kernel<<<b * heads, kAttnThreads, attn_smem, st>>>(e->qkv, e->mask, s, H, heads, e->ctx);
-    LXG_CUDA(cudaGetLastError());
+      LXG_CUDA(lxg_launch(attention_scalar_kernel, dim3(b * heads), dim3(kAttnThreads), attn_smem, st, pdl, qkv_c, mask_c, s, H, heads, e->ctx));
     // attention.output.dense + residual -> LayerNorm
     gp.bias = reinterpret_cast<const float*>(L.bo);
     gp.residual = e->h;
     gp.out = e->pre;
     gp.n = H;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiResid>(e->map_ctx, e->map_wo[l], gp, st));
-    layernorm_kernel<<<row_blocks, 256, 0, st>>>(e->pre, tokens, H, reinterpret_cast<const float*>(L.ln1_g),
-                                                 reinterpret_cast<const float*>(L.ln1_b), e->w.ln_eps, e->h);
-    LXG_CUDA(cudaGetLastError());
+    LXG_CUDA(launch_gemm<kEpiResid>(e->map_ctx, e->map_wo[l], gp, st, pdl));
+    LXG_CUDA(lxg_launch(layernorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, static_cast<const float*>(e->pre), tokens, H,
+                        reinterpret_cast<const float*>(L.ln1_g), reinterpret_cast<const float*>(L.ln1_b), e->w.ln_eps, e->h));
     // intermediate.dense + GELU
     gp.bias = reinterpret_cast<const float*>(L.b1);
     gp.residual = nullptr;
     gp.out = e->ffn;
     gp.n = F;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiGelu>(e->map_h, e->map_w1[l], gp, st));
+    LXG_CUDA(launch_gemm<kEpiGelu>(e->map_h, e->map_w1[l], gp, st, pdl));
     // output.dense + residual -> LayerNorm
     gp.bias = reinterpret_cast<const float*>(L.b2);
     gp.residual = e->h;
     gp.out = e->pre;
     gp.n = H;
     gp.k = F;
-    LXG_CUDA(launch_gemm<kEpiResid>(e->map_ffn, e->map_w2[l], gp, st));
-    layernorm_kernel<<<row_blocks, 256, 0, st>>>(e->pre, tokens, H, reinterpret_cast<const float*>(L.ln2_g),
-                                                 reinterpret_cast<const float*>(L.ln2_b), e->w.ln_eps, e->h);
-    LXG_CUDA(cudaGetLastError());
+    LXG_CUDA(launch_gemm<kEpiResid>(e->map_ffn, e->map_w2[l], gp, st, pdl));
+    LXG_CUDA(lxg_launch(layernorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, static_cast<const float*>(e->pre), tokens, H,
+                        reinterpret_cast<const float*>(L.ln2_g), reinterpret_cast<const float*>(L.ln2_b), e->w.ln_eps, e->h));
     launches += 7;
   }
-  pool_normalize_kernel<<<b, 256, H * sizeof(float), st>>>(e->h, e->mask, s, H, pool == LXG_POOL_CLS ? 1 : 0, e->out_buf);
-  LXG_CUDA(cudaGetLastError());
+  LXG_CUDA(lxg_launch(pool_normalize_kernel, dim3(b), dim3(256), H * sizeof(float), st, pdl, static_cast<const __half*>(e->h),
+                      static_cast<const int*>(e->mask), s, H, pool == LXG_POOL_CLS ? 1 : 0, e->out_buf));
   ++launches;
   e->launches = launches;
   return LXG_OK;
