@@ -46,6 +46,12 @@ class GpuEmbeddingClient:
         if max_length is not None:
             logger.info("Set max sequence length to %d", max_length)
 
+    def embed_array(self, texts: list[str], is_query: bool = False):
+        """Batched twin without the per-float Python lists of ``EmbeddingResponse``: float32
+        ``[len(texts), d]`` straight from the encoder (what ``retrieve_semantic_candidates_batch``
+        feeds the k-NN search with; a 1024 x 1024 batch spends ~50 ms in ``tolist()`` otherwise)."""
+        return self.model.encode(texts, batch_size=self.batch_size, is_query=is_query)
+
     async def embed(self, texts: list[str], is_query: bool = False) -> EmbeddingResponse:
         loop = asyncio.get_event_loop()
 

@@ -9,9 +9,9 @@ out-of-range labels -> max similarity per declaration id, info log line).  Added
 ``retrieve_semantic_candidates_batch`` - the nq > 1 entry point the reference lacks (its
 call is hard-wired to one query, ``:237-238``) that BASELINE.json's QPS configs need.
 
-BM25, RRF, dependency boost, reranking, SQL and the MCP/CLI front-ends are out of scope
-(DESIGN.md); an unmodified reference engine gets this path through
-``lean_explore_b200.faiss_compat.install()`` + ``SearchEngine(embedding_client=...)``.
+BM25, RRF, dependency boost and the rerank blend around this path live in
+``lean_explore_b200.hybrid`` (``HybridSearchEngine``); an unmodified reference engine gets this
+path through ``lean_explore_b200.faiss_compat.install()`` + ``SearchEngine(embedding_client=...)``.
 """
 
 from __future__ import annotations
@@ -111,8 +111,15 @@ class SemanticRetriever:
         """nq > 1 twin: one encoder call and one search for the whole batch."""
         if not queries:
             return []
-        embedding_response = await self.embedding_client.embed(list(queries), is_query=True)
-        x = np.array(embedding_response.embeddings, dtype=np.float32)
+        client = self.embedding_client
+        if hasattr(client, "embed_array"):  # GpuEmbeddingClient: numpy straight from the encoder
+            import asyncio
+
+            x = await asyncio.get_event_loop().run_in_executor(None, lambda: client.embed_array(list(queries), is_query=True))
+            x = np.ascontiguousarray(x, dtype=np.float32)
+        else:  # any other client with the reference's duck type
+            embedding_response = await client.embed(list(queries), is_query=True)
+            x = np.array(embedding_response.embeddings, dtype=np.float32)
         distances, indices = self.faiss_informal_index.search(x, faiss_k, normalize=True)
         id_map = self.faiss_informal_id_map
         return [self._to_map(indices[i], distances[i], id_map) for i in range(len(queries))]

@@ -171,6 +171,17 @@ def test_retrieve_semantic_candidates_single_and_batch(tmp_path):
     assert max(batch[1], key=batch[1].get) == 1000 + 77 // 2
     assert asyncio.run(r.retrieve_semantic_candidates_batch([], 5)) == []
 
+    class _ArrayClient(_FakeEmbeddingClient):  # GpuEmbeddingClient's batched twin: numpy, no per-float lists
+        def embed_array(self, texts, is_query=False):
+            self.calls.append((list(texts), is_query, "array"))
+            return np.array([self.table[t] for t in texts], dtype=np.float32)
+
+    fast = _ArrayClient(table)
+    r2 = _retriever(tmp_path, mat, id_map, fast)
+    batch2 = asyncio.run(r2.retrieve_semantic_candidates_batch(["q0", "q1"], 20))
+    assert fast.calls == [(["q0", "q1"], True, "array")]
+    assert [sorted(b.items()) for b in batch2] == [sorted(b.items()) for b in batch]
+
 
 # ------------------------------------------------------------------ sharding arithmetic
 def test_shard_rows_partition():
