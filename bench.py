@@ -12,6 +12,10 @@ normalise + fp16 tensor-core scan + exact re-score + top-k).  Prints ONE JSON li
   roofline  the scan kernel's achieved TFLOP/s (or GB/s) against MEASURED_PEAKS.json
   cpu_baseline / --impl reference: the FAISS restatement (numpy sgemm + FAISS-style heaps,
             oracle/) on this box's host cores.
+  extra     (default workload, one GPU) the query-batch sweep Q in {1, 8, 64, 256, 4096} and the
+            engine's own request shape (one query, faiss_k = 1000); the same on the shape of the
+            shipped index (400k x 1024 fp32); the BERT-class encoders and the Qwen3 embedding model /
+            reranker through their host APIs, each with its CPU leg (HF fp32 on the host cores)
 
 Workloads (BASELINE.json configs): cfg1 50k x 384 fp32 top-10 (Q=1000); cfg2 500k x 384 fp16
 top-50 (default; Q=1024); cfg3 2M x 768 fp16 top-50; cfg4 16M x 768 fp16 row-sharded over the
