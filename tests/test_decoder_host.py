@@ -116,3 +116,84 @@ def test_reranker_client_batching_rule_with_a_stub_model(monkeypatch):
     calls.clear()
     assert asyncio.run(client.rerank("q", docs[:3])).scores == r.scores[:3] and calls == [3]
     assert asyncio.run(client.rerank("q", docs, batch_size=100)).scores == r.scores
+
+
+# ---------------------------------------------------------------------------------------
+# The reference's own client tests, replayed against the drop-in classes with a stub model
+# (reference tests/util/reranker_client_test.py:19-185, tests/util/embedding_client_test.py:15-118
+# mock the third-party model the same way).
+
+class _StubTok:
+    def convert_tokens_to_ids(self, t):
+        return 1 if t == "true" else 0
+
+
+class _StubDecoder:
+    tokenizer = _StubTok()
+    max_length = None
+
+    def score_pairs(self, pairs, tt, tf):
+        return [0.5 for _ in pairs]
+
+
+def _reranker(**kw):
+    from lean_explore_b200.reranker_client import GpuRerankerClient
+
+    return GpuRerankerClient(model_name="test-model", model=_StubDecoder(), **kw)
+
+
+def test_reference_reranker_response_and_instruction_cases():
+    import asyncio
+
+    from lean_explore_b200.reranker_client import DEFAULT_INSTRUCTION, RerankerResponse
+
+    response = RerankerResponse(query="test query", scores=[0.9, 0.7, 0.3], model="test-model")
+    assert response.query == "test query" and response.scores == [0.9, 0.7, 0.3] and response.model == "test-model"
+    assert _reranker().instruction == DEFAULT_INSTRUCTION                      # test_default_instruction
+    assert _reranker(instruction="Custom instruction").instruction == "Custom instruction"  # test_custom_instruction
+    result = _reranker()._format_pair("search query", "document text")          # test_format_pair
+    assert "<Instruct>:" in result and "<Query>: search query" in result and "<Document>: document text" in result
+    assert DEFAULT_INSTRUCTION in result                                        # test_format_pair_includes_instruction
+    client = _reranker()
+    empty = asyncio.run(client.rerank("query", []))                            # test_rerank_empty_documents
+    assert isinstance(empty, RerankerResponse) and empty.scores == [] and empty.query == "query"
+    assert client.rerank_sync("query", []).scores == []                        # test_rerank_sync_empty_documents
+    got = asyncio.run(client.rerank("query", ["doc1", "doc2"]))                # test_rerank_returns_response
+    assert isinstance(got, RerankerResponse) and got.model == "test-model" and len(got.scores) == 2
+    assert client._token_true_id == 1 and client._token_false_id == 0          # reranker_client.py:85-86
+
+
+def test_reference_embedding_client_cases(monkeypatch):
+    """EmbeddingResponse fields; max_length / batch size plumbing; is_query reaches the encoder as the
+    query-prompt switch (the reference passes prompt_name="query", embedding_client.py:97-98)."""
+    import asyncio
+
+    import lean_explore_b200.decoder as dec_mod
+    import lean_explore_b200.encoder as enc_mod
+    from lean_explore_b200.embedding_client import EmbeddingResponse, GpuEmbeddingClient
+
+    response = EmbeddingResponse(texts=["hello", "world"], embeddings=[[0.1, 0.2], [0.3, 0.4]], model="test-model")
+    assert response.texts == ["hello", "world"] and len(response.embeddings) == 2 and response.model == "test-model"
+
+    calls = []
+
+    class _Model:
+        def __init__(self, max_length):
+            self.max_length = max_length
+
+        def encode(self, texts, batch_size=8, is_query=False):
+            calls.append((list(texts), batch_size, is_query))
+            return np.arange(len(texts) * 4, dtype=np.float32).reshape(len(texts), 4)
+
+    monkeypatch.setattr(dec_mod, "model_type_of", lambda name: "bert")
+    monkeypatch.setattr(enc_mod, "load_sentence_encoder", lambda name, device=None, max_length=None: _Model(max_length))
+    monkeypatch.setenv("LEAN_EXPLORE_EMBEDDING_BATCH_SIZE", "5")
+    client = GpuEmbeddingClient(model_name="test-model", max_length=256)       # test_max_length_setting
+    assert client.model.max_length == 256 and client.batch_size == 5 and client.device == "cuda"
+    got = asyncio.run(client.embed(["hello", "world"]))                        # test_embed_returns_response
+    assert isinstance(got, EmbeddingResponse) and len(got.embeddings) == 2 and got.model == "test-model"
+    assert calls[-1] == (["hello", "world"], 5, False)                         # test_embed_without_query_flag
+    asyncio.run(client.embed(["search query"], is_query=True))                 # test_embed_with_query_flag
+    assert calls[-1] == (["search query"], 5, True)
+    assert client.embed_array(["a", "b", "c"], is_query=True).shape == (3, 4)
+    assert GpuEmbeddingClient(model_name="test-model", batch_size=2).batch_size == 2
