@@ -144,6 +144,12 @@ def main():
     g["normalize_scores"] = [dict(scores=s, out=scoring.normalize_scores(s)) for s in score_lists]
     count_lists = [[], [0, 0], [1], [0, 3, 7, 1], [rng.randint(0, 40) for _ in range(23)]]
     g["normalize_dependency_counts"] = [dict(counts=c, out=scoring.normalize_dependency_counts(c)) for c in count_lists]
+    g["compute_ranks"] = [dict(scores=s, out=scoring.compute_ranks(s)) for s in score_lists + [[0.5, 1.0, 0.3, 0.8], [1.0, 0.0, 0.5]]]
+    rank_sets = [[[1, 2, 3], [3, 1, 2]], [[rng.randint(1, 30) for _ in range(12)] for _ in range(3)]]
+    g["rrf_lists"] = [dict(ranks=r, k=k, out=scoring.reciprocal_rank_fusion(r, k=k)) for r in rank_sets for k in (0, 60)]
+    fusion_sets = [([[0.0, 0.5, 1.0], [1.0, 0.5, 0.0]], [0.5, 0.5]), ([[3.0, 3.0], [1.0, 2.0]], [0.7, 0.3]), ([], []), ([[], []], [1.0, 1.0]),
+                   ([[rng.uniform(0, 5) for _ in range(9)] for _ in range(3)], [1.0, 0.4, 0.2])]
+    g["weighted_fusion"] = [dict(scores=sl, weights=w, out=scoring.weighted_score_fusion(sl, w)) for sl, w in fusion_sets]
     pairs = [("add comm", "Nat.add_comm"), ("Nat.add_comm", "Nat.add_comm"), ("prime two", "Nat.Prime.two_le"), ("", "x"), ("", ""),
              ("continuous lipschitz", "continuous_of_lipschitz"), ("SUM_COMM", "Finset.sum_comm"), ("det mul", "Matrix.det_mul"),
              ("nat add comm", "Nat.add_comm"), ("list map", "Set.union_comm")]
