@@ -78,6 +78,18 @@ def test_random_strings_match(toks):
         assert mine.tokenize_ids(text) == ref.encode(text, add_special_tokens=False).ids, repr(text)
 
 
+def test_wide_unicode_fuzz_matches(toks):
+    """Letters / digits / punctuation / whitespace of several scripts, combining marks (NFC matters),
+    astral code points, contractions in both cases, runs of newlines and spaces."""
+    mine, ref, _ = toks
+    rng = np.random.default_rng(1)
+    pieces = ["a", "Z", "é", "e\u0301", "ß", "ℕ", "→", "∀", "日", "本", "한", "🎉", "👩\u200d🔬", "0", "7", "٣", "½", " ", "  ", "\t", "\n", "\r\n",
+              "\u00a0", "\u2003", "'s", "'RE", "'ll", "'", "\"", ".", ",", "(", ")", "_", "-", "+=", "<|", "|>", "theorem", "Nat", "add_comm"]
+    for _ in range(400):
+        text = "".join(rng.choice(pieces, size=int(rng.integers(1, 40))))
+        assert mine.tokenize_ids(text) == ref.encode(text, add_special_tokens=False).ids, repr(text)
+
+
 def test_left_padding_truncation_and_eos(toks):
     mine, _, specials = toks
     pad = specials["<|endoftext|>"]
