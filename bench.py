@@ -1,33 +1,40 @@
 #!/usr/bin/env python
 """Benchmark of the semantic-search hot path: queries/sec for exact top-k over an N x d corpus.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg1|cfg4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg4|cfg3|cfg2|cfg1]
                   [--queries Q] [--impl b200|reference]
 
 A "step" is one batch of Q synthetic queries searched against the whole corpus (fused
-normalise + fp16 tensor-core scan + exact re-score + top-k).  Prints ONE JSON line (rank 0).
+normalise + fp16 tensor-core scan + exact re-score + top-k [+ all-gather + shard merge]).
+Prints ONE JSON line (rank 0).
 
-  value     QPS with the query batch already resident in HBM (CUDA events, max over ranks)
-  e2e       QPS through the public host API (numpy in / numpy out, copies inside the timing)
+Default workload for EVERY --gpus N: BASELINE.json config 4 - a 16M x 768 fp16 corpus, top-50,
+1024 queries per step, row-sharded over the N ranks through ShardedFlatIP (lxg_search_ex ->
+ONE NCCL all-gather of the packed per-shard candidates -> lxg_merge_topk_packed).  The corpus is
+24.6 GB, so N = 1 holds all of it and 1/2/4/8 is a STRONG-scaling sweep ("scaling": "strong").
+
+  value     whole-job QPS with the query batch already resident in HBM (CUDA events, max over ranks)
+  e2e       QPS through the host API (numpy in / numpy out, copies inside the timing), pinned and pageable
+  phases    per-step device time of local search / all-gather / merge (CUDA events on the launching stream)
   roofline  the scan kernel's achieved TFLOP/s (or GB/s) against MEASURED_PEAKS.json
-  cpu_baseline / --impl reference: the FAISS restatement (numpy sgemm + FAISS-style heaps,
-            oracle/) on this box's host cores.
-  extra     (default workload, one GPU) the query-batch sweep Q in {1, 8, 64, 256, 4096} and the
-            engine's own request shape (one query, faiss_k = 1000); the same on the shape of the
-            shipped index (400k x 1024 fp32); the BERT-class encoders and the Qwen3 embedding model /
-            reranker through their host APIs, each with its CPU leg (HF fp32 on the host cores)
+  sustained a >= 2 s loop of the same step against the SUSTAINED tensor peak, with the SM clock under load
+  parity    ids of the first queries of the batch against the exact-arithmetic ranking over the FULL corpus
+            (oracle/flat_ip.c lxo_f64_topk_add_rows, streamed from HBM; every rank checks its shard, rank 0 merges)
+  cpu_baseline / --impl reference: the FAISS restatement (numpy sgemm + FAISS-style heaps, oracle/)
+            on this box's host cores.
+  extra     (N = 1 only) the same block for cfg3 (2M x 768, the north star's >= 10k QPS / >= 60 % target)
+            and cfg2 (500k x 384), the query-batch sweep, the shape of the shipped index
+            (400k x 1024 fp32, one query with faiss_k = 1000), the BERT-class encoders and the Qwen3
+            embedding model / reranker through their host APIs, each with its CPU leg.
 
-Workloads (BASELINE.json configs): cfg1 50k x 384 fp32 top-10 (Q=1000); cfg2 500k x 384 fp16
-top-50 (default; Q=1024); cfg3 2M x 768 fp16 top-50; cfg4 16M x 768 fp16 row-sharded over the
-ranks with an NCCL all-gather of per-shard candidates (strong scaling).
-With --gpus N > 1 the default workload runs as N query-parallel replicas (each rank holds the
-whole corpus and searches its own batches; no collective; weak scaling) - the corpus fits one
-GPU, and the north star shards rows only when it does not.
+--workload cfg1|cfg2|cfg3 runs that config on one GPU (with --gpus N > 1: N query-parallel replicas,
+no collective, weak scaling).
 """
 
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import sys
@@ -35,12 +42,17 @@ import threading
 import time
 from pathlib import Path
 
-# The reference arm times the CPU path "with all the host threads it can use": torchrun exports
-# OMP_NUM_THREADS=1 to every rank, which would silently make it a one-core baseline.  Must happen
-# before numpy (OpenBLAS) and the OpenMP oracle library are loaded.
+_WORLD = int(os.environ.get("WORLD_SIZE", "1"))
 if "reference" in sys.argv[1:] or "--impl=reference" in sys.argv[1:]:
+    # The reference arm times the CPU path "with all the host threads it can use": torchrun exports
+    # OMP_NUM_THREADS=1 to every rank, which would silently make it a one-core baseline.  Must happen
+    # before numpy (OpenBLAS) and the OpenMP oracle library are loaded.
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
+elif _WORLD > 1:
+    # the parity check runs the C oracle on every rank's shard: share the host cores between the ranks
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[_v] = str(max(1, (os.cpu_count() or 1) // _WORLD))
 
 import numpy as np
 
@@ -48,14 +60,14 @@ ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 WORKLOADS = {
-    "cfg1": dict(n=50_000, d=384, dtype="float32", k=10, q=1000,
+    "cfg1": dict(n=50_000, d=384, dtype="float32", k=10, q=1000, check_q=64, cpu_q=4000,
                  name="cfg1: 1k-query batch, 50k x 384 fp32 corpus, top-10"),
-    "cfg2": dict(n=500_000, d=384, dtype="float16", k=50, q=1024,
+    "cfg2": dict(n=500_000, d=384, dtype="float16", k=50, q=1024, check_q=64, cpu_q=4096,
                  name="cfg2: Mathlib-scale 500k x 384 fp16 corpus, top-50"),
-    "cfg3": dict(n=2_000_000, d=768, dtype="float16", k=50, q=1024,
+    "cfg3": dict(n=2_000_000, d=768, dtype="float16", k=50, q=1024, check_q=64, cpu_q=1024,
                  name="cfg3: 2M x 768 fp16 corpus, top-50"),
-    "cfg4": dict(n=16_000_000, d=768, dtype="float16", k=50, q=1024,
-                 name="cfg4: 16M x 768 fp16 corpus row-sharded, top-50"),
+    "cfg4": dict(n=16_000_000, d=768, dtype="float16", k=50, q=1024, check_q=16, cpu_q=256,
+                 name="cfg4: 16M x 768 fp16 corpus row-sharded + NCCL all-gather of per-shard top-k, top-50"),
 }
 
 
@@ -66,6 +78,15 @@ def load_peaks():
         return dict(hbm_gbs=j["hbm_gbs"], tflops=j["bf16_tflops"],
                     tflops_sustained=j.get("bf16_tflops_sustained", j["bf16_tflops"]), source="measured")
     return dict(hbm_gbs=6650.0, tflops=1590.0, tflops_sustained=1400.0, source="fallback")
+
+
+def scan_source_sha():
+    """Digest of the scan kernel's sources: a static ncu traffic figure is only quoted for the build it
+    was captured on."""
+    h = hashlib.sha256()
+    for f in ("scan_topk.cuh", "ptx.cuh"):
+        h.update((ROOT / "lean_explore_b200" / "csrc" / f).read_bytes())
+    return h.hexdigest()[:12]
 
 
 # --------------------------------------------------------------------------- synthetic data
@@ -131,7 +152,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.01)
+            time.sleep(0.005)
 
     def __enter__(self):
         if self.nv is not None:
@@ -156,12 +177,14 @@ class CpuFlatIP:
     """The reference's CPU path for this hot path, restated (oracle/): faiss.normalize_L2 +
     IndexFlatIP.search = blocked sgemm (numpy/OpenBLAS, all cores) + FAISS-style per-query
     heaps (oracle/flat_ip.c, OpenMP, all cores).  bench.py is one of the three places allowed
-    to execute oracle/ code, and only as the baseline being reported."""
+    to execute oracle/ code, and only as the baseline being reported / the checker.
 
-    def __init__(self, corpus32: np.ndarray):
+    Streaming form: begin(x, k); add_block(rows fp32, j0) for ascending row blocks; finish().
+    `seconds` accumulates the time spent in the reference's own arithmetic (renorm, sgemm, heaps)."""
+
+    def __init__(self):
         import ctypes
 
-        self.c = corpus32
         so = ROOT / "oracle" / "liblxoracle.so"
         if not so.exists():
             import subprocess
@@ -174,48 +197,287 @@ class CpuFlatIP:
         self.lib.lxo_heap_add_block.argtypes = [sz, sz, vp, vp, vp, sz, i64]
         self.lib.lxo_heap_finish.argtypes = [sz, sz, vp, vp]
         self.threads = int(self.lib.lxo_num_threads())
+        self.seconds = 0.0
 
-    def search(self, x: np.ndarray, k: int, block: int = 16384):
-        x = np.ascontiguousarray(x, dtype=np.float32).copy()
-        nq, d = x.shape
-        self.lib.lxo_renorm_l2(d, nq, x.ctypes.data)
-        D = np.empty((nq, k), dtype=np.float32)
-        I = np.empty((nq, k), dtype=np.int64)
-        self.lib.lxo_heap_init(nq, k, D.ctypes.data, I.ctypes.data)
-        for j0 in range(0, self.c.shape[0], block):
-            s = x @ self.c[j0 : j0 + block].T
-            s = np.ascontiguousarray(s)
-            self.lib.lxo_heap_add_block(nq, k, D.ctypes.data, I.ctypes.data, s.ctypes.data, s.shape[1], j0)
-        self.lib.lxo_heap_finish(nq, k, D.ctypes.data, I.ctypes.data)
-        return D, I
-
-
-def time_cpu(cpu: CpuFlatIP, x: np.ndarray, k: int, budget_s: float):
-    """QPS of the CPU path on a bounded sample: grow the query sample until ~budget_s."""
-    nq = min(16, x.shape[0])
-    cpu.search(x[:nq], k)  # warm-up (BLAS thread pool, page-in)
-    while True:
+    def begin(self, x: np.ndarray, k: int):
         t0 = time.perf_counter()
-        cpu.search(x[:nq], k)
-        dt = time.perf_counter() - t0
-        if dt > budget_s / 3 or nq >= x.shape[0]:
-            return nq / dt, nq, dt
-        nq = min(x.shape[0], max(nq * 2, int(nq * budget_s / 2 / max(dt, 1e-3))))
+        self.x = np.ascontiguousarray(x, dtype=np.float32).copy()
+        nq, d = self.x.shape
+        self.k = k
+        self.lib.lxo_renorm_l2(d, nq, self.x.ctypes.data)
+        self.D = np.empty((nq, k), dtype=np.float32)
+        self.I = np.empty((nq, k), dtype=np.int64)
+        self.lib.lxo_heap_init(nq, k, self.D.ctypes.data, self.I.ctypes.data)
+        self.seconds += time.perf_counter() - t0
+
+    def add_block(self, rows32: np.ndarray, j0: int, block: int = 16384):
+        t0 = time.perf_counter()
+        nq = self.x.shape[0]
+        for b0 in range(0, rows32.shape[0], block):
+            s = np.ascontiguousarray(self.x @ rows32[b0 : b0 + block].T)
+            self.lib.lxo_heap_add_block(nq, self.k, self.D.ctypes.data, self.I.ctypes.data, s.ctypes.data, s.shape[1], j0 + b0)
+        self.seconds += time.perf_counter() - t0
+
+    def finish(self):
+        t0 = time.perf_counter()
+        self.lib.lxo_heap_finish(self.x.shape[0], self.k, self.D.ctypes.data, self.I.ctypes.data)
+        self.seconds += time.perf_counter() - t0
+        return self.D, self.I
+
+    def search(self, corpus32: np.ndarray, x: np.ndarray, k: int):
+        self.begin(x, k)
+        self.add_block(corpus32, 0)
+        return self.finish()
+
+
+def stream_rows_fp32(corpus, chunk_rows=262144):
+    """Yields (first row, fp32 numpy rows) over a CUDA corpus tensor: up-cast on the GPU (exact for
+    fp16), copied through one pinned buffer.  The array is only valid until the next iteration."""
+    import torch
+
+    n, d = corpus.shape
+    chunk_rows = min(chunk_rows, max(1, n))
+    pin = torch.empty((chunk_rows, d), dtype=torch.float32, pin_memory=True)
+    for r0 in range(0, n, chunk_rows):
+        m = min(chunk_rows, n - r0)
+        pin[:m].copy_(corpus[r0 : r0 + m], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        yield r0, pin[:m].numpy()
+
+
+def host_pass(corpus, row_offset, x_check, x_cpu, k):
+    """ONE streaming pass over this rank's corpus rows on the host: the exact-arithmetic top-k of the
+    check queries (oracle, the checker) and - when x_cpu is given - the timed fp32 FAISS restatement
+    on its query sample (the cpu_baseline).  Returns (exact D64, exact I, port or None)."""
+    from oracle import c_oracle, faiss_flat as ff
+
+    xn = np.ascontiguousarray(x_check, dtype=np.float32).copy()
+    ff.normalize_L2(xn)
+    exact = c_oracle.ExactTopK(xn, k)
+    port = None
+    if x_cpu is not None:
+        port = CpuFlatIP()
+        port.begin(x_cpu, k)
+    for r0, rows in stream_rows_fp32(corpus):
+        exact.add(rows, row_offset + r0)
+        if port is not None:
+            port.add_block(rows, row_offset + r0)
+    if port is not None:
+        port.finish()
+    return exact, port
+
+
+# --------------------------------------------------------------------------- one workload
+def run_workload(key, wl, args, dev, rank, world, peaks, sharded, cpu_baseline, parity):
+    """Builds the corpus of one BASELINE.json config on this rank and measures it.  sharded: rows are
+    split over the ranks behind ShardedFlatIP (the same code at world == 1, minus the NCCL call);
+    otherwise every rank holds the whole corpus and searches its own batches (replicas)."""
+    import torch
+    import torch.distributed as dist
+
+    from lean_explore_b200 import GpuIndexFlatIP
+    from lean_explore_b200.sharded import ShardedFlatIP, shard_rows
+
+    n, d, k, q = wl["n"], wl["d"], wl["k"], wl["q"]
+    steps, warmup = args.steps, max(3, args.warmup)
+    lo, hi = shard_rows(n, world, rank) if sharded else (0, n)
+    corpus = make_corpus_gpu(hi - lo, d, wl["dtype"], dev, row0=lo)
+    index = GpuIndexFlatIP.from_tensor(corpus, row_offset=lo)
+    engine = ShardedFlatIP(index, world if sharded else 1, rank if sharded else 0, timing=True) if sharded else None
+    # sharded: the same queries on every rank; replicas: every rank its own batches
+    batches = [make_queries_gpu(q, d, dev, seed=(0 if sharded else rank * 16) + s) for s in range(4)]
+    rows_local = hi - lo
+    D = torch.empty((q, k), dtype=torch.float32, device=dev)
+    I = torch.empty((q, k), dtype=torch.int64, device=dev)
+
+    def step(i):
+        x = batches[i % len(batches)]
+        if sharded:
+            return engine.search_torch(x, k, normalize=True)
+        return index.search_torch(x, k, normalize=True, out=(D, I))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(*vals):
+        if world == 1:
+            return vals
+        t = torch.tensor(vals, device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return tuple(float(v) for v in t)
+
+    for i in range(warmup):
+        step(i)
+    barrier()
+    if sharded:
+        engine.pop_timing()
+
+    # ---- the timed region: K steps, CUDA events on the launching stream, max over ranks
+    sampler = ClockSampler(dev.index or 0)
+    index.set_timing(True)
+    index.get_timing()
+    with sampler:
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for i in range(steps):
+            step(i)
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    tm = index.get_timing()
+    index.set_timing(False)
+    phases = engine.pop_timing() if sharded else None
+    if sharded:
+        engine.timing = False
+    my_launches = index.last_stats()["kernel_launches"] + (1 if sharded else 0)  # + merge_shards_kernel
+    (ms,) = max_over_ranks(ms)
+    units = q * steps * (1 if sharded else world)
+    res = {"value": round(units / (ms / 1e3), 1), "ms_per_step": round(ms / steps, 4), "gpu_launches": my_launches * steps,
+           "clocks": sampler.summary()}
+
+    # ---- end to end through the public host API: numpy in, numpy out, copies inside the timing
+    api = engine if sharded else index
+    e2e = {}
+    for kind in ("pinned", "pageable"):
+        if kind == "pinned":
+            xh = [b.cpu().pin_memory().numpy() for b in batches]
+        else:
+            xh = [np.array(b.cpu().numpy(), copy=True) for b in batches]
+        api.search(xh[0], k, normalize=True)
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(steps):
+            api.search(xh[i % len(xh)], k, normalize=True)
+        torch.cuda.synchronize()
+        (dt,) = max_over_ranks(time.perf_counter() - t0)
+        e2e[kind] = units / dt
+    res["e2e"] = {"value": round(e2e["pinned"], 1), "unit": "queries/s", "h2d_bytes_per_step": q * d * 4,
+                  "d2h_bytes_per_step": q * k * 12,
+                  "api": ("ShardedFlatIP.search(numpy) -> lxg_search_ex + all_gather + lxg_merge_topk_packed" if sharded
+                          else "GpuIndexFlatIP.search(numpy) -> lxg_search"),
+                  "host_buffers": "pinned (page-locked) query / result arrays",
+                  "pageable_value": round(e2e["pageable"], 1),
+                  "pageable_note": "what SearchEngine passes today (np.array, engine.py:238): bounced through a pinned stage"}
+
+    # ---- roofline of the dominant kernel (pass-1 scan), per launch, from CUDA events on its stream
+    calls = max(1, tm["calls"])
+    scan_ms = tm["scan_ms"] / calls
+    flops = 2.0 * q * rows_local * d
+    bytes_alg = rows_local * d * 2 + q * d * 4 + q * k * 12
+    tf = flops / (scan_ms / 1e3) / 1e12
+    gbs = bytes_alg / (scan_ms / 1e3) / 1e9
+    tensor_frac, hbm_frac = tf / peaks["tflops"], gbs / peaks["hbm_gbs"]
+    ridge_q = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)  # fp16: flop/byte == Q
+    if q >= ridge_q:
+        roof = dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tflops"], unit="TFLOP/s", frac=round(tensor_frac, 4))
+    else:
+        roof = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s", frac=round(hbm_frac, 4))
+    roof.update(traffic=None, traffic_source=None, kernel="scan_topk_kernel", ms_per_launch=round(scan_ms, 4),
+                peak_source=peaks["source"] + " burst (kernel timed per launch)",
+                other_bound_frac=round(hbm_frac if roof["bound"] == "tensor" else tensor_frac, 4),
+                rows_per_launch=rows_local, algorithmic_bytes=int(bytes_alg), algorithmic_flops=flops,
+                prep_ms_per_launch=round(tm.get("prep_ms", 0.0) / calls, 4),
+                merge_ms_per_launch=round(tm["merge_ms"] / calls, 4),
+                exact_ms_per_launch=round(tm["exact_ms"] / calls, 4),
+                step_frac=round(flops / (ms / steps / 1e3) / 1e12 / peaks["tflops"], 4))
+    traffic_file = ROOT / "profiles" / "traffic.json"
+    if traffic_file.exists():
+        tj = json.loads(traffic_file.read_text())
+        ent = tj.get("%dx%d" % (rows_local, d))
+        if ent:
+            fresh = ent.get("scan_sha") == scan_source_sha()
+            roof["traffic"] = ent["bytes"] if fresh else None
+            roof["traffic_source"] = ("static ncu --set full capture %s (%s), same kernel sources" % (ent["file"], ent["date"])
+                                      if fresh else "stale: %s was captured on other kernel sources" % ent["file"])
+    res["roofline"] = roof
+    if phases:
+        pc = max(1, phases["calls"])
+        res["phases"] = {"local_search_ms": round(phases["local_ms"] / pc, 4),
+                         "collective_ms": round(phases["collective_ms"] / pc, 4),
+                         "shard_merge_ms": round(phases["merge_ms"] / pc, 4),
+                         "collective": ("all_gather_into_tensor of %d B per rank" % (q * k * 16)) if world > 1 else "none (one shard)"}
+
+    # ---- sustained: the same step for >= 2 s (clocks settle at the power limit), against the sustained peak
+    if not args.no_sustained:
+        n_sus = max(steps, int(2000.0 / max(ms / steps, 1e-3)) + 1)
+        sus_sampler = ClockSampler(dev.index or 0)
+        with sus_sampler:
+            barrier()
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for i in range(n_sus):
+                step(i)
+            s1.record()
+            barrier()
+        (sms,) = max_over_ranks(s0.elapsed_time(s1))
+        step_tf = 2.0 * q * rows_local * d / (sms / n_sus / 1e3) / 1e12
+        res["sustained"] = {"seconds": round(sms / 1e3, 2), "steps": n_sus,
+                            "value": round(q * n_sus * (1 if sharded else world) / (sms / 1e3), 1),
+                            "ms_per_step": round(sms / n_sus, 4), "step_tflops_per_gpu": round(step_tf, 1),
+                            "peak": peaks["tflops_sustained"], "frac_of_sustained_peak": round(step_tf / peaks["tflops_sustained"], 4),
+                            "clocks": sus_sampler.summary()}
+
+    # ---- parity at full size + the CPU baseline, in ONE host pass over the corpus
+    if parity or cpu_baseline:
+        cq = min(wl["check_q"], q)
+        xs_all = torch.cat(batches).cpu().numpy()
+        x_cpu = xs_all[: min(wl["cpu_q"], xs_all.shape[0])] if cpu_baseline else None
+        Dg, Ig = api.search(xs_all if cpu_baseline else xs_all[:q], k, normalize=True)
+        exact, port = host_pass(corpus, lo, xs_all[:cq], x_cpu, k)
+        if sharded and world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, (exact.D, exact.I))
+            if rank == 0:
+                for r in range(1, world):
+                    exact.merge(*parts[r])
+        D64, I64 = exact.result()
+        live = I64 >= 0
+        res["parity"] = {"queries_checked": cq, "corpus_rows_checked": n,
+                         "oracle": "exact arithmetic (fp64 sums of exact products) over the full corpus, oracle/flat_ip.c",
+                         "ids_equal_exact": round(float((Ig[:cq] == I64).mean()), 6),
+                         "max_abs_score_err": float(np.abs(Dg[:cq][live] - D64[live]).max()) if live.any() else 0.0}
+        if port is not None:
+            Ic, nq_s = port.I, port.x.shape[0]
+            differ = Ig[:nq_s] != Ic
+            # a disagreement with the fp32 restatement is legitimate where two ranks are closer than fp32
+            # sgemm noise: the GPU's own scores are the correctly rounded exact ones (checked above)
+            scale = 1.0  # queries are normalised by the search, corpus rows are unit vectors: |score| <= 1
+            gap = np.abs(np.diff(Dg[:nq_s].astype(np.float64), axis=1))
+            near = np.zeros(differ.shape, dtype=bool)
+            tol = 4e-6 * scale
+            near[:, :-1] |= gap < tol
+            near[:, 1:] |= gap < tol
+            res["cpu_baseline"] = {
+                "value": round(nq_s / port.seconds, 1), "unit": "queries/s", "cores": port.threads, "kind": "port",
+                "sample": "%d queries x full %d x %d corpus (fp32 rows streamed from HBM), %.1f s of renorm + sgemm + heaps; "
+                          "numpy/OpenBLAS sgemm + FAISS-style heaps (faiss-cpu is not installable offline)" % (nq_s, n, d, port.seconds),
+                "host_cpus": os.cpu_count(),
+                "ids_vs_fp32_port": {"frac_equal": round(float(1.0 - differ.mean()), 6), "mismatches": int(differ.sum()),
+                                     "mismatches_at_near_ties": int((differ & near).sum()), "near_tie_tol": tol,
+                                     "positions": int(differ.size)}}
+    res["_rows_local"] = rows_local
+    res["_index"] = index
+    res["_corpus"] = corpus
+    return res
 
 
 # --------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="cfg4", choices=sorted(WORKLOADS))
     ap.add_argument("--queries", type=int, default=None)
     ap.add_argument("--k", type=int, default=None)
-    ap.add_argument("--cpu-budget", type=float, default=15.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extra", action="store_true", help="skip the secondary cfg3 / sweep numbers")
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary cfg3 / cfg2 / sweep / encoder numbers")
     args = ap.parse_args()
 
     wl = dict(WORKLOADS[args.workload])
@@ -235,8 +497,6 @@ def main():
     import torch
     import torch.distributed as dist
 
-    from lean_explore_b200 import GpuIndexFlatIP
-
     assert torch.cuda.is_available(), "bench.py needs a B200; there is no CPU fallback"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -247,163 +507,70 @@ def main():
     sharded = args.workload == "cfg4"
     n, d, k, q = wl["n"], wl["d"], wl["k"], wl["q"]
     peaks = load_peaks()
-
-    if sharded:
-        from lean_explore_b200.sharded import ShardedFlatIP, shard_rows
-
-        lo, hi = shard_rows(n, world, rank)
-        corpus = make_corpus_gpu(hi - lo, d, wl["dtype"], dev, row0=lo)
-        index = GpuIndexFlatIP.from_tensor(corpus, row_offset=lo)
-        engine = ShardedFlatIP(index, world, rank)
-        batches = [make_queries_gpu(q, d, dev, seed=s) for s in range(4)]  # same queries on every rank
-        rows_local = hi - lo
-    else:
-        corpus = make_corpus_gpu(n, d, wl["dtype"], dev)
-        index = GpuIndexFlatIP.from_tensor(corpus)
-        engine = None
-        batches = [make_queries_gpu(q, d, dev, seed=rank * 16 + s) for s in range(4)]
-        rows_local = n
-    D = torch.empty((q, k), dtype=torch.float32, device=dev)
-    I = torch.empty((q, k), dtype=torch.int64, device=dev)
-
-    def step(i):
-        x = batches[i % len(batches)]
-        if sharded:
-            return engine.search_torch(x, k, normalize=True)
-        return index.search_torch(x, k, normalize=True, out=(D, I))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
-
-    sampler = ClockSampler(local_rank)
-    index.set_timing(True)
-    index.get_timing()
-    with sampler:
-        barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for i in range(args.steps):
-            step(i)
-        ev1.record()
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        tm = index.get_timing()
-        index.set_timing(False)
-        launches = index.last_stats()["kernel_launches"] * args.steps + (args.steps if sharded else 0)
-
-        # end to end through the public host API: numpy in, numpy out, copies inside the timing
-        e2e = None
-        if not sharded:
-            xh = [b.cpu().pin_memory().numpy() for b in batches]  # pinned host inputs (bench contract)
-            index.search(xh[0], k, normalize=True)
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
-                index.search(xh[i % len(xh)], k, normalize=True)
-            torch.cuda.synchronize()
-            e2e_s = time.perf_counter() - t0
-        else:
-            xh = [b.cpu().numpy() for b in batches]
-            engine.search(xh[0], k, normalize=True)
-            barrier()
-            t0 = time.perf_counter()
-            for i in range(args.steps):
-                engine.search(xh[i % len(xh)], k, normalize=True)
-            torch.cuda.synchronize()
-            e2e_s = time.perf_counter() - t0
-
-    if world > 1:
-        t = torch.tensor([ms, e2e_s * 1e3], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_s = float(t[0]), float(t[1]) / 1e3
-    units = q * args.steps * (1 if sharded else world)
-    value = units / (ms / 1e3)
-    e2e_value = units / e2e_s
-
-    # roofline of the dominant kernel (pass-1 scan), per launch, from CUDA events on its stream
-    scan_ms = tm["scan_ms"] / max(1, tm["calls"])
-    flops = 2.0 * q * rows_local * d
-    bytes_alg = rows_local * d * 2 + q * d * 4 + q * k * 12
-    tf = flops / (scan_ms / 1e3) / 1e12
-    gbs = bytes_alg / (scan_ms / 1e3) / 1e9
-    tensor_frac, hbm_frac = tf / peaks["tflops"], gbs / peaks["hbm_gbs"]
-    ridge_q = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)  # fp16: flop/byte == Q
-    if q >= ridge_q:
-        roof = dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tflops"], unit="TFLOP/s",
-                    frac=round(tensor_frac, 4), traffic=None)
-    else:
-        roof = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s",
-                    frac=round(hbm_frac, 4), traffic=None)
-    roof.update(kernel="scan_topk_kernel", ms_per_launch=round(scan_ms, 4), peak_source=peaks["source"],
-                other_bound_frac=round(hbm_frac if roof["bound"] == "tensor" else tensor_frac, 4),
-                prep_ms_per_launch=round(tm.get("prep_ms", 0.0) / max(1, tm["calls"]), 4),
-                merge_ms_per_launch=round(tm["merge_ms"] / max(1, tm["calls"]), 4),
-                exact_ms_per_launch=round(tm["exact_ms"] / max(1, tm["calls"]), 4))
-    traffic_file = ROOT / "profiles" / "traffic.json"
-    if traffic_file.exists():
-        roof["traffic"] = json.loads(traffic_file.read_text()).get(args.workload)
+    res = run_workload(args.workload, wl, args, dev, rank, world, peaks, sharded,
+                       cpu_baseline=(world == 1 and not args.no_cpu_baseline), parity=not args.no_parity)
+    index, corpus = res.pop("_index"), res.pop("_corpus")
+    res.pop("_rows_local")
 
     out = {
         "metric": "queries/sec top-50 over Nxd corpus" if k == 50 else f"queries/sec top-{k} over Nxd corpus",
-        "value": round(value, 1), "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-        "warmup": max(3, args.warmup), "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True,
+        "value": res["value"], "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": res["ms_per_step"], "higher_is_better": True,
         "scaling": "strong" if sharded else "weak", "vs_baseline": None, "dtype": "f16xf16->f32 scan, f64 re-score",
         "data": "synthetic",
         "config": {"workload": wl["name"], "corpus_rows": n, "d": d, "corpus_dtype": wl["dtype"], "k": k,
                    "queries_per_step": q, "normalize": True,
-                   "parallelism": ("row-sharded x%d + NCCL all-gather of per-shard top-k" % world) if sharded
+                   "parallelism": ("row-sharded x%d, one NCCL all-gather of per-shard top-k per step" % world) if sharded
                    else ("query-parallel replicas x%d" % world if world > 1 else "single GPU"),
-                   "l2_policy": "corpus (%.0f MB) larger than L2; 4 rotating query batches" % (n * d * 2 / 1e6)
-                   if n * d * 2 > 126e6 else "inputs fit L2 (config as specified by BASELINE.json)"},
-        "e2e": {"value": round(e2e_value, 1), "unit": "queries/s", "h2d_bytes_per_step": q * d * 4,
-                "d2h_bytes_per_step": q * k * 12, "api": "GpuIndexFlatIP.search(numpy) -> lxg_search",
-                "host_buffers": "pinned; read / written in place by the kernels over PCIe (no staging copies)"},
-        "gpu_launches": int(launches),
-        "roofline": roof,
-        "clocks": sampler.summary(),
+                   "l2_policy": "corpus shard (%.0f MB per GPU) larger than L2; 4 rotating query batches" % (n * d * 2 / 1e6 / (world if sharded else 1))
+                   if n * d * 2 / (world if sharded else 1) > 126e6 else "inputs fit L2 (config as specified by BASELINE.json)"},
+        "e2e": res["e2e"], "gpu_launches": int(res["gpu_launches"]), "roofline": res["roofline"], "clocks": res["clocks"],
     }
+    for key in ("phases", "sustained", "parity", "cpu_baseline"):
+        if key in res:
+            out[key] = res[key]
 
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        c32 = corpus.float().cpu().numpy()
-        cpu = CpuFlatIP(c32)
-        xs = torch.cat(batches).cpu().numpy()
-        qps, nq_s, dt = time_cpu(cpu, xs, k, args.cpu_budget)
-        out["cpu_baseline"] = {"value": round(qps, 1), "unit": "queries/s", "cores": cpu.threads, "kind": "port",
-                               "sample": "%d queries x full %d x %d corpus (fp32), %.1f s; numpy sgemm + FAISS-style heaps"
-                               % (nq_s, n, d, dt), "host_cpus": os.cpu_count()}
-        # parity spot check of what was just timed
-        Dg, Ig = index.search(xs[:nq_s], k, normalize=True)
-        Dc, Ic = cpu.search(xs[:nq_s], k)
-        out["cpu_baseline"]["ids_equal_frac"] = round(float((Ig == Ic).mean()), 6)
-        del c32, cpu
-
-    if rank == 0 and world == 1 and not args.no_extra and args.workload == "cfg2":
-        out["extra"] = extra_numbers(index, d, k, dev, peaks)
+    if rank == 0 and world == 1 and not args.no_extra and args.workload == "cfg4":
+        extra = out["extra"] = {}
+        del index, corpus, res  # release the 24.6 GB corpus
+        torch.cuda.empty_cache()
+        for key in ("cfg3", "cfg2"):
+            try:
+                w2 = dict(WORKLOADS[key])
+                r2 = run_workload(key, w2, args, dev, 0, 1, peaks, sharded=False,
+                                  cpu_baseline=not args.no_cpu_baseline, parity=not args.no_parity)
+                ix2 = r2.pop("_index")
+                r2.pop("_corpus")
+                r2.pop("_rows_local")
+                r2["config"] = {"workload": w2["name"], "corpus_rows": w2["n"], "d": w2["d"], "k": w2["k"],
+                                "queries_per_step": w2["q"], "steps": args.steps}
+                extra[key] = r2
+                if key == "cfg2":
+                    extra["cfg2 query-batch sweep"] = extra_numbers(ix2, w2["d"], w2["k"], dev, peaks)
+                del ix2
+            except Exception as exc:  # noqa: BLE001 - secondary numbers must not lose the headline line
+                extra[key] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
         try:
             # the shape of the index the reference ships: Qwen3-Embedding vectors (d = 1024) stored as
             # fp32 (extract/index.py:59-71), ~400 k declarations; one query with faiss_k = 1000 is the
             # engine's own request, the 1024-query batch shows the d = 1024 scan variant's throughput
-            index = None  # release the cfg2 corpus
+            from lean_explore_b200 import GpuIndexFlatIP
+
             big = GpuIndexFlatIP.from_tensor(make_corpus_gpu(400_000, 1024, "float32", dev, seed=3))
-            out["extra"]["shipped index shape: 400k x 1024 fp32"] = extra_numbers(big, 1024, k, dev, peaks,
-                                                                                  sweep=((1, 1000), (64, 1000), (1024, 50)))
+            extra["shipped index shape: 400k x 1024 fp32"] = extra_numbers(big, 1024, 50, dev, peaks,
+                                                                           sweep=((1, 1000), (64, 1000), (1024, 50)))
             del big
         except Exception as exc:  # noqa: BLE001
-            out["extra"]["shipped index shape: 400k x 1024 fp32"] = {"error": repr(exc)}
+            extra["shipped index shape: 400k x 1024 fp32"] = {"error": repr(exc)}
         try:
-            out["extra"]["encoder"] = encoder_numbers(dev, cpu=not args.no_cpu_baseline)
-        except Exception as exc:  # noqa: BLE001 - secondary numbers must not lose the headline line
-            out["extra"]["encoder"] = {"error": repr(exc)}
-        try:
-            out["extra"]["qwen3"] = decoder_numbers(dev, cpu=not args.no_cpu_baseline)
+            extra["encoder"] = encoder_numbers(dev, cpu=not args.no_cpu_baseline)
         except Exception as exc:  # noqa: BLE001
-            out["extra"]["qwen3"] = {"error": repr(exc)}
+            extra["encoder"] = {"error": repr(exc)}
+        try:
+            extra["qwen3"] = decoder_numbers(dev, cpu=not args.no_cpu_baseline)
+        except Exception as exc:  # noqa: BLE001
+            extra["qwen3"] = {"error": repr(exc)}
 
     if world > 1:
         dist.barrier()
@@ -591,45 +758,56 @@ def decoder_numbers(dev, cpu: bool):
 
 def run_reference(args, wl, rank):
     """--impl reference: the reference's CPU path for this hot path (FAISS restatement from
-    oracle/) on the host cores, same config/metric; rank 0 only."""
+    oracle/) on the host cores, same config/metric; rank 0 only.  Fixed sizes (no calibration): every
+    step searches REF_Q queries; cfg4's 16M x 768 fp32 rows (49 GB) are represented by a 2M-row
+    slice and the QPS is scaled by 1/8 (brute force is linear in the rows), stated in `sample`."""
     if rank != 0:
         return
-    n, d, k, q = wl["n"], wl["d"], wl["k"], wl["q"]
-    if args.workload == "cfg4":
-        n = 2_000_000  # 16M x 768 fp32 does not fit host RAM: time a 2M slice, scale x1/8 below
+    try:
+        from threadpoolctl import threadpool_limits
+
+        threadpool_limits(limits=os.cpu_count() or 1)
+    except Exception:  # noqa: BLE001
+        pass
+    n, d, k = wl["n"], wl["d"], wl["k"]
+    scale_rows = 1.0
+    if n > 2_000_000:
+        scale_rows = 2_000_000 / n
+        n = 2_000_000
     rng = np.random.default_rng(0)
     c32 = np.empty((n, d), dtype=np.float32)
     for j0 in range(0, n, 65536):
         blk = rng.standard_normal((min(65536, n - j0), d), dtype=np.float32)
         blk /= np.linalg.norm(blk, axis=1, keepdims=True)
         c32[j0 : j0 + blk.shape[0]] = blk.astype(np.float16).astype(np.float32) if wl["dtype"] == "float16" else blk
-    cpu = CpuFlatIP(c32)
-    xs = np.random.default_rng(1).standard_normal((q, d), dtype=np.float32)
-    # bounded sample per step: as many queries as keep one step near 1 s
-    qps0, nq_s, dt0 = time_cpu(cpu, xs, k, 3.0)
-    nq_step = int(min(q, max(1, qps0 * 1.0)))
-    for _ in range(min(args.warmup, 3)):
-        cpu.search(xs[:nq_step], k)
-    steps = max(1, min(args.steps, int(120.0 / max(nq_step / qps0, 1e-3))))
+    nq_step = min(wl["q"], max(16, int(0.8e12 / (2.0 * n * d))))  # ~0.8 TFLOP of sgemm per step
+    xs = np.random.default_rng(1).standard_normal((nq_step, d), dtype=np.float32)
+    cpu = CpuFlatIP()
+    warm = min(args.warmup, 3)
+    t_w = time.perf_counter()
+    for _ in range(max(1, warm)):
+        cpu.search(c32, xs, k)
+    per_step = (time.perf_counter() - t_w) / max(1, warm)
+    steps = max(1, min(args.steps, int(150.0 / max(per_step, 1e-3))))  # whole run bounded to a few minutes
     t0 = time.perf_counter()
     for _ in range(steps):
-        cpu.search(xs[:nq_step], k)
+        cpu.search(c32, xs, k)
     dt = time.perf_counter() - t0
-    value = nq_step * steps / dt
-    if args.workload == "cfg4":
-        value /= 8.0
+    value = nq_step * steps / dt * scale_rows
     out = {
         "impl": "reference", "metric": "queries/sec top-50 over Nxd corpus" if k == 50 else f"queries/sec top-{k} over Nxd corpus",
-        "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 3),
-        "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "value": round(value, 1), "unit": "queries/s", "n_gpus": args.gpus, "steps": steps, "warmup": max(1, warm),
+        "ms_per_step": round(dt / steps * 1e3, 3), "higher_is_better": True,
+        "scaling": "strong" if args.workload == "cfg4" else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": wl["name"], "corpus_rows": wl["n"], "d": d, "corpus_dtype": wl["dtype"], "k": k,
                    "queries_per_step": nq_step, "normalize": True, "parallelism": "host CPU, all cores"},
         "cpu_baseline": {"value": round(value, 1), "unit": "queries/s", "cores": cpu.threads, "kind": "port",
                          "sample": "%d queries/step x %d steps over %d x %d fp32 rows%s; faiss-cpu is not installable "
                                    "offline, so this is its restatement (numpy/OpenBLAS sgemm + FAISS-style heaps)"
-                                   % (nq_step, steps, n, d, " (2M-row slice, QPS scaled 1/8)" if args.workload == "cfg4" else ""),
-                         "host_cpus": os.cpu_count()},
+                                   % (nq_step, steps, n, d,
+                                      " (2M-row slice of the 16M rows, QPS scaled by 1/8)" if scale_rows != 1.0 else ""),
+                         "host_cpus": os.cpu_count(), "affinity": len(os.sched_getaffinity(0))},
         "e2e": {"value": round(value, 1), "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

@@ -17,7 +17,12 @@
  *   - device memory handed in (corpus, weights) stays owned by the caller (a torch.Tensor on
  *     the Python side) and must outlive the handle.
  *   - `stream` is a cudaStream_t passed as void*; NULL is the legacy default stream.
- *   - handles may be used from any host thread; calls on one handle are serialised.
+ *   - handles may be used from any host thread and with any stream; calls on one handle are
+ *     serialised on the host (per-handle mutex) AND on the device (a search waits for the previous
+ *     search of the same handle, whatever stream that ran on, before it touches the shared
+ *     workspaces).  Every entry point makes the handle's device current for the duration of the
+ *     call and restores the caller's device, so executor threads that start on device 0 are fine;
+ *     call lxg_init once for every device that will hold a handle.
  *   - there is no CPU fallback: without an sm_100 device lxg_init fails.
  */
 #ifndef LXG_H_
@@ -84,9 +89,17 @@ int lxg_search(lxg_index* index, const float* x, int32_t nq, int32_t k, int norm
                float* D_out, int64_t* I_out, void* stream);
 
 /* Same, plus optional exact fp64 scores D64_out [nq, k] (device memory) used to merge
- * row-shards without losing the order of scores that collide in fp32. */
+ * row-shards without losing the order of scores that collide in fp32.  D64_out and I_out may be
+ * the two planes of one packed [2, nq, k] 8-byte buffer - the unit lxg_merge_topk_packed consumes
+ * after an all-gather. */
 int lxg_search_ex(lxg_index* index, const float* x, int32_t nq, int32_t k, int normalize,
                   float* D_out, int64_t* I_out, double* D64_out, void* stream);
+
+/* For callers of the asynchronous (device-output) form: waits for the last search on the handle
+ * and reports what a synchronous call would have returned - LXG_ETIES if a query had more exact
+ * ties with its k-th score than the exact path can hold, else LXG_OK; *uncertified (may be NULL)
+ * receives the number of queries the exact path re-did. */
+int lxg_index_sync(lxg_index* index, int32_t* uncertified);
 
 /* In-place faiss.normalize_L2(x) on a device or host [nq, d] float32 matrix
  * (src/lean_explore/search/engine.py:242) for callers that want the normalised queries. */
@@ -94,10 +107,18 @@ int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream);
 
 /* Merge step of a row-sharded index: Dg/Ig are the all-gathered per-shard results
  * [shards, nq, k] (exact fp64 scores, global ids, -1 padded; device memory); writes the global
- * top-k to D_out/I_out (device).  No reference analogue (the reference is single-process);
- * it is the exchange step of SURVEY.md section 8(e). */
+ * top-k to D_out/I_out (device).  Every per-shard list must be ordered best first (score
+ * descending, ties by ascending id, padding last) - what lxg_search_ex writes.  No reference
+ * analogue (the reference is single-process); it is the exchange step of SURVEY.md section 8(e). */
 int lxg_merge_topk(const double* Dg, const int64_t* Ig, int32_t nq, int32_t k, int32_t shards,
                    float* D_out, int64_t* I_out, void* stream);
+
+/* Same merge, reading the all-gather buffer in place: `gathered` is [shards][2][nq][k] 8-byte
+ * words, plane 0 of a shard = the bits of its fp64 scores (lxg_search_ex's D64_out), plane 1 =
+ * its int64 ids (I_out) - each rank contributes one contiguous [2, nq, k] block, so the exchange
+ * is exactly one all-gather with no repacking on either side. */
+int lxg_merge_topk_packed(const int64_t* gathered, int32_t nq, int32_t k, int32_t shards,
+                          float* D_out, int64_t* I_out, void* stream);
 
 /* Counters of the last lxg_search on this handle (tests, bench.py). */
 typedef struct lxg_search_stats {

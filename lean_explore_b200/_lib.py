@@ -87,6 +87,8 @@ SIGNATURES = {
     "lxg_normalize_l2": (c_int, [c_void_p, c_int32, c_int32, c_void_p]),
     "lxg_merge_topk": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p,
                                c_void_p]),
+    "lxg_merge_topk_packed": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "lxg_index_sync": (c_int, [c_void_p, POINTER(c_int32)]),
     "lxg_index_last_stats": (c_int, [c_void_p, POINTER(SearchStats)]),
     "lxg_index_set_timing": (c_int, [c_void_p, c_int]),
     "lxg_index_get_timing": (c_int, [c_void_p, POINTER(Timing)]),
@@ -108,7 +110,7 @@ SIGNATURES = {
 
 _lock = threading.Lock()
 _lib = None
-_inited_device = None
+_inited_devices: set[int] = set()
 
 
 def load() -> ctypes.CDLL:
@@ -138,9 +140,16 @@ def check(rc: int) -> None:
 
 def init(device: int = 0) -> ctypes.CDLL:
     """Load the library and bring up `device` (must be an sm_100 GPU)."""
-    global _inited_device
     lib = load()
-    if _inited_device != device:
+    if device not in _inited_devices:
+        # lxg_init makes `device` current on the calling thread; every later entry point switches to
+        # its handle's device by itself, so restore what the caller (torch) had selected
+        import torch
+
+        prev = torch.cuda.current_device() if torch.cuda.is_available() else None
         check(lib.lxg_init(device))
-        _inited_device = device
+        if prev is not None and prev != device:
+            torch.cuda.set_device(prev)
+        with _lock:
+            _inited_devices.add(device)
     return lib

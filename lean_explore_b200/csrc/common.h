@@ -9,7 +9,31 @@ namespace lxg {
 // Records `msg` as the calling thread's last error and returns `code`.
 int set_error(int code, const std::string& msg);
 bool is_device_ptr(const void* p);
+// SM count of the calling thread's current device (filled by lxg_init for every device it brought up).
 int num_sms();
+// Ordinal of the device that owns device pointer `p`, or -1 (host / unknown memory).
+int device_of_ptr(const void* p);
+// Raises the dynamic shared-memory limit of kernel `func` ON THE CURRENT DEVICE to at least `bytes`.
+// The attribute is per device and the cache behind this is per (device, kernel) and thread safe -
+// handles on different GPUs of one process and concurrent host threads do not trip over each other.
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
+
+// Every entry point that takes a handle makes the handle's device current for the duration of the
+// call (worker threads of an executor start on device 0) and restores the caller's device on exit.
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int device) {
+    if (device >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != device) {
+      if (cudaSetDevice(device) == cudaSuccess) changed = true;
+    }
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
 // cuTensorMapEncodeTiled resolved through the runtime by lxg_init (no link-time libcuda dependency).
 bool encode_tensor_map_ready();
 CUresult encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base,

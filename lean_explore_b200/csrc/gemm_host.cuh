@@ -41,21 +41,17 @@ template <int EPI>
 inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st, bool pdl = false) {
   // more than one row tile and N a multiple of 256: 256 x 256 tiles on CTA pairs
   if (gp.m > kGemmBM && gp.n % kPairBN == 0 && gemm_pairs_enabled()) {
-    static bool pair_attr_set = false;
-    if (!pair_attr_set) {
-      cudaError_t e = cudaFuncSetAttribute(gemm_pair_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmem);
+    {
+      cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_pair_kernel<EPI>), kPairSmem);
       if (e != cudaSuccess) return e;
-      pair_attr_set = true;
     }
     const int tiles = ((gp.m + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (gp.n / kPairBN);
     const int clusters = std::min(tiles, std::max(1, lxg::num_sms() / 2));
     return lxg_launch(gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(kPairThreads), kPairSmem, st, pdl, a, w, gp);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<EPI>), kGemmSmem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   const int tiles = ((gp.m + kGemmBM - 1) / kGemmBM) * (gp.n / kGemmBN) * std::max(1, gp.ksplit);
   return lxg_launch(gemm_tc_kernel<EPI>, dim3(std::min(tiles, std::max(1, lxg::num_sms()))), dim3(kGemmThreads), kGemmSmem, st, pdl, a, w, gp);

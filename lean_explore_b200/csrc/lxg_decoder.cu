@@ -21,6 +21,7 @@
 using namespace lxg;
 
 struct lxg_decoder {
+  int device = 0;  // the GPU that holds the weights; made current by every entry point
   lxg_qwen3_weights w{};
   std::vector<lxg_qwen3_layer> layers;
   std::mutex mu;
@@ -128,11 +129,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   const int hgroup = tokens >= 2048 ? 4 : 1;  // heads per RoPE warp (cos / sin are evaluated once per warp)
   const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
   const dim3 attn_grid((s + kCausalRows - 1) / kCausalRows, heads, b);
-  static bool attn_attr_set = false;
-  if (!attn_attr_set) {
-    LXG_CUDA(cudaFuncSetAttribute(attention_causal_kernel<kHeadDim>, cudaFuncAttributeMaxDynamicSharedMemorySize, kCausalSmem));
-    attn_attr_set = true;
-  }
+  LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_causal_kernel<kHeadDim>), kCausalSmem));
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     // input_layernorm (layer 0: fused with the embed_tokens gather)
@@ -219,6 +216,7 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
     if (tt < 0 || tt >= e->w.vocab || tf < 0 || tf >= e->w.vocab) return set_error(LXG_EINVAL, "true/false token id outside the vocabulary");
   }
   if (b == 0) return LXG_OK;
+  DeviceGuard guard(e->device);
   std::lock_guard<std::mutex> lock(e->mu);
   cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
   const long long tokens_ll = static_cast<long long>(b) * s;
@@ -382,7 +380,11 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   for (const void* p : globals)
     if (!p || !is_device_ptr(p)) return set_error(LXG_EINVAL, "tok_emb / final_norm / inv_freq must be device memory");
   if (w->lm_head && !is_device_ptr(w->lm_head)) return set_error(LXG_EINVAL, "lm_head must be device memory");
+  const int device = device_of_ptr(w->tok_emb);
+  DeviceGuard guard(device);
+  if (lxg::num_sms() == 0) return set_error(LXG_EINVAL, "lxg_init has not been called for the device that holds the weights");
   lxg_decoder* e = new lxg_decoder();
+  e->device = device;
   e->w = *w;
   e->layers.assign(w->layer, w->layer + w->layers);
   e->w.layer = e->layers.data();
@@ -416,6 +418,7 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
 
 int lxg_decoder_destroy(lxg_decoder* e) {
   if (!e) return LXG_OK;
+  DeviceGuard guard(e->device);
   free_ws(e);
   cudaFree(e->out_buf);
   cudaFree(e->cu);

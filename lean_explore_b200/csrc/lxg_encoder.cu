@@ -18,6 +18,7 @@
 using namespace lxg;
 
 struct lxg_encoder {
+  int device = 0;  // the GPU that holds the weights; made current by every entry point
   lxg_bert_weights w{};
   std::vector<lxg_bert_layer> layers;
   std::mutex mu;
@@ -122,17 +123,13 @@ int launch_forward(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
       : static_cast<size_t>(2) * s * (dh + 2) * sizeof(__half) + static_cast<size_t>(s) * sizeof(float) +
             static_cast<size_t>(kAttnThreads / 32) * s * sizeof(float);
   if (attn_smem > 200 * 1024) return set_error(LXG_EUNSUPPORTED, "sequence too long for the attention kernel's shared memory");
-  static size_t attn_attr[3] = {48 * 1024, 48 * 1024, 48 * 1024};
   const int attn_which = !attn_mma ? 0 : (dh == 32 ? 1 : 2);
-  if (attn_smem > attn_attr[attn_which]) {
-    if (attn_which == 0)
-      LXG_CUDA(cudaFuncSetAttribute(attention_scalar_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
-    else if (attn_which == 1)
-      LXG_CUDA(cudaFuncSetAttribute(attention_mma_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
-    else
-      LXG_CUDA(cudaFuncSetAttribute(attention_mma_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(attn_smem)));
-    attn_attr[attn_which] = attn_smem;
-  }
+  if (attn_which == 0)
+    LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_scalar_kernel), attn_smem));
+  else if (attn_which == 1)
+    LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_mma_kernel<32>), attn_smem));
+  else
+    LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_mma_kernel<64>), attn_smem));
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_bert_layer& L = e->layers[l];
     GemmParams gp{};
@@ -201,7 +198,12 @@ int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w) {
   if (dh > 64 || dh % 2 != 0) return set_error(LXG_EUNSUPPORTED, "encoder geometry: head size must be even and <= 64");
   if (!w->word_emb || !w->pos_emb || !w->type_emb || !w->emb_ln_g || !w->emb_ln_b)
     return set_error(LXG_EINVAL, "embedding weights are NULL");
+  const int device = device_of_ptr(w->word_emb);
+  if (device < 0) return set_error(LXG_EINVAL, "embedding weights are not device memory");
+  DeviceGuard guard(device);
+  if (lxg::num_sms() == 0) return set_error(LXG_EINVAL, "lxg_init has not been called for the device that holds the weights");
   lxg_encoder* e = new lxg_encoder();
+  e->device = device;
   e->w = *w;
   e->layers.assign(w->layer, w->layer + w->layers);
   e->w.layer = e->layers.data();
@@ -231,6 +233,7 @@ int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w) {
 
 int lxg_encoder_destroy(lxg_encoder* e) {
   if (!e) return LXG_OK;
+  DeviceGuard guard(e->device);
   free_ws(e);
   if (e->own) cudaStreamDestroy(e->own);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
@@ -248,6 +251,7 @@ int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t 
   if (s > e->w.max_pos) return set_error(LXG_EINVAL, "sequence longer than the position table");
   if (pool != LXG_POOL_MEAN && pool != LXG_POOL_CLS) return set_error(LXG_EINVAL, "bad pooling mode");
   if (b == 0) return LXG_OK;
+  DeviceGuard guard(e->device);
   std::lock_guard<std::mutex> lock(e->mu);
   cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
   const long long tokens_ll = static_cast<long long>(b) * s;

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -27,8 +28,8 @@ int set_error(int code, const std::string& msg) {
 
 static std::mutex g_init_mutex;
 static bool g_inited = false;
-static int g_device = -1;
-static int g_num_sms = 0;
+constexpr int kMaxDevices = 64;
+static int g_sms[kMaxDevices] = {0};  // SM count of every device lxg_init has brought up (0 = not initialised)
 static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
 static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
 static bool g_asmem_768 = true;      // LXG_SCAN_ASMEM=0: 512 < d <= 768 falls back to 64-row tiles, all of A in tensor memory (A/B)
@@ -42,7 +43,33 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode_tiled = nullptr;
 
-int num_sms() { return g_num_sms; }
+int num_sms() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return g_sms[dev];
+}
+int device_of_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) ? a.device : -1;
+}
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+  if (bytes <= 48u * 1024u) return cudaSuccess;
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  static std::mutex mu;
+  static std::map<std::pair<int, const void*>, size_t> have;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& cur = have[std::make_pair(dev, func)];
+  if (bytes <= cur) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
 bool encode_tensor_map_ready() { return g_encode_tiled != nullptr; }
 CUresult encode_tensor_map(CUtensorMap* map, CUtensorMapDataType dt, cuuint32_t rank, void* base,
                            const cuuint64_t* gdim, const cuuint64_t* gstride, const cuuint32_t* box,
@@ -131,6 +158,11 @@ struct lxg_index {
   __half* scan = nullptr;  // fp16 rows the tensor cores stream (== cv.rows when it can alias)
   bool scan_owned = false;
   int scan_pitch = 0;      // elements
+  int device = 0;          // the GPU that holds the corpus; made current by every entry point
+  int sms = 0;
+  cudaEvent_t done_ev = nullptr;  // end of the last search on this handle: the next one (any stream, any
+  bool have_done = false;         // thread) waits for it before it touches the shared workspaces
+  int* last_flags = nullptr;      // device flag_count / overflow words of the last search
   int tile_rows = 0;       // N_T
   int num_kc = 0;
   int a_smem_chunks = 0;    // k-chunks of the query block the scan keeps in shared memory (kASm)
@@ -143,6 +175,9 @@ struct lxg_index {
   bool timing = false;
   std::vector<cudaEvent_t> ev_pool;   // 5 events per timed call
   size_t ev_used = 0;
+  ~lxg_index() {
+    if (done_ev) cudaEventDestroy(done_ev);
+  }
 };
 
 namespace {
@@ -228,7 +263,7 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     pl.slices = std::max(1, (pl.num_tiles + pl.tiles_per_slice - 1) / std::max(1, pl.tiles_per_slice));
     pl.lists = kGroups * pl.slices;
   };
-  slice_up(std::max(1, g_num_sms / pl.grid_x));
+  slice_up(std::max(1, ix->sms / pl.grid_x));
   // cross-list level: needs lists * r >= kp with r <= kTrack
   // with hundreds of lists (one or two query blocks) only every stride-th list publishes, so that a
   // refresh reads ~32 values per query - as long as that still leaves lists * 8 >= kp
@@ -268,13 +303,10 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
 
 template <int N_T, bool kPair, int kASm = 0>
 cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, cudaStream_t st) {
-  static bool attr_set = false;
   const int smem = (kASm == 0 ? kStageRing : kScanSmemMax) + 1024;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_topk_kernel<N_T, kPair, kASm>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&scan_topk_kernel<N_T, kPair, kASm>), smem);
     if (e != cudaSuccess) return e;
-    attr_set = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid_x, sp.slices, 1);
@@ -293,12 +325,9 @@ cudaError_t launch_scan(const lxg_index* ix, const ScanParams& sp, int grid_x, c
 
 template <int THREADS>
 cudaError_t launch_merge(int nq, size_t smem, const MergeParams& mp, const CorpusView& cv, cudaStream_t st) {
-  static size_t attr = 0;
-  if (smem > attr) {
-    cudaError_t e = cudaFuncSetAttribute(merge_rescore_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         static_cast<int>(smem));
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&merge_rescore_kernel<THREADS>), smem);
     if (e != cudaSuccess) return e;
-    attr = smem;
   }
   merge_rescore_kernel<THREADS><<<nq, THREADS, smem, st>>>(mp, cv);
   return cudaGetLastError();
@@ -308,7 +337,7 @@ cudaError_t launch_merge(int nq, size_t smem, const MergeParams& mp, const Corpu
 
 extern "C" {
 
-int lxg_abi_version(void) { return 2; }
+int lxg_abi_version(void) { return 3; }
 
 const char* lxg_last_error(void) { return g_last_error.c_str(); }
 
@@ -339,7 +368,8 @@ int lxg_init(int device) {
       return set_error(LXG_ECUDA, "driver does not export cuTensorMapEncodeTiled");
     g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  g_num_sms = prop.multiProcessorCount;
+  if (device >= kMaxDevices) return set_error(LXG_EINVAL, "device index out of range");
+  g_sms[device] = prop.multiProcessorCount;
   const char* fs = std::getenv("LXG_SCAN_SINGLE");
   g_force_single = fs && fs[0] == '1';
   const char* zc = std::getenv("LXG_ZERO_COPY");
@@ -354,7 +384,6 @@ int lxg_init(int device) {
   g_no_level = nl && nl[0] == '1';
   const char* pm = std::getenv("LXG_SCAN_PERF_MODE");
   g_perf_mode = pm ? std::atoi(pm) : 0;
-  g_device = device;
   g_inited = true;
   return LXG_OK;
 }
@@ -379,7 +408,19 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
                      "d > 1024: the fp16 query block must fit tensor memory + shared memory next to the corpus pipeline");
   if (n > 0 && (!corpus_dev || !is_device_ptr(corpus_dev)))
     return set_error(LXG_EINVAL, "corpus_dev must be device memory");
+  // the index lives on the device that holds the corpus (an empty index: on the current device)
+  int device = n > 0 ? device_of_ptr(corpus_dev) : -1;
+  if (device < 0 && cudaGetDevice(&device) != cudaSuccess) return set_error(LXG_ECUDA, "cudaGetDevice failed");
+  if (device >= kMaxDevices || g_sms[device] == 0)
+    return set_error(LXG_EINVAL, "lxg_init has not been called for device " + std::to_string(device) + " (the one that holds the corpus)");
+  DeviceGuard guard(device);
   lxg_index* ix = new lxg_index();
+  ix->device = device;
+  ix->sms = g_sms[device];
+  if (cudaEventCreateWithFlags(&ix->done_ev, cudaEventDisableTiming) != cudaSuccess) {
+    delete ix;
+    return set_error(LXG_ECUDA, "cudaEventCreate failed");
+  }
   ix->cv.rows = corpus_dev;
   ix->cv.pitch = d;
   ix->cv.dtype = dtype;
@@ -399,7 +440,7 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
   const bool alias = dtype == LXG_F16 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(corpus_dev) % 16 == 0);
   if (n > 0) {
     // statistics for the certificate: max row norm, max |element|
-    const int blocks = std::min<int64_t>(4 * g_num_sms, (n + 7) / 8);
+    const int blocks = std::min<int64_t>(4 * ix->sms, (n + 7) / 8);
     DevBuf tmp;
     cudaError_t e = tmp.reserve(blocks * (sizeof(double) + sizeof(float)));
     if (e != cudaSuccess) {
@@ -444,7 +485,7 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
         return set_error(LXG_ECUDA, std::string("scan copy: ") + cudaGetErrorString(e));
       }
       ix->scan_owned = true;
-      make_scan_copy_kernel<<<8 * g_num_sms, 256>>>(corpus_dev, d, dtype, n, d, ix->scan,
+      make_scan_copy_kernel<<<8 * ix->sms, 256>>>(corpus_dev, d, dtype, n, d, ix->scan,
                                                     ix->scan_pitch, scale);
       e = cudaDeviceSynchronize();
       if (e != cudaSuccess) {
@@ -473,6 +514,8 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
 
 int lxg_index_destroy(lxg_index* ix) {
   if (!ix) return LXG_OK;
+  DeviceGuard guard(ix->device);
+  if (ix->have_done) cudaEventSynchronize(ix->done_ev);
   if (ix->scan_owned && ix->scan) cudaFree(ix->scan);
   for (cudaEvent_t e : ix->ev_pool) cudaEventDestroy(e);
   ix->ws_cand.release();
@@ -498,6 +541,7 @@ int lxg_index_set_timing(lxg_index* ix, int enable) {
 
 int lxg_index_get_timing(lxg_index* ix, lxg_timing* out) {
   if (!ix || !out) return set_error(LXG_EINVAL, "NULL argument");
+  DeviceGuard guard(ix->device);
   std::lock_guard<std::mutex> lock(ix->mu);
   *out = lxg_timing{};
   for (size_t i = 0; i + 5 <= ix->ev_used; i += 5) {
@@ -562,6 +606,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   uint8_t* sm = reinterpret_cast<uint8_t*>(ix->ws_small.p);
   int* flag_count = reinterpret_cast<int*>(sm + o_flags);
   int* overflow = flag_count + 1;
+  ix->last_flags = flag_count;
   float* xn = reinterpret_cast<float*>(ix->ws_x.p);
   __half* xh = reinterpret_cast<__half*>(reinterpret_cast<uint8_t*>(ix->ws_x.p) + xn_bytes);
   float* qscale = dbg_qscale ? dbg_qscale : reinterpret_cast<float*>(sm + o_qscale);
@@ -711,7 +756,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   ep.nq = nq;
   ep.k = k;
   ep.nflag_max = nflag_max;
-  exact_collect_kernel<<<2 * g_num_sms, 256, d * sizeof(float), st>>>(ep, ix->cv);
+  exact_collect_kernel<<<2 * ix->sms, 256, d * sizeof(float), st>>>(ep, ix->cv);
   LXG_CUDA(cudaGetLastError());
   exact_finalize_kernel<<<nflag_max, 256, 0, st>>>(ep, ix->cv);
   LXG_CUDA(cudaGetLastError());
@@ -742,9 +787,21 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   if (k > 2048) return set_error(LXG_EUNSUPPORTED, "k > 2048");
   if (nq == 0) return LXG_OK;
   if (!x) return set_error(LXG_EINVAL, "x is NULL");
+  DeviceGuard guard(ix->device);
   std::lock_guard<std::mutex> lock(ix->mu);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int d = ix->cv.d;
+  // Searches on one handle share its workspaces (candidate lists, counters, staging): order this one
+  // behind the previous one ON THE DEVICE, whatever stream / host thread that was issued from (with
+  // device outputs a call returns before its kernels have run).
+  if (ix->have_done) LXG_CUDA(cudaStreamWaitEvent(st, ix->done_ev, 0));
+  struct RecordDone {
+    lxg_index* ix;
+    cudaStream_t st;
+    ~RecordDone() {
+      if (cudaEventRecord(ix->done_ev, st) == cudaSuccess) ix->have_done = true;
+    }
+  } record_done{ix, st};
   const bool x_dev = is_device_ptr(x);
   const bool out_dev = is_device_ptr(D_out);
   if (out_dev != is_device_ptr(I_out))
@@ -841,10 +898,29 @@ int lxg_debug_scores(lxg_index* ix, const float* x_dev, int32_t nq, int normaliz
                      float* qscale_dev, float* scan_scale_host, void* stream) {
   if (!ix || !x_dev || !scores_dev || !qscale_dev) return set_error(LXG_EINVAL, "NULL argument");
   if (nq <= 0 || nq > 148 * kQueryBlock) return set_error(LXG_EINVAL, "nq out of range");
+  DeviceGuard guard(ix->device);
   std::lock_guard<std::mutex> lock(ix->mu);
   if (scan_scale_host) *scan_scale_host = ix->cv.scan_scale;
-  return search_device(ix, x_dev, nq, 1, normalize, nullptr, nullptr, nullptr, scores_dev, qscale_dev,
-                       reinterpret_cast<cudaStream_t>(stream), false);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ix->have_done) LXG_CUDA(cudaStreamWaitEvent(st, ix->done_ev, 0));
+  const int rc = search_device(ix, x_dev, nq, 1, normalize, nullptr, nullptr, nullptr, scores_dev, qscale_dev, st, false);
+  if (cudaEventRecord(ix->done_ev, st) == cudaSuccess) ix->have_done = true;
+  return rc;
+}
+
+int lxg_index_sync(lxg_index* ix, int32_t* uncertified) {
+  if (!ix) return set_error(LXG_EINVAL, "NULL argument");
+  DeviceGuard guard(ix->device);
+  std::lock_guard<std::mutex> lock(ix->mu);
+  if (uncertified) *uncertified = 0;
+  if (!ix->have_done || !ix->last_flags) return LXG_OK;
+  LXG_CUDA(cudaEventSynchronize(ix->done_ev));
+  int h[2] = {0, 0};
+  LXG_CUDA(cudaMemcpy(h, ix->last_flags, sizeof(h), cudaMemcpyDeviceToHost));
+  ix->stats.uncertified = h[0];
+  if (uncertified) *uncertified = h[0];
+  if (h[1]) return set_error(LXG_ETIES, "more than 16384 corpus rows tie with the k-th best score of a query");
+  return LXG_OK;
 }
 
 int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream) {
@@ -852,22 +928,56 @@ int lxg_normalize_l2(float* x, int32_t nq, int32_t d, void* stream) {
   if (nq == 0) return LXG_OK;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const size_t bytes = static_cast<size_t>(nq) * d * sizeof(float);
-  if (is_device_ptr(x)) {
+  const int dev = device_of_ptr(x);
+  if (dev >= 0) {
+    DeviceGuard guard(dev);
     normalize_l2_kernel<<<(nq + 7) / 8, 256, 0, st>>>(x, nq, d);
     LXG_CUDA(cudaGetLastError());
     return LXG_OK;
   }
-  float* tmp = nullptr;
-  LXG_CUDA(cudaMalloc(&tmp, bytes));
-  cudaError_t e = cudaMemcpyAsync(tmp, x, bytes, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) {
-    normalize_l2_kernel<<<(nq + 7) / 8, 256, 0, st>>>(tmp, nq, d);
-    e = cudaGetLastError();
+  // Host array (the reference's own call: one [1, d] query per request, engine.py:242).  Page-locked
+  // memory is normalised in place through its device alias; pageable memory goes through a device
+  // scratch buffer that is kept per device (no allocation on the request path).
+  if (void* alias = g_zero_copy ? mapped_host_alias(x) : nullptr) {
+    normalize_l2_kernel<<<(nq + 7) / 8, 256, 0, st>>>(reinterpret_cast<float*>(alias), nq, d);
+    LXG_CUDA(cudaGetLastError());
+    LXG_CUDA(cudaStreamSynchronize(st));
+    return LXG_OK;
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(x, tmp, bytes, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(tmp);
-  LXG_CUDA(e);
+  int cur = 0;
+  LXG_CUDA(cudaGetDevice(&cur));
+  if (cur < 0 || cur >= kMaxDevices) return set_error(LXG_EINVAL, "device index out of range");
+  static std::mutex mu;
+  static DevBuf scratch[kMaxDevices];
+  std::lock_guard<std::mutex> lock(mu);
+  LXG_CUDA(scratch[cur].reserve(bytes));
+  float* tmp = reinterpret_cast<float*>(scratch[cur].p);
+  LXG_CUDA(cudaMemcpyAsync(tmp, x, bytes, cudaMemcpyHostToDevice, st));
+  normalize_l2_kernel<<<(nq + 7) / 8, 256, 0, st>>>(tmp, nq, d);
+  LXG_CUDA(cudaGetLastError());
+  LXG_CUDA(cudaMemcpyAsync(x, tmp, bytes, cudaMemcpyDeviceToHost, st));
+  LXG_CUDA(cudaStreamSynchronize(st));
+  return LXG_OK;
+}
+
+static int merge_shards(const double* dg, const long long* ig, long long shard_stride, int nq, int k, int shards,
+                        float* D_out, int64_t* I_out, cudaStream_t st) {
+  const int dev = device_of_ptr(D_out);
+  if (dev < 0 || device_of_ptr(dg) != dev || device_of_ptr(ig) != dev || device_of_ptr(I_out) != dev)
+    return set_error(LXG_EINVAL, "the gathered candidates and the outputs must be memory of one device");
+  DeviceGuard guard(dev);
+  const int total = shards * k;
+  const int threads = std::min(256, (total + 31) / 32 * 32);
+  const size_t smem = static_cast<size_t>(total) * 16;
+  if (smem <= 160u * 1024u) {
+    LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&merge_shards_kernel<true>), smem));
+    merge_shards_kernel<true><<<nq, threads, smem, st>>>(dg, ig, shard_stride, nq, k, shards, D_out,
+                                                          reinterpret_cast<long long*>(I_out));
+  } else {
+    merge_shards_kernel<false><<<nq, threads, 0, st>>>(dg, ig, shard_stride, nq, k, shards, D_out,
+                                                        reinterpret_cast<long long*>(I_out));
+  }
+  LXG_CUDA(cudaGetLastError());
   return LXG_OK;
 }
 
@@ -876,12 +986,18 @@ int lxg_merge_topk(const double* Dg, const int64_t* Ig, int32_t nq, int32_t k, i
   if (!Dg || !Ig || !D_out || !I_out) return set_error(LXG_EINVAL, "NULL argument");
   if (nq < 0 || k <= 0 || shards <= 0) return set_error(LXG_EINVAL, "bad nq / k / shards");
   if (nq == 0) return LXG_OK;
-  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-  const int warps = 8;
-  merge_shards_kernel<<<(nq + warps - 1) / warps, warps * 32, 0, st>>>(
-      Dg, reinterpret_cast<const long long*>(Ig), nq, k, shards, D_out, reinterpret_cast<long long*>(I_out));
-  LXG_CUDA(cudaGetLastError());
-  return LXG_OK;
+  return merge_shards(Dg, reinterpret_cast<const long long*>(Ig), static_cast<long long>(nq) * k, nq, k, shards, D_out,
+                      I_out, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int lxg_merge_topk_packed(const int64_t* gathered, int32_t nq, int32_t k, int32_t shards, float* D_out,
+                          int64_t* I_out, void* stream) {
+  if (!gathered || !D_out || !I_out) return set_error(LXG_EINVAL, "NULL argument");
+  if (nq < 0 || k <= 0 || shards <= 0) return set_error(LXG_EINVAL, "bad nq / k / shards");
+  if (nq == 0) return LXG_OK;
+  const long long plane = static_cast<long long>(nq) * k;
+  return merge_shards(reinterpret_cast<const double*>(gathered), reinterpret_cast<const long long*>(gathered) + plane,
+                      2 * plane, nq, k, shards, D_out, I_out, reinterpret_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -537,42 +537,68 @@ __global__ void __launch_bounds__(256) exact_finalize_kernel(const ExactParams p
 }
 
 // ---------------------------------------------------------------------------------------
-// Row-sharded indexes: merge `shards` per-shard results ([shards, nq, k], exact fp64 scores +
-// global int64 ids, as all-gathered over NCCL) into the global top-k.  One warp per query.
+// Row-sharded indexes: merge `shards` per-shard results (exact fp64 scores + global int64 ids, as
+// all-gathered over NCCL) into the global top-k.  Shard s's [nq, k] planes start at
+// dg + s * shard_stride and ig + s * shard_stride (elements), so both the legacy [shards, nq, k]
+// pair of arrays and the packed all-gather buffer [shards][2][nq][k] are read in place.
+// One CTA per query, one thread per candidate.  Every per-shard list is ordered best first
+// ((score desc, id asc), -1 padding at the end - what lxg_search_ex writes), so a candidate's
+// global rank is its position in its own list plus, for every other shard, the number of entries
+// that beat it: one binary search per (candidate, other shard) over shared memory (kSmem) or,
+// for pools beyond the shared-memory budget, over the gathered buffer itself (L2).
+template <bool kSmem>
 __global__ void __launch_bounds__(256)
-merge_shards_kernel(const double* __restrict__ dg, const long long* __restrict__ ig, int nq, int k,
-                    int shards, float* __restrict__ out_d, long long* __restrict__ out_i) {
-  const int q = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (q >= nq) return;
+merge_shards_kernel(const double* __restrict__ dg, const long long* __restrict__ ig, long long shard_stride,
+                    int nq, int k, int shards, float* __restrict__ out_d, long long* __restrict__ out_i) {
+  extern __shared__ __align__(16) uint8_t msh[];
+  __shared__ int s_valid;
+  const int q = blockIdx.x;
+  const int tid = threadIdx.x;
   const int total = shards * k;
-  for (int j = lane; j < total; j += 32) {
-    const int s = j / k, r = j % k;
-    const size_t src = (static_cast<size_t>(s) * nq + q) * k + r;
-    const long long id = ig[src];
-    if (id < 0) continue;
-    const double sc = dg[src];
-    int rank = 0;
-    for (int u = 0; u < total; ++u) {
-      const size_t us = (static_cast<size_t>(u / k) * nq + q) * k + (u % k);
-      const long long uid = ig[us];
-      if (uid < 0) continue;
-      const double usc = dg[us];
-      rank += (usc > sc || (usc == sc && uid < id)) ? 1 : 0;
-    }
-    if (rank < k) {
-      out_d[static_cast<size_t>(q) * k + rank] = static_cast<float>(sc);
-      out_i[static_cast<size_t>(q) * k + rank] = id;
+  double* sd = reinterpret_cast<double*>(msh);
+  long long* si = reinterpret_cast<long long*>(sd + (kSmem ? total : 0));
+  const size_t qoff = static_cast<size_t>(q) * k;
+  if (tid == 0) s_valid = 0;
+  if (kSmem) {
+    for (int j = tid; j < total; j += blockDim.x) {
+      const size_t src = static_cast<size_t>(j / k) * shard_stride + qoff + (j % k);
+      sd[j] = dg[src];
+      si[j] = ig[src];
     }
   }
-  // padding: count valid entries
+  __syncthreads();
+  auto score_at = [&](int s, int r) { return kSmem ? sd[s * k + r] : dg[static_cast<size_t>(s) * shard_stride + qoff + r]; };
+  auto id_at = [&](int s, int r) { return kSmem ? si[s * k + r] : ig[static_cast<size_t>(s) * shard_stride + qoff + r]; };
   int valid = 0;
-  for (int j = lane; j < total; j += 32)
-    valid += (ig[(static_cast<size_t>(j / k) * nq + q) * k + (j % k)] >= 0) ? 1 : 0;
+  for (int j = tid; j < total; j += blockDim.x) {
+    const int s = j / k, r = j % k;
+    const long long id = id_at(s, r);
+    if (id < 0) continue;
+    ++valid;
+    const double sc = score_at(s, r);
+    int rank = r;
+    for (int u = 0; u < shards; ++u) {
+      if (u == s) continue;
+      int lo = 0, hi = k;  // first entry of list u that does not beat (sc, id)
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const long long uid = id_at(u, mid);
+        const double usc = score_at(u, mid);
+        if (uid >= 0 && (usc > sc || (usc == sc && uid < id))) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_d[qoff + rank] = static_cast<float>(sc);
+      out_i[qoff + rank] = id;
+    }
+  }
   valid = __reduce_add_sync(0xffffffffu, valid);
-  for (int r = valid + lane; r < k; r += 32) {
-    out_d[static_cast<size_t>(q) * k + r] = -FLT_MAX;
-    out_i[static_cast<size_t>(q) * k + r] = -1;
+  if ((tid & 31) == 0 && valid) atomicAdd(&s_valid, valid);
+  __syncthreads();
+  for (int r = s_valid + tid; r < k; r += blockDim.x) {  // fewer than k rows in the whole corpus
+    out_d[qoff + r] = -FLT_MAX;
+    out_i[qoff + r] = -1;
   }
 }
 

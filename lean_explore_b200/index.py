@@ -138,9 +138,11 @@ class GpuIndexFlatIP:
     def search_torch(self, x: torch.Tensor, k: int, normalize: bool = False, out=None,
                      want_f64: bool = False):
         """Device-resident variant: x float32 CUDA [nq, d]; returns CUDA tensors (D, I[, D64]),
-        asynchronous on the current stream."""
+        asynchronous on the current stream (``sync()`` reports what a synchronous call would)."""
         if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.d:
             raise ValueError(f"search_torch expects a float32 CUDA tensor [nq, {self.d}]")
+        if k <= 0:
+            raise ValueError("k must be positive")
         x = x.contiguous()
         self._materialise()
         nq = x.shape[0]
@@ -154,6 +156,36 @@ class GpuIndexFlatIP:
                                            I.data_ptr(), D64.data_ptr() if want_f64 else None,
                                            _current_stream_ptr(self.device)))
         return (D, I, D64) if want_f64 else (D, I)
+
+    def search_packed(self, x: torch.Tensor, k: int, normalize: bool = False, packed: torch.Tensor | None = None,
+                      scratch_d: torch.Tensor | None = None) -> torch.Tensor:
+        """Row-shard form of ``search_torch``: the result lands in ONE contiguous int64 tensor
+        ``packed[2, nq, k]`` - plane 0 the bits of the exact fp64 scores, plane 1 the global ids -
+        which is exactly this rank's contribution to the all-gather (``lxg_merge_topk_packed``
+        reads the gathered buffer in place).  Asynchronous on the current stream."""
+        if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.shape[1] != self.d:
+            raise ValueError(f"search_packed expects a float32 CUDA tensor [nq, {self.d}]")
+        x = x.contiguous()
+        self._materialise()
+        nq = x.shape[0]
+        if packed is None:
+            packed = torch.empty((2, nq, k), dtype=torch.int64, device=x.device)
+        if scratch_d is None:
+            scratch_d = torch.empty((nq, k), dtype=torch.float32, device=x.device)
+        assert packed.is_contiguous() and packed.shape == (2, nq, k) and packed.dtype == torch.int64
+        _lib.check(self._lib.lxg_search_ex(self._handle, x.data_ptr(), nq, k, int(normalize), scratch_d.data_ptr(),
+                                           packed[1].data_ptr(), packed[0].data_ptr(),
+                                           _current_stream_ptr(self.device)))
+        return packed
+
+    def sync(self) -> int:
+        """Waits for the last (asynchronous) search on this index; raises ``LxgError`` (LXG_ETIES) if a
+        query had more exact ties with its k-th score than can be represented, and returns the
+        number of queries the exact path re-did."""
+        self._materialise()
+        n = ctypes.c_int32(0)
+        _lib.check(self._lib.lxg_index_sync(self._handle, ctypes.byref(n)))
+        return int(n.value)
 
     def last_stats(self) -> dict:
         st = _lib.SearchStats()

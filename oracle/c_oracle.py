@@ -26,6 +26,8 @@ def load() -> ctypes.CDLL:
     lib.lxo_heap_finish.argtypes = [sz, sz, vp, vp]
     lib.lxo_knn_inner_product_seq.argtypes = [vp, vp, sz, sz, sz, sz, vp, vp]
     lib.lxo_num_threads.restype = ctypes.c_int
+    lib.lxo_f64_topk_init.argtypes = [sz, sz, vp, vp]
+    lib.lxo_f64_topk_add_rows.argtypes = [sz, sz, sz, vp, vp, ctypes.c_int, sz, i64, vp, vp]
     return lib
 
 
@@ -60,3 +62,39 @@ def knn_inner_product_blas(x: np.ndarray, y: np.ndarray, k: int, block: int = 10
         lib.lxo_heap_add_block(nq, k, D.ctypes.data, I.ctypes.data, s.ctypes.data, s.shape[1], j0)
     lib.lxo_heap_finish(nq, k, D.ctypes.data, I.ctypes.data)
     return D, I
+
+
+class ExactTopK:
+    """Streaming exact-arithmetic ranking (``lxo_f64_topk_add_rows``): feed the corpus block by block
+    (fp16 or fp32 rows, ascending global row numbers), then ``result()`` gives what
+    ``faiss_flat.flat_ip_search_f64`` gives on the whole matrix - (D float64 [nq, k], I int64 [nq, k]),
+    best first, ``-FLT_MAX`` / ``-1`` padded."""
+
+    def __init__(self, x: np.ndarray, k: int):
+        self.lib = load()
+        self.x = np.ascontiguousarray(x, dtype=np.float32)
+        self.k = int(k)
+        nq = self.x.shape[0]
+        self.D = np.empty((nq, k), dtype=np.float64)
+        self.I = np.empty((nq, k), dtype=np.int64)
+        self.lib.lxo_f64_topk_init(nq, k, self.D.ctypes.data, self.I.ctypes.data)
+
+    def add(self, rows: np.ndarray, row0: int) -> None:
+        assert rows.dtype in (np.float16, np.float32) and rows.flags.c_contiguous and rows.shape[1] == self.x.shape[1]
+        self.lib.lxo_f64_topk_add_rows(self.x.shape[0], self.x.shape[1], self.k, self.x.ctypes.data, rows.ctypes.data,
+                                       int(rows.dtype == np.float16), rows.shape[0], int(row0), self.D.ctypes.data,
+                                       self.I.ctypes.data)
+
+    def merge(self, D: np.ndarray, I: np.ndarray) -> None:
+        """Fold another partial result (e.g. another row shard's) into this one."""
+        d = np.concatenate([self.D, D], axis=1)
+        i = np.concatenate([self.I, I], axis=1)
+        d = np.where(i < 0, -np.inf, d)
+        order = np.lexsort((i, -d), axis=1)[:, : self.k]
+        self.D = np.ascontiguousarray(np.take_along_axis(d, order, axis=1))
+        self.I = np.ascontiguousarray(np.take_along_axis(i, order, axis=1))
+
+    def result(self):
+        D = self.D.copy()
+        D[self.I < 0] = float(np.finfo(np.float32).min)
+        return D, self.I.copy()

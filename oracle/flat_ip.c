@@ -18,6 +18,7 @@
 #include <math.h>
 #include <stddef.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #ifdef _OPENMP
@@ -178,6 +179,98 @@ void lxo_knn_inner_product_seq(const float* x, const float* y, size_t d, size_t 
     }
     heap_reorder(k, simi, idxi);
   }
+}
+
+/* ---- exact-arithmetic ranking at full size (bench.py's ids_equal_exact, tests at the BASELINE
+ * sizes).  Not a FAISS routine: it is the DEFINITION the FAISS fp32 result approximates, the same
+ * one oracle/faiss_flat.py flat_ip_search_f64 evaluates with numpy, written so that a 16M x 768
+ * fp16 corpus can be streamed through it block by block in seconds:
+ *   x     [nq, d] fp32 queries as handed to index.search (engine.py:250; already normalised),
+ *   rows  [m, d]  corpus rows, IEEE fp16 bit patterns (rows_f16 != 0) or fp32, global ids row0..,
+ *   D/I   [nq, k] running result, best first, initialised by lxo_f64_topk_init.
+ * Products of an fp32 by an fp16/fp32 value are exact in fp64; the fp64 sum over d carries a
+ * relative error ~1e-13, nine orders of magnitude below the fp32 resolution of the scores.
+ * Order: score descending, ties by ascending row id (the tie rule of faiss_flat.py). */
+void lxo_f64_topk_init(size_t nq, size_t k, double* D, int64_t* I) {
+  for (size_t i = 0; i < nq * k; ++i) {
+    D[i] = -INFINITY;
+    I[i] = -1;
+  }
+}
+
+static inline int f64_better(double sa, int64_t ia, double sb, int64_t ib) {
+  if (ib < 0) return 1;
+  return sa > sb || (sa == sb && ia < ib);
+}
+
+static void f64_insert(size_t k, double* D, int64_t* I, double s, int64_t id) {
+  if (!f64_better(s, id, D[k - 1], I[k - 1])) return;
+  size_t j = k - 1;
+  while (j > 0 && f64_better(s, id, D[j - 1], I[j - 1])) {
+    D[j] = D[j - 1];
+    I[j] = I[j - 1];
+    --j;
+  }
+  D[j] = s;
+  I[j] = id;
+}
+
+void lxo_f64_topk_add_rows(size_t nq, size_t d, size_t k, const float* x, const void* rows, int rows_f16,
+                           size_t m, int64_t row0, double* D, int64_t* I) {
+  double* xd = (double*)malloc(nq * d * sizeof(double));
+  for (size_t i = 0; i < nq * d; ++i) xd[i] = (double)x[i];
+#pragma omp parallel
+  {
+    enum { R = 4 }; /* rows per pass over a query: each query element is loaded once per R products */
+    double* r = (double*)malloc(R * d * sizeof(double));
+    double* Dl = (double*)malloc(nq * k * sizeof(double));
+    int64_t* Il = (int64_t*)malloc(nq * k * sizeof(int64_t));
+    lxo_f64_topk_init(nq, k, Dl, Il);
+    const int64_t groups = ((int64_t)m + R - 1) / R;
+#pragma omp for schedule(static)
+    for (int64_t g = 0; g < groups; ++g) {
+      const int64_t j0 = g * R;
+      const int nr = (int)((int64_t)m - j0 < R ? (int64_t)m - j0 : R);
+      for (int u = 0; u < R; ++u) {
+        double* ru = r + (size_t)u * d;
+        if (u >= nr) {
+          for (size_t i = 0; i < d; ++i) ru[i] = 0.0;
+        } else if (rows_f16) {
+          const _Float16* src = (const _Float16*)rows + (size_t)(j0 + u) * d;
+          for (size_t i = 0; i < d; ++i) ru[i] = (double)src[i];
+        } else {
+          const float* src = (const float*)rows + (size_t)(j0 + u) * d;
+          for (size_t i = 0; i < d; ++i) ru[i] = (double)src[i];
+        }
+      }
+      const double *r0 = r, *r1 = r + d, *r2 = r + 2 * d, *r3 = r + 3 * d;
+      for (size_t q = 0; q < nq; ++q) {
+        const double* xq = xd + q * d;
+        double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma omp simd reduction(+ : a0, a1, a2, a3)
+        for (size_t i = 0; i < d; ++i) {
+          const double xv = xq[i];
+          a0 += r0[i] * xv;
+          a1 += r1[i] * xv;
+          a2 += r2[i] * xv;
+          a3 += r3[i] * xv;
+        }
+        const double acc[R] = {a0, a1, a2, a3};
+        for (int u = 0; u < nr; ++u)
+          if (acc[u] == acc[u]) f64_insert(k, Dl + q * k, Il + q * k, acc[u], row0 + j0 + u); /* NaN never enters */
+      }
+    }
+#pragma omp critical
+    {
+      for (size_t q = 0; q < nq; ++q)
+        for (size_t t = 0; t < k && Il[q * k + t] >= 0; ++t)
+          f64_insert(k, D + q * k, I + q * k, Dl[q * k + t], Il[q * k + t]);
+    }
+    free(r);
+    free(Dl);
+    free(Il);
+  }
+  free(xd);
 }
 
 int lxo_num_threads(void) {

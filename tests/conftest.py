@@ -17,6 +17,23 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (sm_100a); run with -m gpu on a B200")
 
 
+def pytest_collection_modifyitems(config, items):
+    """`gpu` tests skip (rather than fail inside lxg_init) on a box without a CUDA device, so a plain
+    `pytest tests` is green on the CPU-only build container too."""
+    try:
+        import torch
+
+        have = torch.cuda.is_available()
+    except Exception:  # noqa: BLE001
+        have = False
+    if have:
+        return
+    skip = pytest.mark.skip(reason="needs a CUDA device (sm_100a); run with -m gpu on a B200")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 def make_corpus(n, d, seed=0, dtype=np.float16):
     """BASELINE.md synthetic corpus: N(0,1) rows, L2-normalised in fp32, cast to `dtype`."""
     c = np.random.default_rng(seed).standard_normal((n, d), dtype=np.float32)

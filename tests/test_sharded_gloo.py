@@ -45,10 +45,12 @@ def _worker(rank, world, port, n, d, nq, k, out_dir):
                 ff.normalize_L2(xn)
             dd, ii = ff.flat_ip_search_f64(corpus[lo:hi], xn, kk)
             ii = np.where(ii >= 0, ii + lo, -1)
-            return torch.from_numpy(dd), torch.from_numpy(ii)
+            # this rank's contribution to the all-gather: [2, nq, k] 8-byte words (fp64 bits | ids)
+            return torch.from_numpy(np.stack([np.ascontiguousarray(dd).view(np.int64), ii]))
 
-        def merge(dg, ig, kk):
-            dd, ii = merge_topk_host(dg.numpy(), ig.numpy(), kk)
+        def merge(gathered, kk):
+            g = gathered.numpy()  # [world, 2, nq, k]
+            dd, ii = merge_topk_host(np.ascontiguousarray(g[:, 0]).view(np.float64), np.ascontiguousarray(g[:, 1]), kk)
             return torch.from_numpy(dd), torch.from_numpy(ii)
 
         eng = ShardedFlatIP(None, world, rank, local_search=local_search, merge=merge)
