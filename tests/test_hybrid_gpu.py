@@ -126,7 +126,7 @@ def test_config5_end_to_end_matches_oracle_pipeline(tmp_path, monkeypatch):
 
     # ---- GPU pipeline, everything loaded from disk the way the local backend would
     eng = hy.HybridSearchEngine.from_data_dir(data, embedding_client=GpuEmbeddingClient("emb", max_length=512),
-                                              reranker_client=GpuRerankerClient("rerank", max_length=512))
+                                              reranker_client=GpuRerankerClient("rerank", max_length=256))
     assert eng.semantic.faiss_informal_index.d == 512 and eng.semantic.faiss_informal_index.ntotal == 400
     queries = ["addition of natural numbers is commutative", "Nat.add_comm", "determinant of a product", "finite subcover compact"]
     got = [asyncio.run(eng.search(q, limit=10, faiss_k=200, rerank_top=20)) for q in queries]
