@@ -18,7 +18,7 @@ for step in "$@"; do
   case $kind in
     tests)
       args=${rest:-"tests -m gpu -x -q"}
-      timeout 1500 python -m pytest $args > $OUT/${TAG}_pytest_$i.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest_$i.log; tail -3 $OUT/${TAG}_pytest_$i.log ;;
+      timeout 1500 bash -c "python -m pytest $args" > $OUT/${TAG}_pytest_$i.log 2>&1; echo "pytest rc=$?" >> $OUT/${TAG}_pytest_$i.log; tail -3 $OUT/${TAG}_pytest_$i.log ;;
     bench)
       timeout 900 python bench.py $rest > $OUT/${TAG}_bench_$i.json 2> $OUT/${TAG}_bench_$i.err; echo "bench rc=$?"; head -c 600 $OUT/${TAG}_bench_$i.json; echo ;;
     ref)
@@ -35,7 +35,7 @@ for step in "$@"; do
       python scripts/ncu_summary.py $OUT/${TAG}_prof_$i.ncu-rep > $OUT/${TAG}_ncu_$i.txt 2>&1; tail -30 $OUT/${TAG}_ncu_$i.txt ;;
     san)
       tool=${rest%%:*}; a=${rest#*:}
-      timeout 1500 compute-sanitizer --tool $tool --error-exitcode 9 --log-file $OUT/${TAG}_san_${tool}_$i.log python -m pytest $a -x -q > $OUT/${TAG}_san_${tool}_$i.pytest.log 2>&1; echo "san $tool rc=$?"; tail -5 $OUT/${TAG}_san_${tool}_$i.log; tail -3 $OUT/${TAG}_san_${tool}_$i.pytest.log ;;
+      timeout ${SAN_TIMEOUT:-600} compute-sanitizer --tool $tool --target-processes all --error-exitcode 9 --log-file $OUT/${TAG}_san_${tool}_$i.log bash -c "python -m pytest $a -x -q" > $OUT/${TAG}_san_${tool}_$i.pytest.log 2>&1; echo "san $tool rc=$?"; tail -5 $OUT/${TAG}_san_${tool}_$i.log; tail -3 $OUT/${TAG}_san_${tool}_$i.pytest.log ;;
     py)
       timeout 1200 python $rest > $OUT/${TAG}_py_$i.log 2>&1; echo "py rc=$?"; tail -40 $OUT/${TAG}_py_$i.log ;;
     *) echo "unknown step $step" ;;
