@@ -183,6 +183,17 @@ typedef struct lxg_bert_weights {
 int lxg_encoder_create(lxg_encoder** out, const lxg_bert_weights* w);
 int lxg_encoder_destroy(lxg_encoder* enc);
 int lxg_encoder_last_launches(const lxg_encoder* enc); /* kernels launched by the last lxg_encode */
+/* Calls of at most 64 tokens - what EmbeddingClient.embed sends for a search query
+ * (search/engine.py:236) - run the whole forward as ONE cooperative kernel
+ * (csrc/fused_encoder.cuh) when the geometry allows it (head size 32 / 64, ffn a multiple of
+ * hidden); lxg_encoder_last_launches then reports 1.  enabled = 0 keeps this handle on the layered
+ * kernels (A/B measurements, tests); the environment variable LXG_FUSED=0 does so process-wide. */
+int lxg_encoder_set_fused(lxg_encoder* enc, int enabled);
+/* Tracing aid: after lxg_encoder_set_fused(enc, 2) every single-kernel call records, per CTA and
+ * phase (4 per layer + pooling), six %globaltimer stamps (ns) of its first thread: phase entered,
+ * phase barrier passed, operand staged, accumulator ready, epilogue done, arrived.  out receives
+ * grid x phases x 6 values (zero = the CTA had no job in that phase). */
+int lxg_encoder_read_trace(lxg_encoder* enc, uint64_t* out, int32_t capacity, int32_t* grid, int32_t* phases);
 /* ids/mask: [b, s] int32 token ids / attention mask (host or device); out: [b, H] float32
  * unit vectors (host or device).  pool = LXG_POOL_MEAN | LXG_POOL_CLS. */
 int lxg_encode(lxg_encoder* enc, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s,

@@ -98,6 +98,8 @@ SIGNATURES = {
     "lxg_encoder_create": (c_int, [POINTER(c_void_p), POINTER(BertWeights)]),
     "lxg_encoder_destroy": (c_int, [c_void_p]),
     "lxg_encoder_last_launches": (c_int, [c_void_p]),
+    "lxg_encoder_set_fused": (c_int, [c_void_p, c_int]),
+    "lxg_encoder_read_trace": (c_int, [c_void_p, c_void_p, c_int32, POINTER(c_int32), POINTER(c_int32)]),
     "lxg_encode": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int, c_void_p, c_void_p]),
     "lxg_decoder_create": (c_int, [POINTER(c_void_p), POINTER(Qwen3Weights)]),
     "lxg_decoder_destroy": (c_int, [c_void_p]),

@@ -24,6 +24,11 @@
 //          slabs in slice order (deterministic) + bias + residual -> pre-LN2 (fp32)
 //     LayerNorm needs whole rows, so every consumer CTA normalises the rows it loads itself (the rows
 //     are <= 64 x 1024 values; recomputing beats one more grid barrier).
+//   * Everything on the dependency chain is latency, not throughput, so the chain is kept short:
+//     parameters (gamma / beta / bias) and residual rows are fetched before the phase barrier / the
+//     accumulator is awaited; LayerNorm handles four rows per warp in lock step (the shuffle chains
+//     overlap); each k-block's four K = 16 MMAs go to four independent TMEM accumulators, summed by
+//     the epilogue (a chain of dependent N = 16 MMAs costs ~120 clocks per instruction).
 //   * Pooling (mean over unmasked tokens / CLS) + L2 normalise run in CTA 0 after the last phase.
 //
 // Numerics are those of the layered path: fp16 operands, fp32 accumulation / LayerNorm / softmax,
@@ -39,12 +44,13 @@
 namespace lxg {
 
 constexpr int kFusedMaxTokens = 64;
-constexpr int kFusedComputeWarps = 4;
+constexpr int kFusedComputeWarps = 8;
 constexpr int kFusedComputeThreads = kFusedComputeWarps * 32;
 constexpr int kFusedThreads = kFusedComputeThreads + 64;  // + TMA warp + MMA warp
 constexpr int kFusedSlotBytes = 128 * 64 * 2;             // one k-block of a 128-row weight tile
 constexpr int kFusedMaxSlots = 13;
-constexpr int kFusedTmemCols = 128;                       // two 64-column accumulators
+constexpr int kFusedAcc = 4;                              // independent accumulators per weight tile
+constexpr int kFusedTmemCols = 512;                       // 2 tiles x 4 accumulators x 64 token columns
 
 struct alignas(64) FusedLayer {
   CUtensorMap map_qkv;               // wqkv [3H, H], box = head_dim rows x 64 columns
@@ -72,6 +78,7 @@ struct FusedParams {
   int pool_cls;
   float* out;         // [B, H]
   int nslots;         // weight ring depth
+  unsigned long long* trace;  // optional [grid][4 L + 1][6] %globaltimer stamps of thread 0 (lxg_encoder_set_fused(enc, 2))
 };
 
 namespace fused {
@@ -89,6 +96,11 @@ __device__ __forceinline__ void grid_arrive(unsigned* ctr) {
   __threadfence();
   atomicAdd(ctr, 1u);
 }
+__device__ __forceinline__ unsigned long long timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void grid_wait(const unsigned* ctr, unsigned target) {
   unsigned spins = 0;
   while (ld_acquire(ctr) < target) {
@@ -103,86 +115,94 @@ __device__ __forceinline__ uint32_t operand_offset(int t, int f, int tpad) {
   return static_cast<uint32_t>(kb * tpad * 128 + t * 128 + (((c ^ (t & 7)) << 4) | ((f & 7) << 1)));
 }
 
-struct Row {
-  float4 v[8];
-};
-
-// LayerNorm-on-load.  Warp w normalises tokens w, w + 4, ... (two rows in flight); lane holds the
-// float4s lane, lane + 32, ...  Writes fp16 into the swizzled operand (or row-major when `plain`),
-// optionally also to global `hout` (the copy later residual adds read).
-template <bool EMB>
-__device__ __forceinline__ void load_row(const FusedParams& p, const float* src, int t, int lane, int nv, Row& r) {
-  const int H = p.hidden;
-  if constexpr (EMB) {
-    int id = p.ids[t];
-    id = min(max(id, 0), p.vocab - 1);
-    const uint2* w2 = reinterpret_cast<const uint2*>(p.word + static_cast<size_t>(id) * H);
-    const uint2* p2 = reinterpret_cast<const uint2*>(p.pos + static_cast<size_t>(t % p.seq) * H);
-    const uint2* t2 = reinterpret_cast<const uint2*>(p.type0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i < nv) {
-        const int j = lane + 32 * i;
-        const uint2 a = __ldg(w2 + j), b = __ldg(p2 + j), c = __ldg(t2 + j);
-        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
-        const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
-        const float2 c0 = __half22float2(*reinterpret_cast<const __half2*>(&c.x)), c1 = __half22float2(*reinterpret_cast<const __half2*>(&c.y));
-        r.v[i] = make_float4(a0.x + b0.x + c0.x, a0.y + b0.y + c0.y, a1.x + b1.x + c1.x, a1.y + b1.y + c1.y);
-      }
-    }
-  } else {
-    const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * H);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      if (i < nv) r.v[i] = __ldcg(s4 + lane + 32 * i);  // written by other CTAs in this launch: L2, not L1
-  }
-}
-
-__device__ __forceinline__ void finish_row(const FusedParams& p, const float* g, const float* bt, int t, int lane, int nv,
-                                           const Row& r, uint8_t* bsm, bool plain, __half* hout) {
-  const int H = p.hidden;
-  float sum = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) sum += (r.v[i].x + r.v[i].y) + (r.v[i].z + r.v[i].w);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  const float mean = sum / H;
-  float var = 0.f;
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) {
-      const float a = r.v[i].x - mean, b = r.v[i].y - mean, c = r.v[i].z - mean, d = r.v[i].w - mean;
-      var += (a * a + b * b) + (c * c + d * d);
-    }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-  const float rstd = rsqrtf(var / H + p.eps);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    if (i < nv) {
-      const int j = lane + 32 * i, f = 4 * j;
-      const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + j), bb = __ldg(reinterpret_cast<const float4*>(bt) + j);
-      uint2 o;
-      o.x = pack_half2((r.v[i].x - mean) * rstd * gg.x + bb.x, (r.v[i].y - mean) * rstd * gg.y + bb.y);
-      o.y = pack_half2((r.v[i].z - mean) * rstd * gg.z + bb.z, (r.v[i].w - mean) * rstd * gg.w + bb.w);
-      const uint32_t off = plain ? static_cast<uint32_t>((t * H + f) * 2) : operand_offset(t, f, p.tpad);
-      *reinterpret_cast<uint2*>(bsm + off) = o;
-      if (hout != nullptr) *reinterpret_cast<uint2*>(hout + static_cast<size_t>(t) * H + f) = o;
-    }
-}
-
-template <bool EMB>
+// LayerNorm-on-load.  Warp w normalises tokens w, w + 8, w + 16, w + 24 in lock step (the loads and
+// the two shuffle reductions of the four rows overlap), then the next four; lane holds the float4s
+// lane, lane + 32, ... of a row.  g / bt: gamma / beta staged in shared memory before the phase barrier
+// was awaited.  Writes fp16 into the swizzled operand (or row-major when `plain`), optionally also to
+// global `hout` (the copy later residual adds read).
+template <bool EMB, int NV>
 __device__ __forceinline__ void stage_ln(const FusedParams& p, const float* src, const float* g, const float* bt, uint8_t* bsm,
                                          bool plain, __half* hout, int warp, int lane) {
-  const int nv = p.hidden >> 7;
-  for (int t = warp; t < p.tokens; t += 2 * kFusedComputeWarps) {
-    Row r0, r1;
-    const int t1 = t + kFusedComputeWarps;
-    load_row<EMB>(p, src, t, lane, nv, r0);
-    if (t1 < p.tokens) load_row<EMB>(p, src, t1, lane, nv, r1);
-    finish_row(p, g, bt, t, lane, nv, r0, bsm, plain, hout);
-    if (t1 < p.tokens) finish_row(p, g, bt, t1, lane, nv, r1, bsm, plain, hout);
+  constexpr int R = NV >= 8 ? 2 : 4;  // rows in lock step (register budget)
+  constexpr int H = NV * 128;
+  for (int t0 = warp; t0 < p.tokens; t0 += R * kFusedComputeWarps) {
+    float4 v[R][NV];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int t = t0 + r * kFusedComputeWarps;
+      if (t < p.tokens) {
+        if constexpr (EMB) {
+          int id = p.ids[t];
+          id = min(max(id, 0), p.vocab - 1);
+          const uint2* w2 = reinterpret_cast<const uint2*>(p.word + static_cast<size_t>(id) * H);
+          const uint2* p2 = reinterpret_cast<const uint2*>(p.pos + static_cast<size_t>(t % p.seq) * H);
+          const uint2* t2 = reinterpret_cast<const uint2*>(p.type0);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) {
+            const int j = lane + 32 * i;
+            const uint2 a = __ldg(w2 + j), b = __ldg(p2 + j), c = __ldg(t2 + j);
+            const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&a.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&a.y));
+            const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&b.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&b.y));
+            const float2 c0 = __half22float2(*reinterpret_cast<const __half2*>(&c.x)), c1 = __half22float2(*reinterpret_cast<const __half2*>(&c.y));
+            v[r][i] = make_float4(a0.x + b0.x + c0.x, a0.y + b0.y + c0.y, a1.x + b1.x + c1.x, a1.y + b1.y + c1.y);
+          }
+        } else {
+          const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<size_t>(t) * H);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) v[r][i] = __ldcg(s4 + lane + 32 * i);  // written by other CTAs in this launch: L2, not L1
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) v[r][i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) mean[r] += (v[r][i].x + v[r][i].y) + (v[r][i].z + v[r][i].w);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) mean[r] += __shfl_xor_sync(0xffffffffu, mean[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      mean[r] *= 1.0f / H;
+      float var = 0.f;
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const float a = v[r][i].x - mean[r], b = v[r][i].y - mean[r], c = v[r][i].z - mean[r], d = v[r][i].w - mean[r];
+        var += (a * a + b * b) + (c * c + d * d);
+      }
+      rstd[r] = var;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) rstd[r] += __shfl_xor_sync(0xffffffffu, rstd[r], o);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) rstd[r] = rsqrtf(rstd[r] * (1.0f / H) + p.eps);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int j = lane + 32 * i, f = 4 * j;
+      const float4 gg = reinterpret_cast<const float4*>(g)[j], bb = reinterpret_cast<const float4*>(bt)[j];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int t = t0 + r * kFusedComputeWarps;
+        if (t < p.tokens) {
+          uint2 o;
+          o.x = pack_half2((v[r][i].x - mean[r]) * rstd[r] * gg.x + bb.x, (v[r][i].y - mean[r]) * rstd[r] * gg.y + bb.y);
+          o.y = pack_half2((v[r][i].z - mean[r]) * rstd[r] * gg.z + bb.z, (v[r][i].w - mean[r]) * rstd[r] * gg.w + bb.w);
+          const uint32_t off = plain ? static_cast<uint32_t>((t * H + f) * 2) : operand_offset(t, f, p.tpad);
+          *reinterpret_cast<uint2*>(bsm + off) = o;
+          if (hout != nullptr) *reinterpret_cast<uint2*>(hout + static_cast<size_t>(t) * H + f) = o;
+        }
+      }
+    }
   }
 }
 
@@ -190,10 +210,24 @@ __device__ __forceinline__ void stage_ln(const FusedParams& p, const float* src,
 __device__ __forceinline__ void stage_copy(const FusedParams& p, const __half* src, int ld, int k0, uint8_t* bsm, int tid) {
   const int cpr = p.hidden >> 3;  // 16-byte chunks per row
   const int total = p.tokens * cpr;
-  for (int q = tid; q < total; q += kFusedComputeThreads) {
-    const int t = q / cpr, cg = q - t * cpr;
-    const uint4 v = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(t) * ld + k0) + cg);
-    *reinterpret_cast<uint4*>(bsm + operand_offset(t, cg << 3, p.tpad)) = v;
+  for (int q0 = tid; q0 < total; q0 += 4 * kFusedComputeThreads) {  // four loads in flight per thread
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * kFusedComputeThreads;
+      if (q < total) {
+        const int t = q / cpr, cg = q - t * cpr;
+        v[u] = __ldcg(reinterpret_cast<const uint4*>(src + static_cast<size_t>(t) * ld + k0) + cg);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int q = q0 + u * kFusedComputeThreads;
+      if (q < total) {
+        const int t = q / cpr, cg = q - t * cpr;
+        *reinterpret_cast<uint4*>(bsm + operand_offset(t, cg << 3, p.tpad)) = v[u];
+      }
+    }
   }
 }
 
@@ -293,9 +327,21 @@ __device__ __forceinline__ void head_attention(const __half* qs, const __half* k
   }
 }
 
+// Sum of the four accumulators of tile `mt` over 8 token columns starting at `col` (this thread's lane).
+__device__ __forceinline__ void load_acc8(uint32_t lane_taddr, int mt, int col, float (&v)[8]) {
+  uint32_t r[kFusedAcc][8];
+#pragma unroll
+  for (int a = 0; a < kFusedAcc; ++a) ptx::tmem_ld_32x32b_x8(lane_taddr + (mt * kFusedAcc + a) * 64 + col, r[a]);
+  ptx::tc_wait_ld();
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    v[j] = (__uint_as_float(r[0][j]) + __uint_as_float(r[1][j])) + (__uint_as_float(r[2][j]) + __uint_as_float(r[3][j]));
+}
+
 }  // namespace fused
 
-template <int DH>
+// DH = head size (32 / 64), NV = hidden / 128.
+template <int DH, int NV>
 __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const FusedParams p) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kFusedMaxSlots];
@@ -308,14 +354,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int G = gridDim.x, cta = blockIdx.x;
-  const int H = p.hidden, F = p.ffn, T = p.tokens, tpad = p.tpad;
-  const int KB = H >> 6;          // k-blocks of every job (phase D slices K = F into F / H jobs of H)
+  constexpr int H = NV * 128;
+  const int F = p.ffn, T = p.tokens, tpad = p.tpad;
+  constexpr int KB = H >> 6;      // k-blocks of every job (phase D slices K = F into F / H jobs of H)
   const int KS = F / H;           // split-K factor of phase D
   const int njobs[4] = {p.heads, H >> 7, F >> 7, (H >> 7) * KS};
   constexpr int kTilesA = DH == 32 ? 1 : 2;  // head_dim 32: q|k|v stacked in one 128-row tile; 64: q|k, then v
   constexpr int kTmaWarp = kFusedComputeWarps, kMmaWarp = kFusedComputeWarps + 1;
 
-  // shared-memory carve-up: weight ring | token operand | attention scratch
+  // shared-memory carve-up: weight ring | token operand | attention scratch | LayerNorm parameters
   const uint32_t base_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* base_ptr = smem_raw + (base_u32 - ptx::smem_u32(smem_raw));
   const uint32_t ring_u32 = base_u32;
@@ -326,6 +373,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
   __half* ks = qs + tpad * (DH + 8);
   __half* vt = ks + tpad * (DH + 8);
   int* tag = reinterpret_cast<int*>(vt + DH * (tpad + 8));
+  float* lng = reinterpret_cast<float*>(tag + tpad);  // LayerNorm gamma / beta of the rows being staged
+  float* lnb = lng + H;
 
   if (warp == kMmaWarp && lane == 0) {
     for (int s = 0; s < p.nslots; ++s) {
@@ -404,7 +453,8 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
       }
     }
   } else if (warp == kMmaWarp) {
-    // ---------------- tensor core: D[128 features, tpad tokens] (+)= W tile (ring) x operand^T
+    // ---------------- tensor core: D[128 features, tpad tokens] (+)= W tile (ring) x operand^T; the four
+    // K = 16 steps of a k-block accumulate into four different TMEM accumulators (independent chains)
     const uint32_t full0 = ptx::smem_u32(&full_bar[0]), empty0 = ptx::smem_u32(&empty_bar[0]);
     const uint32_t a_lo0 = ((ring_u32 & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo0 = ((bop_u32 & 0x3FFFFu) >> 4) | (1u << 16);
@@ -430,7 +480,7 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
                 for (int k4 = 0; k4 < 4; ++k4) {
                   const uint64_t adesc = (static_cast<uint64_t>(kDescHi) << 32) | (alo + k4 * 2);
                   const uint64_t bdesc = (static_cast<uint64_t>(kDescHi) << 32) | (blo + k4 * 2);
-                  ptx::mma_f16_ss(tmem_base + mt * 64, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                  ptx::mma_f16_ss(tmem_base + (mt * kFusedAcc + k4) * 64, adesc, bdesc, idesc, kb != 0 ? 1u : 0u);
                 }
                 ptx::tc_commit_a(empty0 + stage * 8);
                 if (mt == ntiles - 1 && kb == KB - 1) ptx::tc_commit(&accfull_bar);
@@ -447,10 +497,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
       }
     }
   } else {
-    // ---------------- compute warps: operand staging, epilogues, attention, phase barriers
+    // ---------------- compute warps: operand staging, epilogues, attention, phase barriers.
+    // Epilogue mapping: lane quarter q = warp & 3 <-> TMEM lanes (features) 32 q .. 32 q + 31,
+    // hf = warp >> 2 <-> the first / second half of the token columns, in chunks of 8.
     const int tid = threadIdx.x;
-    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    const int nchunks = tpad >> 4;
+    const int q = warp & 3, hf = warp >> 2;
+    const uint32_t lane_taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int nch = tpad >> 4;  // chunks of 8 tokens per half: tokens (hf * nch + c) * 8 ..
+    const int ntr = 4 * p.num_layers + 1;
+    unsigned long long* tr = (p.trace != nullptr && tid == 0) ? p.trace + static_cast<size_t>(cta) * ntr * 6 : nullptr;
     uint32_t jcount = 0;
     int jb = 0, bar_idx = 0;
     for (int l = 0; l < p.num_layers; ++l) {
@@ -458,94 +513,140 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
       for (int ph = 0; ph < 4; ++ph, ++bar_idx) {
         const int n = njobs[ph];
         bool waited = bar_idx == 0;  // the first phase reads only weights and token ids
+        if (tr) tr[bar_idx * 6 + 0] = fused::timer_ns();
         for (int i = ((cta - jb) % G + G) % G; i < n; i += G, ++jcount) {
+          // ---- everything that does not depend on other CTAs comes BEFORE the phase barrier is awaited:
+          // LayerNorm gamma / beta into shared memory, this thread's bias into a register
+          float bias = 0.f, bias2 = 0.f;
+          if (ph == 0) {
+            const float* g = l == 0 ? p.emb_g : (L - 1)->ln2_g;
+            const float* bt = l == 0 ? p.emb_b : (L - 1)->ln2_b;
+            for (int j = tid; j < H / 4; j += kFusedComputeThreads) {
+              reinterpret_cast<float4*>(lng)[j] = __ldg(reinterpret_cast<const float4*>(g) + j);
+              reinterpret_cast<float4*>(lnb)[j] = __ldg(reinterpret_cast<const float4*>(bt) + j);
+            }
+            if constexpr (DH == 32) {
+              if (q < 3) bias = __ldg(L->bqkv + q * H + i * DH + lane);
+            } else {
+              bias = __ldg(L->bqkv + (q >> 1) * H + i * DH + (q & 1) * 32 + lane);          // tile 0: q | k
+              if (q < 2) bias2 = __ldg(L->bqkv + 2 * H + i * DH + (q & 1) * 32 + lane);     // tile 1: v
+            }
+          } else if (ph == 2) {
+            for (int j = tid; j < H / 4; j += kFusedComputeThreads) {
+              reinterpret_cast<float4*>(lng)[j] = __ldg(reinterpret_cast<const float4*>(L->ln1_g) + j);
+              reinterpret_cast<float4*>(lnb)[j] = __ldg(reinterpret_cast<const float4*>(L->ln1_b) + j);
+            }
+            bias = __ldg(L->b1 + i * 128 + q * 32 + lane);
+          } else if (ph == 1) {
+            bias = __ldg(L->bo + i * 128 + q * 32 + lane);
+          } else {
+            bias = __ldg(L->b2 + (i / KS) * 128 + q * 32 + lane);
+          }
           if (!waited) {
             if (tid == 0) fused::grid_wait(p.bar + bar_idx - 1, static_cast<unsigned>(G));
-            fused::cbar();
             waited = true;
           }
+          fused::cbar();  // barrier passed, gamma / beta staged
+          if (tr) tr[bar_idx * 6 + 1] = fused::timer_ns();
           // ---- stage the token operand
           if (ph == 0) {
             __half* hout = i == 0 ? p.h0 : nullptr;
             if (l == 0)
-              fused::stage_ln<true>(p, nullptr, p.emb_g, p.emb_b, bop, false, hout, warp, lane);
+              fused::stage_ln<true, NV>(p, nullptr, lng, lnb, bop, false, hout, warp, lane);
             else
-              fused::stage_ln<false>(p, p.pre2, (L - 1)->ln2_g, (L - 1)->ln2_b, bop, false, hout, warp, lane);
+              fused::stage_ln<false, NV>(p, p.pre2, lng, lnb, bop, false, hout, warp, lane);
           } else if (ph == 1) {
             fused::stage_copy(p, p.ctx, H, 0, bop, tid);
           } else if (ph == 2) {
-            fused::stage_ln<false>(p, p.pre1, L->ln1_g, L->ln1_b, bop, false, i == 0 ? p.h1 : nullptr, warp, lane);
+            fused::stage_ln<false, NV>(p, p.pre1, lng, lnb, bop, false, i == 0 ? p.h1 : nullptr, warp, lane);
           } else {
             fused::stage_copy(p, p.act, F, (i % KS) * H, bop, tid);
           }
           ptx::fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's reads
           ptx::tc_fence_before();
           ptx::mbar_arrive(&bready_bar);
+          if (tr) tr[bar_idx * 6 + 2] = fused::timer_ns();
+          // residual rows (written a phase ago) on their way while the tensor core works
+          const int f_out = (ph == 3 ? i / KS : i) * 128 + q * 32 + lane;
+          __half res[4][8];
+          if (ph == 1 || ph == 3) {
+            const __half* hsrc = ph == 1 ? p.h0 : p.h1;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              if (c < nch) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int t = (hf * nch + c) * 8 + j;
+                  res[c][j] = t < T ? __ldcg(hsrc + static_cast<size_t>(t) * H + f_out) : __half();
+                }
+              }
+          }
           ptx::mbar_wait(&accfull_bar, jcount & 1u);
           ptx::tc_fence_after();
+          if (tr) tr[bar_idx * 6 + 3] = fused::timer_ns();
 
           // ---- epilogue: thread = feature (TMEM lane), registers = tokens
           if (ph == 0) {
 #pragma unroll
             for (int mt = 0; mt < kTilesA; ++mt) {
-              const int seg = DH == 32 ? warp : mt * 2 + (warp >> 1);  // 0 = q, 1 = k, 2 = v, 3 = unused lanes
-              const int fh = DH == 32 ? lane : (warp & 1) * 32 + lane;
+              const int seg = DH == 32 ? q : mt * 2 + (q >> 1);  // 0 = q, 1 = k, 2 = v, 3 = unused lanes
+              const int fh = DH == 32 ? lane : (q & 1) * 32 + lane;
+              const float bs = mt == 0 ? bias : bias2;
               if (seg < 3) {
-                const float bias = __ldg(L->bqkv + seg * H + i * DH + fh);
-                for (int c = 0; c < nchunks; ++c) {
-                  uint32_t r[16];
-                  ptx::tmem_ld_32x32b_x16(lane_taddr + mt * 64 + c * 16, r);
-                  ptx::tc_wait_ld();
+                for (int c = 0; c < nch; ++c) {
+                  const int tk0 = (hf * nch + c) * 8;
+                  float v[8];
+                  fused::load_acc8(lane_taddr, mt, tk0, v);
                   if (seg == 2) {
-                    __half* dst = vt + fh * (tpad + 8) + c * 16;
+                    __half* dst = vt + fh * (tpad + 8) + tk0;
 #pragma unroll
-                    for (int j = 0; j < 16; j += 2)
-                      *reinterpret_cast<__half2*>(dst + j) = __floats2half2_rn(__uint_as_float(r[j]) + bias, __uint_as_float(r[j + 1]) + bias);
+                    for (int j = 0; j < 8; j += 2) *reinterpret_cast<__half2*>(dst + j) = __floats2half2_rn(v[j] + bs, v[j + 1] + bs);
                   } else {
-                    __half* dst = (seg == 0 ? qs : ks) + (c * 16) * (DH + 8) + fh;
+                    __half* dst = (seg == 0 ? qs : ks) + tk0 * (DH + 8) + fh;
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) dst[j * (DH + 8)] = __float2half_rn(__uint_as_float(r[j]) + bias);
+                    for (int j = 0; j < 8; ++j) dst[j * (DH + 8)] = __float2half_rn(v[j] + bs);
                   }
                 }
               }
             }
             fused::cbar();
             fused::head_attention<DH>(qs, ks, vt, tag, tpad, T, p.seq, p.ctx + i * DH, H, warp, lane);
-          } else if (ph == 1 || ph == 2) {
-            const int f = i * 128 + warp * 32 + lane;
-            const float bias = __ldg((ph == 1 ? L->bo : L->b1) + f);
-            for (int c = 0; c < nchunks; ++c) {
-              uint32_t r[16];
-              ptx::tmem_ld_32x32b_x16(lane_taddr + c * 16, r);
-              ptx::tc_wait_ld();
+          } else if (ph == 1) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const int t = c * 16 + j;
-                if (t < T) {
-                  const float v = __uint_as_float(r[j]) + bias;
-                  if (ph == 1) {
-                    p.pre1[static_cast<size_t>(t) * H + f] = v + __half2float(__ldcg(p.h0 + static_cast<size_t>(t) * H + f));
-                  } else {
-                    p.act[static_cast<size_t>(t) * F + f] = __float2half_rn(0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
-                  }
+            for (int c = 0; c < 4; ++c)
+              if (c < nch) {
+                const int tk0 = (hf * nch + c) * 8;
+                float v[8];
+                fused::load_acc8(lane_taddr, 0, tk0, v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  if (tk0 + j < T) p.pre1[static_cast<size_t>(tk0 + j) * H + f_out] = v[j] + bias + __half2float(res[c][j]);
+              }
+          } else if (ph == 2) {
+            for (int c = 0; c < nch; ++c) {
+              const int tk0 = (hf * nch + c) * 8;
+              float v[8];
+              fused::load_acc8(lane_taddr, 0, tk0, v);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                if (tk0 + j < T) {
+                  const float x = v[j] + bias;
+                  p.act[static_cast<size_t>(tk0 + j) * F + f_out] = __float2half_rn(0.5f * x * (1.0f + erff(x * 0.70710678118654752f)));
                 }
               }
             }
           } else {
             // split-K: slab out, the last CTA of the tile sums all slabs in slice order
             const int tile = i / KS, ksl = i % KS;
-            const int f = tile * 128 + warp * 32 + lane;
-            float* slab = p.partial + (static_cast<size_t>(tile) * KS) * tpad * 128 + warp * 32 + lane;
+            float* slab = p.partial + (static_cast<size_t>(tile) * KS) * tpad * 128 + q * 32 + lane;
             if (KS > 1) {
-              for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[16];
-                ptx::tmem_ld_32x32b_x16(lane_taddr + c * 16, r);
-                ptx::tc_wait_ld();
+              for (int c = 0; c < nch; ++c) {
+                const int tk0 = (hf * nch + c) * 8;
+                float v[8];
+                fused::load_acc8(lane_taddr, 0, tk0, v);
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int t = c * 16 + j;
-                  if (t < T) slab[(static_cast<size_t>(ksl) * tpad + t) * 128] = __uint_as_float(r[j]);
-                }
+                for (int j = 0; j < 8; ++j)
+                  if (tk0 + j < T) slab[(static_cast<size_t>(ksl) * tpad + tk0 + j) * 128] = v[j];
               }
               __threadfence();
               fused::cbar();
@@ -560,60 +661,77 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
               fused::cbar();
             }
             if (KS == 1 || s_last) {
-              const float bias = __ldg(L->b2 + f);
-              for (int c = 0; c < nchunks; ++c) {
-                uint32_t r[16];
-                ptx::tmem_ld_32x32b_x16(lane_taddr + c * 16, r);
-                ptx::tc_wait_ld();
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const int t = c * 16 + j;
-                  if (t < T) {
-                    float acc = 0.f;
-                    for (int s = 0; s < KS; ++s)
-                      acc += s == ksl ? __uint_as_float(r[j]) : __ldcg(slab + (static_cast<size_t>(s) * tpad + t) * 128);
-                    p.pre2[static_cast<size_t>(t) * H + f] = acc + bias + __half2float(__ldcg(p.h1 + static_cast<size_t>(t) * H + f));
+              for (int c = 0; c < 4; ++c)
+                if (c < nch) {
+                  const int tk0 = (hf * nch + c) * 8;
+                  float own[8], acc[8];
+                  fused::load_acc8(lane_taddr, 0, tk0, own);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+                  for (int s = 0; s < KS; ++s) {  // slice order, whoever arrived last: deterministic
+                    if (s == ksl) {
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) acc[j] += own[j];
+                    } else {
+                      float o[8];
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) o[j] = tk0 + j < T ? __ldcg(slab + (static_cast<size_t>(s) * tpad + tk0 + j) * 128) : 0.f;
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) acc[j] += o[j];
+                    }
                   }
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    if (tk0 + j < T) p.pre2[static_cast<size_t>(tk0 + j) * H + f_out] = acc[j] + bias + __half2float(res[c][j]);
                 }
-              }
             }
           }
           ptx::tc_fence_before();  // accumulator reads done before the next job's MMAs (ordered by bready_bar)
+          if (tr) tr[bar_idx * 6 + 4] = fused::timer_ns();
         }
         jb += n;
         fused::cbar();  // every compute thread's stores of this phase are issued
         if (tid == 0) fused::grid_arrive(p.bar + bar_idx);
+        if (tr) tr[bar_idx * 6 + 5] = fused::timer_ns();
       }
     }
     // ---------------- pooling + L2 normalise (CTA 0)
     if (cta == 0) {
       const int last = 4 * p.num_layers - 1;
+      {
+        const FusedLayer* Ll = p.layers + p.num_layers - 1;
+        for (int j = tid; j < H / 4; j += kFusedComputeThreads) {
+          reinterpret_cast<float4*>(lng)[j] = __ldg(reinterpret_cast<const float4*>(Ll->ln2_g) + j);
+          reinterpret_cast<float4*>(lnb)[j] = __ldg(reinterpret_cast<const float4*>(Ll->ln2_b) + j);
+        }
+      }
       if (tid == 0) fused::grid_wait(p.bar + last, static_cast<unsigned>(G));
       fused::cbar();
-      fused::stage_ln<false>(p, p.pre2, p.layers[p.num_layers - 1].ln2_g, p.layers[p.num_layers - 1].ln2_b, bop, true, nullptr, warp, lane);
+      fused::stage_ln<false, NV>(p, p.pre2, lng, lnb, bop, true, nullptr, warp, lane);
       fused::cbar();
       const __half* hs = reinterpret_cast<const __half*>(bop);
-      const int nf = H >> 7;
+      constexpr int kPF = (H + kFusedComputeThreads - 1) / kFusedComputeThreads;  // features per thread
       for (int b = 0; b < p.batch; ++b) {
         float cnt = 0.f;
-        for (int j = 0; j < p.seq; ++j) cnt += p.mask[b * p.seq + j] != 0 ? 1.f : 0.f;
+        for (int j = 0; j < p.seq; ++j) cnt += tag[b * p.seq + j] >= 0 ? 1.f : 0.f;
         cnt = fmaxf(cnt, 1e-9f);
-        float v[8];
+        float v[kPF];
         float ss = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          v[q] = 0.f;
-          if (q < nf) {
-            const int f = tid + q * kFusedComputeThreads;
+        for (int u = 0; u < kPF; ++u) {
+          v[u] = 0.f;
+          const int f = tid + u * kFusedComputeThreads;
+          if (f < H) {
             if (p.pool_cls) {
-              v[q] = __half2float(hs[static_cast<size_t>(b) * p.seq * H + f]);
+              v[u] = __half2float(hs[static_cast<size_t>(b) * p.seq * H + f]);
             } else {
               float acc = 0.f;
               for (int j = 0; j < p.seq; ++j)
-                if (p.mask[b * p.seq + j] != 0) acc += __half2float(hs[(static_cast<size_t>(b) * p.seq + j) * H + f]);
-              v[q] = acc / cnt;
+                if (tag[b * p.seq + j] >= 0) acc += __half2float(hs[(static_cast<size_t>(b) * p.seq + j) * H + f]);
+              v[u] = acc / cnt;
             }
-            ss += v[q] * v[q];
+            ss += v[u] * v[u];
           }
         }
 #pragma unroll
@@ -625,12 +743,15 @@ __global__ void __launch_bounds__(kFusedThreads, 1) bert_fused_kernel(const Fuse
         for (int w = 0; w < kFusedComputeWarps; ++w) tot += s_red[w];
         const float inv = 1.f / fmaxf(sqrtf(tot), 1e-12f);
 #pragma unroll
-        for (int q = 0; q < 8; ++q)
-          if (q < nf) p.out[static_cast<size_t>(b) * H + tid + q * kFusedComputeThreads] = v[q] * inv;
+        for (int u = 0; u < kPF; ++u) {
+          const int f = tid + u * kFusedComputeThreads;
+          if (f < H) p.out[static_cast<size_t>(b) * H + f] = v[u] * inv;
+        }
         fused::cbar();
       }
       // every CTA has arrived at every phase counter: clear them for the next launch
       for (int j = tid; j <= last; j += kFusedComputeThreads) p.bar[j] = 0u;
+      if (tr) tr[(last + 1) * 6 + 0] = fused::timer_ns();
     }
   }
   ptx::tc_fence_before();

@@ -14,11 +14,11 @@
 
 namespace lxg {
 
-inline int make_map(CUtensorMap* m, const void* base, int rows, int cols) {
-  // row-major fp16 [rows, cols]; box = 64 columns x 128 rows, 128-byte swizzle
+inline int make_map(CUtensorMap* m, const void* base, int rows, int cols, int box_rows = kGemmBM) {
+  // row-major fp16 [rows, cols]; box = 64 columns x box_rows (128) rows, 128-byte swizzle
   cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
   cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * sizeof(__half)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(kGemmBM)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kGemmBK), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = lxg::encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride,
                                       box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,

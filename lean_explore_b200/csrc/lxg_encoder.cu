@@ -13,6 +13,7 @@
 #include "../../include/lxg.h"
 #include "common.h"
 #include "encoder_kernels.cuh"
+#include "fused_encoder.cuh"
 #include "gemm_host.cuh"
 
 using namespace lxg;
@@ -44,6 +45,17 @@ struct lxg_encoder {
   // the caller's stream may be the legacy default stream, which cannot be captured.
   cudaStream_t own = nullptr;
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  // Query path (<= 64 tokens): the whole forward as one cooperative kernel (fused_encoder.cuh).
+  // 0 = not probed yet, 1 = available, -1 = geometry / device cannot run it (layered path only).
+  int fused_state = 0;
+  int fused_grid = 0;
+  FusedLayer* fused_layers = nullptr;  // device array, one entry per layer (tensor maps + vectors)
+  uint8_t* fused_ws = nullptr;         // activations, split-K slabs, counters
+  FusedParams fused_base{};
+  bool last_fused = false;
+  bool fused_allowed = true;  // lxg_encoder_set_fused
+  bool fused_trace = false;   // lxg_encoder_set_fused(enc, 2): per-phase %globaltimer stamps of every CTA
+  unsigned long long* trace_buf = nullptr;
 };
 
 namespace {
@@ -51,6 +63,142 @@ namespace {
 void drop_graphs(lxg_encoder* e) {
   for (auto& g : e->graphs) cudaGraphExecDestroy(g.exec);
   e->graphs.clear();
+}
+
+constexpr size_t kFusedSmemLimit = 226 * 1024;  // dynamic part; the kernel also has ~300 B of static shared memory
+
+// shared memory of the fused kernel besides the weight ring: token operand + attention scratch + alignment
+size_t fused_fixed_smem(int tpad, int H, int dh) {
+  return static_cast<size_t>(tpad) * H * 2 + static_cast<size_t>(2) * tpad * (dh + 8) * 2 + static_cast<size_t>(dh) * (tpad + 8) * 2 +
+         static_cast<size_t>(tpad) * 4 + static_cast<size_t>(2) * H * 4 + 1024 + 256;
+}
+
+using FusedKernel = void (*)(FusedParams);
+// instantiated geometries: (head size, hidden / 128); anything else stays on the layered kernels
+FusedKernel fused_kernel_for(int dh, int nv) {
+  if (dh == 32 && nv == 1) return bert_fused_kernel<32, 1>;
+  if (dh == 32 && nv == 3) return bert_fused_kernel<32, 3>;   // MiniLM-L6 / L12 (H = 384, 12 heads)
+  if (dh == 64 && nv == 6) return bert_fused_kernel<64, 6>;   // BERT-base / bge-base (H = 768, 12 heads)
+  if (dh == 64 && nv == 8) return bert_fused_kernel<64, 8>;   // BERT-large / bge-large (H = 1024, 16 heads)
+  return nullptr;
+}
+
+bool fused_enabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("LXG_FUSED");
+    return !(v && v[0] == '0');
+  }();
+  return on;
+}
+
+// One-time set-up of the single-kernel query path; leaves fused_state = -1 when this model cannot use it.
+int fused_prepare(lxg_encoder* e) {
+  e->fused_state = -1;
+  const int H = e->w.hidden, F = e->w.ffn, heads = e->w.heads, dh = H / heads, L = e->w.layers;
+  if (H % 128 != 0 || F % H != 0 || F % 128 != 0 || L > 64) return LXG_OK;
+  const FusedKernel kernel = fused_kernel_for(dh, H / 128);
+  if (kernel == nullptr) return LXG_OK;
+  std::vector<FusedLayer> host(L);
+  for (int l = 0; l < L; ++l) {
+    const lxg_bert_layer& W = e->layers[l];
+    int rc;
+    if ((rc = make_map(&host[l].map_qkv, W.wqkv, 3 * H, H, dh)) != LXG_OK || (rc = make_map(&host[l].map_wo, W.wo, H, H)) != LXG_OK ||
+        (rc = make_map(&host[l].map_w1, W.w1, F, H)) != LXG_OK || (rc = make_map(&host[l].map_w2, W.w2, H, F)) != LXG_OK)
+      return rc;
+    host[l].bqkv = reinterpret_cast<const float*>(W.bqkv);
+    host[l].bo = reinterpret_cast<const float*>(W.bo);
+    host[l].ln1_g = reinterpret_cast<const float*>(W.ln1_g);
+    host[l].ln1_b = reinterpret_cast<const float*>(W.ln1_b);
+    host[l].b1 = reinterpret_cast<const float*>(W.b1);
+    host[l].b2 = reinterpret_cast<const float*>(W.b2);
+    host[l].ln2_g = reinterpret_cast<const float*>(W.ln2_g);
+    host[l].ln2_b = reinterpret_cast<const float*>(W.ln2_b);
+  }
+  LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(kernel), kFusedSmemLimit));
+  int per_sm = 0;
+  LXG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kFusedThreads, kFusedSmemLimit));
+  int coop = 0;
+  LXG_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, e->device));
+  if (per_sm < 1 || !coop || lxg::num_sms() < 8) return LXG_OK;
+  e->fused_grid = lxg::num_sms();
+  LXG_CUDA(cudaMalloc(&e->fused_layers, L * sizeof(FusedLayer)));
+  LXG_CUDA(cudaMemcpy(e->fused_layers, host.data(), L * sizeof(FusedLayer), cudaMemcpyHostToDevice));
+  // workspace: h0 | h1 | ctx (fp16 [64, H]) | act (fp16 [64, F]) | pre1 | pre2 (fp32 [64, H]) | slabs | sem | bar
+  const size_t T = kFusedMaxTokens;
+  const size_t b_h = T * H * 2, b_act = T * F * 2, b_pre = T * H * 4, b_slab = static_cast<size_t>(H / 128) * (F / H) * T * 128 * 4;
+  const size_t b_ctr = (static_cast<size_t>(H / 128) + 4 * L + 64) * 4;
+  const size_t total = 3 * b_h + b_act + 2 * b_pre + b_slab + b_ctr;
+  LXG_CUDA(cudaMalloc(&e->fused_ws, total));
+  LXG_CUDA(cudaMemset(e->fused_ws, 0, total));
+  uint8_t* q = e->fused_ws;
+  FusedParams& fp = e->fused_base;
+  fp.layers = e->fused_layers;
+  fp.num_layers = L;
+  fp.hidden = H;
+  fp.ffn = F;
+  fp.heads = heads;
+  fp.vocab = e->w.vocab;
+  fp.eps = e->w.ln_eps;
+  fp.word = reinterpret_cast<const __half*>(e->w.word_emb);
+  fp.pos = reinterpret_cast<const __half*>(e->w.pos_emb);
+  fp.type0 = reinterpret_cast<const __half*>(e->w.type_emb);
+  fp.emb_g = reinterpret_cast<const float*>(e->w.emb_ln_g);
+  fp.emb_b = reinterpret_cast<const float*>(e->w.emb_ln_b);
+  fp.h0 = reinterpret_cast<__half*>(q), q += b_h;
+  fp.h1 = reinterpret_cast<__half*>(q), q += b_h;
+  fp.ctx = reinterpret_cast<__half*>(q), q += b_h;
+  fp.act = reinterpret_cast<__half*>(q), q += b_act;
+  fp.pre1 = reinterpret_cast<float*>(q), q += b_pre;
+  fp.pre2 = reinterpret_cast<float*>(q), q += b_pre;
+  fp.partial = reinterpret_cast<float*>(q), q += b_slab;
+  fp.sem = reinterpret_cast<unsigned*>(q), q += static_cast<size_t>(H / 128) * 4;
+  fp.bar = reinterpret_cast<unsigned*>(q);
+  e->fused_state = 1;
+  return LXG_OK;
+}
+
+// Whether this call goes through the single kernel.
+bool fused_applies(const lxg_encoder* e, int tokens) {
+  if (e->fused_state != 1 || tokens > kFusedMaxTokens) return false;
+  const int tpad = (tokens + 15) / 16 * 16;
+  const int H = e->w.hidden, dh = H / e->w.heads;
+  return fused_fixed_smem(tpad, H, dh) + 3 * static_cast<size_t>(kFusedSlotBytes) <= kFusedSmemLimit;
+}
+
+int launch_fused(lxg_encoder* e, int b, int s, int pool, cudaStream_t st) {
+  FusedParams fp = e->fused_base;
+  const int tokens = b * s, H = e->w.hidden, dh = H / e->w.heads;
+  fp.tokens = tokens;
+  fp.seq = s;
+  fp.batch = b;
+  fp.tpad = (tokens + 15) / 16 * 16;
+  fp.ids = e->ids;
+  fp.mask = e->mask;
+  fp.pool_cls = pool == LXG_POOL_CLS ? 1 : 0;
+  fp.out = e->out_buf;
+  fp.trace = nullptr;
+  if (e->fused_trace) {
+    const size_t n = static_cast<size_t>(e->fused_grid) * (4 * e->w.layers + 1) * 6;
+    if (!e->trace_buf) LXG_CUDA(cudaMalloc(&e->trace_buf, n * sizeof(unsigned long long)));
+    LXG_CUDA(cudaMemsetAsync(e->trace_buf, 0, n * sizeof(unsigned long long), st));
+    fp.trace = e->trace_buf;
+  }
+  const size_t fixed = fused_fixed_smem(fp.tpad, H, dh);
+  fp.nslots = static_cast<int>(std::min<size_t>(kFusedMaxSlots, (kFusedSmemLimit - fixed) / kFusedSlotBytes));
+  const size_t smem = fixed + static_cast<size_t>(fp.nslots) * kFusedSlotBytes;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(e->fused_grid);
+  cfg.blockDim = dim3(kFusedThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;  // all CTAs co-resident: the phase barriers cannot deadlock
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  LXG_CUDA(cudaLaunchKernelEx(&cfg, fused_kernel_for(dh, H / 128), fp));
+  e->launches = 1;
+  return LXG_OK;
 }
 
 void free_ws(lxg_encoder* e) {
@@ -235,6 +383,9 @@ int lxg_encoder_destroy(lxg_encoder* e) {
   if (!e) return LXG_OK;
   DeviceGuard guard(e->device);
   free_ws(e);
+  cudaFree(e->fused_layers);
+  cudaFree(e->fused_ws);
+  cudaFree(e->trace_buf);
   if (e->own) cudaStreamDestroy(e->own);
   if (e->ev_in) cudaEventDestroy(e->ev_in);
   if (e->ev_out) cudaEventDestroy(e->ev_out);
@@ -243,6 +394,28 @@ int lxg_encoder_destroy(lxg_encoder* e) {
 }
 
 int lxg_encoder_last_launches(const lxg_encoder* e) { return e ? e->launches : -1; }
+
+int lxg_encoder_set_fused(lxg_encoder* e, int enabled) {
+  if (!e) return set_error(LXG_EINVAL, "NULL encoder");
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->fused_allowed = enabled != 0;
+  e->fused_trace = enabled == 2;
+  return LXG_OK;
+}
+
+int lxg_encoder_read_trace(lxg_encoder* e, uint64_t* out, int32_t capacity, int32_t* grid, int32_t* phases) {
+  if (!e || !out || !grid || !phases) return set_error(LXG_EINVAL, "NULL argument");
+  DeviceGuard guard(e->device);
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (!e->trace_buf) return set_error(LXG_EINVAL, "no trace recorded (lxg_encoder_set_fused(enc, 2), then a call of <= 64 tokens)");
+  *grid = e->fused_grid;
+  *phases = 4 * e->w.layers + 1;
+  const size_t n = static_cast<size_t>(*grid) * *phases * 6;
+  if (static_cast<size_t>(capacity) < n) return set_error(LXG_EINVAL, "trace buffer too small");
+  if (e->own) LXG_CUDA(cudaStreamSynchronize(e->own));
+  LXG_CUDA(cudaMemcpy(out, e->trace_buf, n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return LXG_OK;
+}
 
 int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int32_t s, int pool, float* out,
                void* stream) {
@@ -281,8 +454,19 @@ int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t 
     LXG_CUDA(cudaMalloc(&e->out_buf, static_cast<size_t>(cap) * H * sizeof(float)));
     e->out_cap = cap;
   }
+  const bool want_fused = fused_enabled() && e->fused_allowed;
+  if (e->fused_state == 0 && want_fused) {
+    rc = fused_prepare(e);
+    if (rc != LXG_OK) return rc;
+  }
+  const bool fused = want_fused && fused_applies(e, tokens);
+  e->last_fused = fused;
+  if (fused) {
+    rc = launch_fused(e, b, s, pool, st);
+    if (rc != LXG_OK) return rc;
+  }
   cudaGraphExec_t exec = nullptr;
-  if (e->use_graphs) {
+  if (!fused && e->use_graphs) {
     for (auto& g : e->graphs)
       if (g.b == b && g.s == s && g.pool == pool) exec = g.exec;
     if (!exec) {
@@ -313,7 +497,7 @@ int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t 
       LXG_CUDA(cudaGraphLaunch(exec, st));
     }
   }
-  if (!e->use_graphs) {
+  if (!fused && !e->use_graphs) {
     rc = launch_forward(e, b, s, pool, st);
     if (rc != LXG_OK) return rc;
   }

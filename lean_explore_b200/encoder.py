@@ -121,6 +121,19 @@ class BertSentenceEncoder:
     def last_launches(self) -> int:
         return int(self._lib.lxg_encoder_last_launches(self._handle))
 
+    def set_fused(self, enabled: bool) -> None:
+        """Calls of <= 64 tokens (search queries) run as one persistent kernel; False keeps this
+        encoder on the layered kernels."""
+        _lib.check(self._lib.lxg_encoder_set_fused(self._handle, int(enabled)))
+
+    def read_trace(self) -> np.ndarray:
+        """After ``set_fused(2)`` and a query-path call: uint64 [grid, phases, 6] %globaltimer stamps (ns)."""
+        cap = 256 * 260 * 6
+        buf = np.zeros(cap, dtype=np.uint64)
+        grid, phases = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(self._lib.lxg_encoder_read_trace(self._handle, buf.ctypes.data, cap, ctypes.byref(grid), ctypes.byref(phases)))
+        return buf[: grid.value * phases.value * 6].reshape(grid.value, phases.value, 6)
+
     # ------------------------------------------------------------------ text in, vectors out
     def encode(self, texts: list[str], batch_size: int = 8, is_query: bool = False) -> np.ndarray:
         """``SentenceTransformer.encode(texts, batch_size=..., prompt_name="query" if is_query)``:

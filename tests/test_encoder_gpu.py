@@ -47,7 +47,57 @@ def test_encoder_matches_hf_oracle(geom, b, s, pool):
     enc = _encoder(model, cfg, pool)
     got = enc.encode_ids(ids, mask)
     _compare(got, want)
+    # <= 64 tokens: the single persistent kernel; more: the layered kernels
+    assert enc.last_launches() == (1 if b * s <= 64 else 2 + 7 * cfg.num_hidden_layers)
+
+
+@pytest.mark.parametrize("geom,b,s,pool", [
+    ("tiny", 1, 1, "cls"), ("tiny", 7, 9, "mean"), ("tiny", 1, 64, "mean"),
+    ("minilm-l6", 1, 5, "mean"), ("minilm-l6", 1, 16, "mean"), ("minilm-l6", 1, 33, "mean"), ("minilm-l6", 1, 64, "cls"),
+    ("minilm-l6", 4, 7, "mean"), ("minilm-l6", 8, 8, "mean"), ("minilm-l6", 3, 21, "cls"),
+    ("bge-base", 1, 9, "cls"), ("bge-base", 1, 16, "mean"), ("bge-base", 1, 48, "cls"), ("bge-base", 2, 32, "mean"),
+    ("bge-base", 5, 11, "cls"),
+])
+def test_query_path_single_kernel_matches_oracle_and_layered_path(geom, b, s, pool):
+    """The query path (<= 64 tokens, EmbeddingClient.embed([query]) at search/engine.py:236) is one
+    cooperative kernel: same tolerance against the HF oracle as the layered kernels, and the two
+    paths agree with each other far inside it (same operand precision, different summation split)."""
+    model, cfg = be.make_model(geom, seed=0)
+    ids, mask = be.make_inputs(b, s, seed=3 + b + s)
+    want = be.encode(model, ids, mask, pool)
+    enc = _encoder(model, cfg, pool)
+    got = enc.encode_ids(ids, mask)
+    assert enc.last_launches() == 1
+    _compare(got, want)
+    again = enc.encode_ids(ids, mask)
+    assert (again == got).all(), "the single kernel must be deterministic (fixed-order split-K sums)"
+    enc.set_fused(False)
+    layered = enc.encode_ids(ids, mask)
     assert enc.last_launches() == 2 + 7 * cfg.num_hidden_layers
+    assert np.abs(layered - got).max() < 5e-4  # fp16 roundings of different summation orders, 12 layers deep
+    enc.set_fused(True)
+    # garbage under the mask must not matter, nor a different call in between (workspace / counters reuse)
+    enc.encode_ids(ids[:1, : min(3, s)], np.ones((1, min(3, s)), np.int32))
+    ids2 = np.where(mask == 1, ids, 777).astype(np.int32)
+    assert np.abs(enc.encode_ids(ids2, mask) - got).max() < 1e-6
+
+
+def test_query_path_fully_masked_sequence_and_device_io():
+    model, cfg = be.make_model("minilm-l6", seed=0)
+    ids, mask = be.make_inputs(3, 12, seed=5)
+    enc = _encoder(model, cfg, "mean")
+    got = enc.encode_ids_torch(torch.from_numpy(ids).cuda(), torch.from_numpy(mask).cuda())
+    torch.cuda.synchronize()
+    assert enc.last_launches() == 1
+    _compare(got.cpu().numpy(), be.encode(model, ids, mask, "mean"))
+    # a sequence whose mask is all zero: finite output (zero vector), the other rows unchanged
+    mask2 = mask.copy()
+    mask2[1] = 0
+    got2 = enc.encode_ids(ids, mask2)
+    assert np.isfinite(got2).all()
+    assert np.abs(got2[[0, 2]] - got.cpu().numpy()[[0, 2]]).max() < 1e-6
+    enc.set_fused(False)
+    assert np.abs(enc.encode_ids(ids, mask2) - got2).max() < 2e-4
 
 
 def test_encoder_matches_committed_golden_vectors():
