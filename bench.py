@@ -654,6 +654,21 @@ def encoder_numbers(dev, cpu: bool):
             flops = 2.0 * b * sl * g["num_hidden_layers"] * (4 * g["hidden_size"] ** 2 + 2 * g["hidden_size"] * g["intermediate_size"])
             entry[label] = {"ms_per_call": round(ms, 4), "sentences_per_s": round(b / (ms / 1e3), 1),
                             "gemm_tflops": round(flops / (ms / 1e3) / 1e12, 2), "launches": enc.last_launches()}
+            if b == 1:
+                # the query path is a weight read: fraction of the HBM roofline, and the layered kernels beside it
+                wbytes = 2.0 * g["num_hidden_layers"] * (4 * g["hidden_size"] ** 2 + 2 * g["hidden_size"] * g["intermediate_size"])
+                entry[label]["weight_read_hbm_frac"] = round(wbytes / (ms / 1e3) / 1e9 / load_peaks()["hbm_gbs"], 4)
+                enc.set_fused(False)
+                for _ in range(3):
+                    enc.encode_ids_torch(ids, mask)
+                e0.record()
+                for _ in range(iters):
+                    enc.encode_ids_torch(ids, mask)
+                e1.record()
+                torch.cuda.synchronize()
+                entry[label]["layered_kernels_ms_per_call"] = round(e0.elapsed_time(e1) / iters, 4)
+                entry[label]["layered_kernels_launches"] = enc.last_launches()
+                enc.set_fused(True)
         # host API, one query text per call (numpy ids in, numpy vector out; copies inside the timing)
         ids_h = np.random.default_rng(0).integers(1000, 30000, (1, 16)).astype(np.int32)
         mask_h = np.ones((1, 16), dtype=np.int32)

@@ -162,6 +162,9 @@ bool fused_applies(const lxg_encoder* e, int tokens) {
   if (e->fused_state != 1 || tokens > kFusedMaxTokens) return false;
   const int tpad = (tokens + 15) / 16 * 16;
   const int H = e->w.hidden, dh = H / e->w.heads;
+  // measured cross-over with the layered kernels (profiles/r2e_encoder_query.json): the per-phase cost
+  // of the single kernel grows with the rows every CTA normalises; H >= 768 only wins up to 32 tokens
+  if (H > 512 && tokens > 32) return false;
   return fused_fixed_smem(tpad, H, dh) + 3 * static_cast<size_t>(kFusedSlotBytes) <= kFusedSmemLimit;
 }
 
