@@ -390,6 +390,10 @@ def run_workload(key, wl, args, dev, rank, world, peaks, sharded, cpu_baseline, 
         if ent:
             fresh = ent.get("scan_sha") == scan_source_sha()
             roof["traffic"] = ent["bytes"] if fresh else None
+            if fresh and "tensor_pipe_active_pct_of_elapsed" in ent:
+                # same capture: sm__pipe_tensor_cycles_active (% of elapsed cycles, at the clock the capture ran at)
+                roof["ncu_tensor_pipe_active_pct"] = ent["tensor_pipe_active_pct_of_elapsed"]
+                roof["ncu_sm_clock_ghz"] = ent.get("sm_clock_ghz_under_ncu")
             roof["traffic_source"] = ("static ncu --set full capture %s (%s), same kernel sources" % (ent["file"], ent["date"])
                                       if fresh else "stale: %s was captured on other kernel sources" % ent["file"])
     res["roofline"] = roof

@@ -27,7 +27,7 @@ for step in "$@"; do
       n=${rest%%:*}; a=""; [[ "$rest" == *:* ]] && a=${rest#*:}
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n $a > $OUT/${TAG}_bench_n${n}_$i.json 2> $OUT/${TAG}_bench_n${n}_$i.err; echo "benchN rc=$?"; tail -c 1500 $OUT/${TAG}_bench_n${n}_$i.json; echo ;;
     launches)
-      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $OUT/${TAG}_launches_$i.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline --no-parity --no-sustained $rest > $OUT/${TAG}_launches_$i.log 2>&1; echo "launches rc=$?"
+      timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k "regex:scan_topk|merge_|prep_queries|exact_|normalize_l2|make_scan|bert_fused|gemm_|attention_|rmsnorm|layernorm|embed_|pool_|qk_norm|last_token" -c 400 --csv --log-file $OUT/${TAG}_launches_$i.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline --no-parity --no-sustained $rest > $OUT/${TAG}_launches_$i.log 2>&1; echo "launches rc=$?"
       python scripts/ncu_launches.py $OUT/${TAG}_launches_$i.csv > $OUT/${TAG}_launches_$i.txt 2>&1; tail -12 $OUT/${TAG}_launches_$i.txt ;;
     ncu)
       kern=${rest%%:*}; a=${rest#*:}

@@ -82,6 +82,34 @@ def test_reranker_scores_match_hf_oracle(geom, b, s):
     assert np.abs(swapped + dec.rerank_ids(ids, mask, TOKEN_TRUE, TOKEN_FALSE) - 1).max() < 1e-5
 
 
+@pytest.mark.parametrize("scale", [4.0, 8.0])
+def test_large_activations_near_the_fp16_range(scale):
+    """Real Qwen3 checkpoints carry large-magnitude channels; the random-init models above do not.
+    Scale the MLP input projections (gate / up) and a few residual channels so that SwiGLU outputs and
+    the residual stream run far above the init_std = 0.05 regime, and require the same tolerances.
+    The product keeps SwiGLU outputs and GEMM operands in fp16 - this is the
+    test that says how much head-room that leaves."""
+    from lean_explore_b200.decoder import Qwen3Decoder
+
+    model, cfg = qd.make_model("small", seed=2)
+    with torch.no_grad():
+        for layer in model.model.layers:
+            layer.mlp.gate_proj.weight.mul_(scale)
+            layer.mlp.up_proj.weight.mul_(scale)
+        model.model.embed_tokens.weight[:, :4].mul_(40.0)  # a few "massive" residual channels
+    dec = Qwen3Decoder(model.state_dict(), hidden=cfg.hidden_size, layers=cfg.num_hidden_layers,
+                       heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads, ffn=cfg.intermediate_size,
+                       head_dim=cfg.head_dim, rms_eps=cfg.rms_norm_eps, rope_theta=1e6)
+    ids, mask = qd.make_inputs(4, 48, seed=9, side="left")
+    with torch.no_grad():  # how large the oracle's SwiGLU outputs actually get (reported on failure)
+        hs = model.model(input_ids=torch.from_numpy(ids).long(), attention_mask=torch.from_numpy(mask).long(),
+                         output_hidden_states=True).hidden_states
+        peak = max(float(h.abs().max()) for h in hs)
+    assert peak > 50.0, f"the stress model is not stressing anything (peak |h| = {peak})"
+    _compare_emb(dec.embed_ids(ids, mask), qd.embed(model, ids, mask))
+    _compare_scores(dec.rerank_ids(ids, mask, TOKEN_TRUE, TOKEN_FALSE), qd.rerank(model, ids, mask, TOKEN_TRUE, TOKEN_FALSE))
+
+
 def test_matches_committed_golden_vectors():
     z = np.load(GOLDEN)
     for key in sorted({k.split("/")[0] for k in z.files}):

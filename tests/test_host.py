@@ -6,6 +6,8 @@ import asyncio
 import json
 import sqlite3
 
+from pathlib import Path
+
 import numpy as np
 import pytest
 
@@ -85,6 +87,22 @@ def test_ivfflat_index_file_reconstructs_label_order(tmp_path, nlist, sparse):
     got, info = lc.read_index_matrix(p)
     assert info["kind"] == "IwFl" and info["nlist"] == nlist and info["ntotal"] == 300
     assert np.array_equal(got, mat)
+
+
+@pytest.mark.parametrize("name,rows,kind,nprobe", [("faiss_ivfflat_23x8.index", 23, "IwFl", 64),
+                                                   ("faiss_ivfflat_sparse_7x8.index", 7, "IwFl", 1),
+                                                   ("faiss_flat_23x8.index", 23, "IxFI", None)])
+def test_committed_faiss_file_bytes_written_independently_of_this_package(name, rows, kind, nprobe):
+    """tests/golden/*.index were assembled field by field from FAISS' published serialisation order
+    (faiss/impl/index_write.cpp) by tests/golden/make_faiss_file_golden.py, which does not import this
+    package: the reader is no longer checked only against its own writer.  They exercise an Array
+    direct map with entries, "full" and "sprs" list sizes, empty lists and unsorted labels in a list."""
+    golden = Path(__file__).resolve().parent / "golden"
+    want = np.load(golden / "faiss_file_vectors_23x8.npy")[:rows]
+    got, info = lc.read_index_matrix(golden / name)
+    assert info["kind"] == kind and info["ntotal"] == rows and info["d"] == 8 and info["metric_type"] == 0
+    assert info.get("nprobe") == nprobe
+    assert got.dtype == np.float32 and np.array_equal(got, want)
 
 
 def test_index_file_errors(tmp_path):
