@@ -153,6 +153,8 @@ int lxg_debug_scores(lxg_index* index, const float* x_dev, int32_t nq, int norma
  * shape (each argument: 0 / 1 sets, -1 leaves unchanged).  no_level: never use the cross-list
  * level (thresholds from list compaction only); force_single: never pair CTAs (cta_group::1
  * only); perf_mode: see LXG_SCAN_PERF_MODE in DESIGN.md (results are NOT produced when != 0).
+ * perf_mode 16 / 17 only switch the three-stage merge of small batches off / on (results are
+ * identical either way; LXG_MERGE_SPLIT=0 in the environment does the same).
  * The same switches are read from the environment (LXG_SCAN_NOLEVEL, LXG_SCAN_SINGLE,
  * LXG_SCAN_PERF_MODE) by lxg_init. */
 int lxg_debug_config(int no_level, int force_single, int perf_mode);

@@ -37,6 +37,8 @@ static int g_sync_mb = 28;           // LXG_SCAN_SYNC_MB: L2 megabytes the reade
 static bool g_zero_copy = true;      // LXG_ZERO_COPY=0: pinned host queries / results go through staging copies
 static bool g_sync_readers = true;   // LXG_SCAN_SYNC=0: the readers of a corpus slice are not kept in step (A/B)
 static bool g_force_single = false;  // LXG_SCAN_SINGLE=1: never pair CTAs (A/B measurements, tests)
+static bool g_no_split_merge = false;  // LXG_MERGE_SPLIT=0 / lxg_debug_config perf_mode 16: small batches keep the one-kernel merge
+constexpr int kSplitMergeQueries = 8;  // up to this many queries with k' >= 256 run the merge in three stages (rescore.cuh)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -382,6 +384,8 @@ int lxg_init(int device) {
   g_asmem_768 = !(am && am[0] == '0');
   const char* nl = std::getenv("LXG_SCAN_NOLEVEL");
   g_no_level = nl && nl[0] == '1';
+  const char* ms = std::getenv("LXG_MERGE_SPLIT");
+  g_no_split_merge = ms && ms[0] == '0';
   const char* pm = std::getenv("LXG_SCAN_PERF_MODE");
   g_perf_mode = pm ? std::atoi(pm) : 0;
   g_inited = true;
@@ -391,6 +395,10 @@ int lxg_init(int device) {
 int lxg_debug_config(int no_level, int force_single, int perf_mode) {
   if (no_level >= 0) g_no_level = no_level != 0;
   if (force_single >= 0) g_force_single = force_single != 0;
+  if (perf_mode == 16 || perf_mode == 17) {
+    g_no_split_merge = perf_mode == 16;  // 16: one-kernel merge for every batch size, 17: back to the default
+    return LXG_OK;
+  }
   if (perf_mode >= 0) g_perf_mode = perf_mode;
   return LXG_OK;
 }
@@ -599,6 +607,14 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   constexpr int kProgWords = 1024;
   const size_t o_flags = take(256 + kProgWords * sizeof(int));
   const size_t o_lvl = take(lists * sizeof(uint32_t));
+  // split merge (a handful of queries, large k): selected rows and their exact scores between the stages
+  int sort_n = 1;
+  while (sort_n < pl.kp) sort_n <<= 1;
+  const bool split_merge = nq <= kSplitMergeQueries && pl.kp >= 256 && !g_no_split_merge;
+  const size_t o_selrow = take(split_merge ? static_cast<size_t>(nq) * sort_n * sizeof(unsigned) : 0);
+  const size_t o_selscore = take(split_merge ? static_cast<size_t>(nq) * sort_n * sizeof(double) : 0);
+  const size_t o_seln = take(split_merge ? nq * sizeof(int) : 0);
+  const size_t o_selamin = take(split_merge ? nq * sizeof(float) : 0);
   LXG_CUDA(ix->ws_small.reserve(off));
   // normalised fp32 queries, then the prepared fp16 query blocks
   const size_t xn_bytes = (static_cast<size_t>(nq) * d * sizeof(float) + 255) / 256 * 256;
@@ -727,13 +743,25 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.lists = pl.lists;
   mp.lvl_slots = pl.lvl_slots;
   mp.max_items = pl.max_items;
-  int sort_n = 1;
-  while (sort_n < pl.kp) sort_n <<= 1;
   mp.sort_n = sort_n;
+  mp.stage = 0;
+  mp.sel_row_g = reinterpret_cast<unsigned*>(sm + o_selrow);
+  mp.sel_score_g = reinterpret_cast<double*>(sm + o_selscore);
+  mp.sel_n_g = reinterpret_cast<int*>(sm + o_seln);
+  mp.sel_amin_g = reinterpret_cast<float*>(sm + o_selamin);
   const size_t msmem = static_cast<size_t>(pl.max_items) * 8 + static_cast<size_t>(sort_n) * 12 +
                        static_cast<size_t>(d) * 4 + 64;
   // one CTA per query, sized by the batch (see rescore.cuh)
-  if (nq <= 64) LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
+  if (split_merge) {
+    // select (one CTA per query) -> exact re-score on every SM -> rank + certify
+    mp.stage = 1;
+    LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
+    rescore_rows_kernel<<<dim3(sort_n / 32, nq), 256, d * sizeof(float), st>>>(mp, ix->cv);
+    LXG_CUDA(cudaGetLastError());
+    mp.stage = 2;
+    LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
+    launches += 2;
+  } else if (nq <= 64) LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
   else if (nq <= 512) LXG_CUDA((launch_merge<256>(nq, msmem, mp, ix->cv, st)));
   else LXG_CUDA((launch_merge<128>(nq, msmem, mp, ix->cv, st)));
   LXG_CUDA(cudaGetLastError());

@@ -48,6 +48,15 @@ struct MergeParams {
   int nq, k, kp, cap, lists, lvl_slots;
   int max_items;       // capacity of the shared-memory candidate pool
   int sort_n;          // kp rounded up to a power of two (bitonic ranking of the re-scored rows)
+  // A handful of queries with a large k (the engine's own request: one query, faiss_k = 1000): the exact
+  // re-score of ~k' rows of 2-4 KB is the work of one CTA for ~0.1 ms, so the kernel is run in three
+  // stages - 1: select the rows (this kernel, returns after writing them to sel_row_g), 2: re-score them
+  // with every SM (rescore_rows_kernel), 3: rank + certify (this kernel again).  stage 0 = all in one.
+  int stage;
+  unsigned* sel_row_g;   // [nq, sort_n]
+  double* sel_score_g;   // [nq, sort_n]
+  int* sel_n_g;          // [nq] rows selected, or -1 when stage 1 already finished the query
+  float* sel_amin_g;     // [nq] largest tensor-core score a dropped row can have (stage 1 -> 3)
 };
 
 // Exact inner products of R corpus rows with a query held in shared memory, computed by a full
@@ -161,6 +170,20 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   }
   for (int i = tid; i < cv.d; i += kMergeThreads) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
   __syncthreads();
+  int nsel = 0;
+  float a_min = -CUDART_INF_F;
+  if (p.stage == 2) {
+    // stage 3 of the split run: the rows were selected by stage 1 and re-scored by rescore_rows_kernel
+    nsel = p.sel_n_g[q];
+    if (nsel < 0) return;  // zero query / handed to the exact path: finished in stage 1
+    a_min = p.sel_amin_g[q];
+    for (int j = tid; j < nsel; j += kMergeThreads) {
+      sel_row[j] = p.sel_row_g[static_cast<size_t>(q) * p.sort_n + j];
+      sel_score[j] = p.sel_score_g[static_cast<size_t>(q) * p.sort_n + j];
+    }
+    __syncthreads();
+  } else {
+  if (p.stage == 1 && tid == 0) p.sel_n_g[q] = -1;  // until the selection below completes
   if (p.qnorm[q] == 0.0f) {
     // all-zero query (normalize_L2 leaves it untouched): every inner product is exactly 0, so the
     // answer is the k lowest row ids.  Pass 1 keeps no candidates for it (every score ties with
@@ -232,27 +255,75 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     __syncthreads();
     m = s_m;
     if (m <= p.max_items || attempt == 1) break;
-    // ---- tighten: largest prefix with count(key >= prefix) >= kp, stopping as soon as that
-    // count fits the pool (three rotating counters: one barrier per step)
+    // ---- tighten: a prefix with count(key >= prefix) >= kp whose count fits the pool, by radix
+    // histograms over the lists in global memory: 12 + 12 + 8 key bits per pass, stopping at the first
+    // pass whose boundary bin fits (normally the first or second).  The histogram aliases the pool,
+    // which is refilled afterwards.
     uint32_t prefix = 0u;
-    int cur = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-      const uint32_t cnd = prefix | (1u << bit);
-      int mine = 0;
-      for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
-        const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
-        const int c = s_len[s];
-        for (int i = lane; i < c; i += 32) mine += (float_to_key(__ldcg(lst + i).x) >= cnd) ? 1 : 0;
-      }
-      mine = __reduce_add_sync(0xffffffffu, mine);
-      if (lane == 0 && mine) atomicAdd(&s_cnt[cur], mine);
-      __syncthreads();
-      const int ge = s_cnt[cur];
-      if (tid == 0) s_cnt[(cur + 2) % 3] = 0;
-      cur = (cur + 1) % 3;
-      if (ge >= p.kp) {
-        prefix = cnd;
-        if (ge <= p.max_items) break;
+    {
+      int* hist = reinterpret_cast<int*>(items);
+      int above = 0;  // keys above the bin range still being resolved
+      int shift = 20, nbits = 12;
+      for (int pass = 0; pass < 3; ++pass) {
+        const int nbins = 1 << nbits;
+        for (int i = tid; i < nbins; i += kMergeThreads) hist[i] = 0;
+        __syncthreads();
+        const int hs = shift + nbits;  // bits above the pass's digit must equal the prefix
+        for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
+          const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
+          const int c = s_len[s];
+          for (int i = lane; i < c; i += 32) {
+            const uint32_t key = float_to_key(__ldcg(lst + i).x);
+            if (hs >= 32 || (key >> hs) == (prefix >> hs)) atomicAdd(&hist[(key >> shift) & (nbins - 1)], 1);
+          }
+        }
+        __syncthreads();
+        // highest bin b with above + sum(hist[b ..]) >= kp (warp 0: lane owns nbins / 32 bins)
+        if (warp == 0) {
+          const int per = nbins / 32;
+          int mine = 0;
+          for (int i = 0; i < per; ++i) mine += hist[lane * per + i];
+          int suffix = mine;  // inclusive suffix sum over lanes
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_down_sync(0xffffffffu, suffix, o);
+            if (lane + o < 32) suffix += v;
+          }
+          const int need = p.kp - above;
+          const uint32_t ok = __ballot_sync(0xffffffffu, suffix >= need);
+          if (ok == 0u) {
+            if (lane == 0) {  // fewer than kp entries in total: keep everything
+              s_cnt[0] = -1;
+              s_cnt[1] = 0;
+              s_cnt[2] = 0;
+            }
+          } else {
+            const int owner = 31 - __clz(ok);
+            if (lane == owner) {
+              int run = suffix - mine;  // entries in the lanes above this one
+              int b = per - 1;
+              for (; b > 0; --b) {
+                if (run + hist[lane * per + b] >= need) break;
+                run += hist[lane * per + b];
+              }
+              s_cnt[0] = lane * per + b;       // boundary bin
+              s_cnt[1] = run;                  // entries in the bins above it (this pass)
+              s_cnt[2] = hist[lane * per + b]; // entries in it
+            }
+          }
+        }
+        __syncthreads();
+        const int bin = s_cnt[0], over = s_cnt[1], inbin = s_cnt[2];
+        __syncthreads();
+        if (bin < 0) {
+          prefix = 0u;
+          break;
+        }
+        prefix |= static_cast<uint32_t>(bin) << shift;
+        if (above + over + inbin <= p.max_items) break;  // count(key >= prefix) fits the pool
+        above += over;
+        nbits = pass == 0 ? 12 : 8;
+        shift -= nbits;
       }
     }
     __syncthreads();
@@ -290,7 +361,7 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   uint32_t cut = 0;
   int need_eq = 0x7fffffff;
   // approx score no dropped row can exceed (scaled units)
-  float a_min = fmaxf(__uint_as_float(key_to_float_bits(s_tkey)), tau);
+  a_min = fmaxf(__uint_as_float(key_to_float_bits(s_tkey)), tau);
   if (m > p.kp) {
     kmin = s_kmin;
     kmax = s_kmax;
@@ -345,7 +416,15 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     if (take) sel_row[atomicAdd(&s_sel, 1)] = e.y;
   }
   __syncthreads();
-  const int nsel = s_sel;  // == min(m, kp)
+  nsel = s_sel;  // == min(m, kp)
+  if (p.stage == 1) {
+    for (int j = tid; j < nsel; j += kMergeThreads) p.sel_row_g[static_cast<size_t>(q) * p.sort_n + j] = sel_row[j];
+    if (tid == 0) {
+      p.sel_n_g[q] = nsel;
+      p.sel_amin_g[q] = a_min;
+    }
+    return;
+  }
   // exact re-score: four rows in flight per warp (the rows are random gathers from HBM)
   for (int j0 = warp * 4; j0 < nsel; j0 += (kMergeThreads / 32) * 4) {
     long long rows[4];
@@ -358,6 +437,7 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
       if (lane == 0 && j0 + u < nsel) sel_score[j0 + u] = acc[u];
   }
   __syncthreads();
+  }  // stage != 2
   // rank the re-scored rows by (score desc, row asc): bitonic sort in shared memory (padding
   // entries sort last), then the first k are the answer
   const int k = p.k;
@@ -420,6 +500,30 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
       p.flag_theta[slot] = theta;
     }
   }
+}
+
+// Stage 2 of the split merge: exact scores of the rows stage 1 selected, 32 rows per CTA (8 warps x 4
+// rows in flight), grid = (sort_n / 32, nq) - the gathers of one query are spread over every SM.  Same
+// warp_exact_dots as the one-kernel path: identical bits.
+static __global__ void __launch_bounds__(256) rescore_rows_kernel(const MergeParams p, const CorpusView cv) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  float* xq = reinterpret_cast<float*>(rsm);
+  const int q = blockIdx.y;
+  const int nsel = p.sel_n_g[q];
+  const int j0 = blockIdx.x * 32 + (threadIdx.x >> 5) * 4;
+  if (blockIdx.x * 32 >= nsel) return;
+  for (int i = threadIdx.x; i < cv.d; i += 256) xq[i] = p.xn[static_cast<size_t>(q) * cv.d + i];
+  __syncthreads();
+  if (j0 >= nsel) return;
+  const unsigned* rows_g = p.sel_row_g + static_cast<size_t>(q) * p.sort_n;
+  long long rows[4];
+  double acc[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) rows[u] = static_cast<long long>(rows_g[min(j0 + u, nsel - 1)]);
+  warp_exact_dots<4>(cv, rows, xq, threadIdx.x & 31, acc);
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+    if ((threadIdx.x & 31) == 0 && j0 + u < nsel) p.sel_score_g[static_cast<size_t>(q) * p.sort_n + j0 + u] = acc[u];
 }
 
 // ---------------------------------------------------------------------------------------

@@ -228,6 +228,48 @@ def test_every_scan_mode_returns_the_same_exact_result(scan_modes):
             assert np.array_equal(I, want[1]) and np.array_equal(D, want[0])
 
 
+@pytest.mark.parametrize("n,d,nq,k,dtype", [(60000, 384, 1, 1000, np.float16), (40000, 1024, 1, 1000, np.float32),
+                                           (30000, 256, 5, 400, np.float16), (3000, 128, 8, 2048, np.float32),
+                                           (50000, 64, 2, 300, np.float16)])
+def test_few_queries_large_k_three_stage_merge(n, d, nq, k, dtype):
+    """The engine's own request (one query, faiss_k = 1000, engine.py:538) and its neighbours: up to 8
+    queries with k' >= 256 run the merge as select -> re-score on every SM -> rank.  Exact ids
+    against the oracle, and bit-identical results (scores included) to the one-kernel merge."""
+    from lean_explore_b200 import _lib
+
+    lib = _lib.init(0)
+    corpus = make_corpus(n, d, dtype=dtype)
+    x = make_queries(nq, d)
+    x[nq // 2] *= 37.0  # un-normalised queries: the fused normalise is part of the call
+    ix = _check(corpus, x, k)
+    D3, I3 = ix.search(x, k, normalize=True)
+    assert ix.last_stats()["kernel_launches"] == 7  # prep, scan, 3 merge stages, 2 exact-path kernels
+    try:
+        _lib.check(lib.lxg_debug_config(-1, -1, 16))
+        D1, I1 = ix.search(x, k, normalize=True)
+        assert ix.last_stats()["kernel_launches"] == 5
+    finally:
+        _lib.check(lib.lxg_debug_config(-1, -1, 17))
+    assert np.array_equal(I1, I3) and np.array_equal(D1, D3)
+
+
+def test_three_stage_merge_zero_query_duplicates_and_sorted_corpus():
+    """Paths of stage 1 that finish a query by themselves (all-zero query; more near-ties than the pool
+    holds -> exact path) and a row order that overflows the pool (radix tightening of the level)."""
+    rng = np.random.default_rng(3)
+    corpus = make_corpus(40000, 128)
+    # rows sorted by their score against query 0: every list keeps appending, the pool overflows
+    x = make_queries(3, 128)
+    order = np.argsort(corpus.astype(np.float32) @ x[0])
+    corpus = np.ascontiguousarray(corpus[order])
+    x[1] = 0.0
+    _check(corpus, x, 600)
+    dup = make_corpus(20000, 96)
+    dup[5000:9000] = dup[4999]  # 4001 identical rows: ties far beyond k
+    x2 = np.stack([dup[4999].astype(np.float32) + 0.01 * rng.standard_normal(96).astype(np.float32), make_queries(1, 96)[0]])
+    _check(dup, x2, 500)
+
+
 @pytest.mark.parametrize("d", [64, 768, 1024])
 def test_adversarial_row_order_overflows_the_lists(d):
     """Rows sorted by ascending score for the probe query: every tile beats everything seen before,
