@@ -23,7 +23,8 @@ ONE NCCL all-gather of the packed per-shard candidates -> lxg_merge_topk_packed)
   cpu_baseline / --impl reference: the FAISS restatement (numpy sgemm + FAISS-style heaps, oracle/)
             on this box's host cores.
   extra     (N = 1 only) the same block for cfg3 (2M x 768, the north star's >= 10k QPS / >= 60 % target)
-            and cfg2 (500k x 384), the query-batch sweep, the shape of the shipped index
+            and cfg2 (500k x 384), cfg1 (50k x 384 fp32, top-10 - the reference's own CPU-sized case), the query-batch
+            sweep, the shape of the shipped index
             (400k x 1024 fp32, one query with faiss_k = 1000), the BERT-class encoders and the Qwen3
             embedding model / reranker through their host APIs, each with its CPU leg.
 
@@ -366,11 +367,12 @@ def run_workload(key, wl, args, dev, rank, world, peaks, sharded, cpu_baseline, 
     calls = max(1, tm["calls"])
     scan_ms = tm["scan_ms"] / calls
     flops = 2.0 * q * rows_local * d
-    bytes_alg = rows_local * d * 2 + q * d * 4 + q * k * 12
+    esize = 2 if wl["dtype"] == "float16" else 4  # bytes per stored corpus element
+    bytes_alg = rows_local * d * esize + q * d * 4 + q * k * 12
     tf = flops / (scan_ms / 1e3) / 1e12
     gbs = bytes_alg / (scan_ms / 1e3) / 1e9
     tensor_frac, hbm_frac = tf / peaks["tflops"], gbs / peaks["hbm_gbs"]
-    ridge_q = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9)  # fp16: flop/byte == Q
+    ridge_q = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9) * esize / 2  # flop/byte == 2 Q / esize
     if q >= ridge_q:
         roof = dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tflops"], unit="TFLOP/s", frac=round(tensor_frac, 4))
     else:
@@ -538,7 +540,7 @@ def main():
         extra = out["extra"] = {}
         del index, corpus, res  # release the 24.6 GB corpus
         torch.cuda.empty_cache()
-        for key in ("cfg3", "cfg2"):
+        for key in ("cfg3", "cfg2", "cfg1"):
             try:
                 w2 = dict(WORKLOADS[key])
                 r2 = run_workload(key, w2, args, dev, 0, 1, peaks, sharded=False,
@@ -546,8 +548,11 @@ def main():
                 ix2 = r2.pop("_index")
                 r2.pop("_corpus")
                 r2.pop("_rows_local")
+                cbytes = w2["n"] * w2["d"] * (2 if w2["dtype"] == "float16" else 4)
                 r2["config"] = {"workload": w2["name"], "corpus_rows": w2["n"], "d": w2["d"], "k": w2["k"],
-                                "queries_per_step": w2["q"], "steps": args.steps}
+                                "queries_per_step": w2["q"], "steps": args.steps, "corpus_dtype": w2["dtype"],
+                                "l2_policy": ("corpus (%.0f MB) larger than L2; 4 rotating query batches" % (cbytes / 1e6)) if cbytes > 126e6
+                                else ("corpus (%.0f MB) fits the 126 MB L2 - the size BASELINE.json specifies; 4 rotating query batches" % (cbytes / 1e6))}
                 extra[key] = r2
                 if key == "cfg2":
                     extra["cfg2 query-batch sweep"] = extra_numbers(ix2, w2["d"], w2["k"], dev, peaks)
