@@ -744,7 +744,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.lvl_slots = pl.lvl_slots;
   mp.max_items = pl.max_items;
   mp.sort_n = sort_n;
-  mp.stage = 0;
+  mp.select_only = 0;
   mp.sel_row_g = reinterpret_cast<unsigned*>(sm + o_selrow);
   mp.sel_score_g = reinterpret_cast<double*>(sm + o_selscore);
   mp.sel_n_g = reinterpret_cast<int*>(sm + o_seln);
@@ -753,13 +753,13 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
                        static_cast<size_t>(d) * 4 + 64;
   // one CTA per query, sized by the batch (see rescore.cuh)
   if (split_merge) {
-    // select (one CTA per query) -> exact re-score on every SM -> rank + certify
-    mp.stage = 1;
+    // select (one CTA per query) -> exact re-score on every SM -> rank + certify (rescore.cuh)
+    mp.select_only = 1;
     LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
     rescore_rows_kernel<<<dim3(sort_n / 32, nq), 256, d * sizeof(float), st>>>(mp, ix->cv);
     LXG_CUDA(cudaGetLastError());
-    mp.stage = 2;
-    LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
+    rank_rows_kernel<<<dim3((sort_n + 31) / 32, nq), 256, static_cast<size_t>(sort_n) * 12, st>>>(mp, ix->cv);
+    LXG_CUDA(cudaGetLastError());
     launches += 2;
   } else if (nq <= 64) LXG_CUDA((launch_merge<1024>(nq, msmem, mp, ix->cv, st)));
   else if (nq <= 512) LXG_CUDA((launch_merge<256>(nq, msmem, mp, ix->cv, st)));

@@ -48,11 +48,11 @@ struct MergeParams {
   int nq, k, kp, cap, lists, lvl_slots;
   int max_items;       // capacity of the shared-memory candidate pool
   int sort_n;          // kp rounded up to a power of two (bitonic ranking of the re-scored rows)
-  // A handful of queries with a large k (the engine's own request: one query, faiss_k = 1000): the exact
-  // re-score of ~k' rows of 2-4 KB is the work of one CTA for ~0.1 ms, so the kernel is run in three
-  // stages - 1: select the rows (this kernel, returns after writing them to sel_row_g), 2: re-score them
-  // with every SM (rescore_rows_kernel), 3: rank + certify (this kernel again).  stage 0 = all in one.
-  int stage;
+  // A handful of queries with a large k (the engine's own request: one query, faiss_k = 1000): gathering,
+  // re-scoring (~k' rows of 2-4 KB) and ranking inside one CTA takes ~0.2 ms, so the merge runs as three
+  // kernels instead - this one with select_only (one CTA per query, returns after the selection),
+  // rescore_rows_kernel (every SM), rank_rows_kernel (rank by counting, k'/64 CTAs per query) - handing over through:
+  int select_only;
   unsigned* sel_row_g;   // [nq, sort_n]
   double* sel_score_g;   // [nq, sort_n]
   int* sel_n_g;          // [nq] rows selected, or -1 when stage 1 already finished the query
@@ -140,6 +140,85 @@ __device__ __forceinline__ double warp_exact_dot(const CorpusView& cv, long long
 __device__ __forceinline__ bool better(double sa, unsigned ia, double sb, unsigned ib) {
   return sa > sb || (sa == sb && ia < ib);
 }
+// The rankings compare scores as order-preserving 64-bit integer keys: fp64 compares issue at a small
+// fraction of the integer rate on this part, and a ranking is nothing but compares.  -0.0 is folded
+// into +0.0 first so that equal scores have equal keys.
+__device__ __forceinline__ unsigned long long score_key(double x) {
+  const unsigned long long b = static_cast<unsigned long long>(__double_as_longlong(x + 0.0));
+  return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_score(unsigned long long k) {
+  return __longlong_as_double(static_cast<long long>((k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k));
+}
+__device__ __forceinline__ bool better_key(unsigned long long ka, unsigned ia, unsigned long long kb, unsigned ib) {
+  return ka > kb || (ka == kb && ia < ib);
+}
+
+// Walks every entry of every candidate list of query q with a warp per PAIR of lists and two 32-entry
+// chunks of each in flight (four independent L2 loads per lane): the lists are short (tens of entries),
+// so a walk is a chain of dependent round trips and their number is what it costs.  f(entry, valid) is
+// called warp-uniformly (it may use ballots).
+template <int kThreads, class F>
+__device__ __forceinline__ void for_each_list_entry(const MergeParams& p, int q, const int* s_len, int warp, int lane, F&& f) {
+  constexpr int kWarps = kThreads / 32;
+  for (int s0 = warp; s0 < p.lists; s0 += 2 * kWarps) {
+    const int s1 = s0 + kWarps;
+    const bool two = s1 < p.lists;
+    const uint2* l0 = p.cand + (static_cast<size_t>(s0) * p.nq + q) * p.cap;
+    const uint2* l1 = p.cand + (static_cast<size_t>(two ? s1 : s0) * p.nq + q) * p.cap;
+    const int c0 = s_len[s0], c1 = two ? s_len[s1] : 0;
+    for (int i0 = 0; i0 < max(c0, c1); i0 += 64) {
+      uint2 e[4];
+      bool v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + (u & 1) * 32 + lane;
+        v[u] = i < (u < 2 ? c0 : c1);
+        e[u] = v[u] ? __ldcg((u < 2 ? l0 : l1) + i) : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) f(e[u], v[u]);
+    }
+  }
+}
+
+// Warp helper of the radix selections below: the highest bin b of hist[0, nbins) with
+// sum(hist[b ..]) >= need.  out[0] = b (-1: the whole histogram holds fewer than `need`), out[1] =
+// entries in the bins above b (or the total when b = -1), out[2] = hist[b].  nbins is a multiple of 32.
+__device__ __forceinline__ void radix_boundary_bin(const int* hist, int nbins, int need, int lane, int* out) {
+  const int per = nbins / 32;
+  int mine = 0;
+  // lane owns bins [lane * per, (lane + 1) * per); read rotated by the lane so that the 32 lanes hit 32
+  // different banks (per is a multiple of 32: unrotated, every lane would read the same bank)
+  for (int i = 0; i < per; ++i) mine += hist[lane * per + ((i + lane) & (per - 1))];
+  int suffix = mine;  // inclusive suffix sum over the lanes
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_down_sync(0xffffffffu, suffix, o);
+    if (lane + o < 32) suffix += v;
+  }
+  const int all = __shfl_sync(0xffffffffu, suffix, 0);
+  const uint32_t ok = __ballot_sync(0xffffffffu, suffix >= need);
+  if (ok == 0u) {
+    if (lane == 0) {
+      out[0] = -1;
+      out[1] = all;
+      out[2] = 0;
+    }
+    return;
+  }
+  if (lane == 31 - __clz(ok)) {
+    int run = suffix - mine;  // entries in the lanes above this one
+    int b = per - 1;
+    for (; b > 0; --b) {
+      if (run + hist[lane * per + b] >= need) break;
+      run += hist[lane * per + b];
+    }
+    out[0] = lane * per + b;
+    out[1] = run;
+    out[2] = hist[lane * per + b];
+  }
+}
 
 // One CTA (kMergeThreads threads) per query.  Dynamic shared memory: max_items (score key, row)
 // pairs, then kp (double,uint) pairs, then d floats.
@@ -172,18 +251,7 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   __syncthreads();
   int nsel = 0;
   float a_min = -CUDART_INF_F;
-  if (p.stage == 2) {
-    // stage 3 of the split run: the rows were selected by stage 1 and re-scored by rescore_rows_kernel
-    nsel = p.sel_n_g[q];
-    if (nsel < 0) return;  // zero query / handed to the exact path: finished in stage 1
-    a_min = p.sel_amin_g[q];
-    for (int j = tid; j < nsel; j += kMergeThreads) {
-      sel_row[j] = p.sel_row_g[static_cast<size_t>(q) * p.sort_n + j];
-      sel_score[j] = p.sel_score_g[static_cast<size_t>(q) * p.sort_n + j];
-    }
-    __syncthreads();
-  } else {
-  if (p.stage == 1 && tid == 0) p.sel_n_g[q] = -1;  // until the selection below completes
+  if (p.select_only && tid == 0) p.sel_n_g[q] = -1;  // "finished here" until the selection below completes
   if (p.qnorm[q] == 0.0f) {
     // all-zero query (normalize_L2 leaves it untouched): every inner product is exactly 0, so the
     // answer is the k lowest row ids.  Pass 1 keeps no candidates for it (every score ties with
@@ -224,34 +292,21 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   for (int attempt = 0; attempt < 2; ++attempt) {
     kmin = 0xFFFFFFFFu;
     kmax = 0u;
-    for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
-      const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
-      const int c = s_len[s];
-      for (int i0 = 0; i0 < c; i0 += 128) {
-        uint2 e[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int i = i0 + u * 32 + lane;
-          e[u] = i < c ? __ldcg(lst + i) : make_uint2(0u, 0u);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const uint32_t key = float_to_key(e[u].x);
-          const bool keep = (i0 + u * 32 + lane < c) && key >= tau_key;
-          const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-          if (bal == 0u) continue;
-          int base = 0;
-          if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          const int pos = base + __popc(bal & ((1u << lane) - 1u));
-          if (keep && pos < p.max_items) {
-            items[pos] = make_uint2(key, e[u].y);
-            kmin = min(kmin, key);
-            kmax = max(kmax, key);
-          }
-        }
+    for_each_list_entry<kMergeThreads>(p, q, s_len, warp, lane, [&](const uint2& e, bool valid) {
+      const uint32_t key = float_to_key(e.x);
+      const bool keep = valid && key >= tau_key;
+      const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+      if (bal == 0u) return;
+      int base = 0;
+      if (lane == 0) base = atomicAdd(&s_m, __popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      const int pos = base + __popc(bal & ((1u << lane) - 1u));
+      if (keep && pos < p.max_items) {
+        items[pos] = make_uint2(key, e.y);
+        kmin = min(kmin, key);
+        kmax = max(kmax, key);
       }
-    }
+    });
     __syncthreads();
     m = s_m;
     if (m <= p.max_items || attempt == 1) break;
@@ -269,49 +324,12 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
         for (int i = tid; i < nbins; i += kMergeThreads) hist[i] = 0;
         __syncthreads();
         const int hs = shift + nbits;  // bits above the pass's digit must equal the prefix
-        for (int s = warp; s < p.lists; s += kMergeThreads / 32) {
-          const uint2* lst = p.cand + (static_cast<size_t>(s) * p.nq + q) * p.cap;
-          const int c = s_len[s];
-          for (int i = lane; i < c; i += 32) {
-            const uint32_t key = float_to_key(__ldcg(lst + i).x);
-            if (hs >= 32 || (key >> hs) == (prefix >> hs)) atomicAdd(&hist[(key >> shift) & (nbins - 1)], 1);
-          }
-        }
+        for_each_list_entry<kMergeThreads>(p, q, s_len, warp, lane, [&](const uint2& e, bool valid) {
+          const uint32_t key = float_to_key(e.x);
+          if (valid && (hs >= 32 || (key >> hs) == (prefix >> hs))) atomicAdd(&hist[(key >> shift) & (nbins - 1)], 1);
+        });
         __syncthreads();
-        // highest bin b with above + sum(hist[b ..]) >= kp (warp 0: lane owns nbins / 32 bins)
-        if (warp == 0) {
-          const int per = nbins / 32;
-          int mine = 0;
-          for (int i = 0; i < per; ++i) mine += hist[lane * per + i];
-          int suffix = mine;  // inclusive suffix sum over lanes
-#pragma unroll
-          for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_down_sync(0xffffffffu, suffix, o);
-            if (lane + o < 32) suffix += v;
-          }
-          const int need = p.kp - above;
-          const uint32_t ok = __ballot_sync(0xffffffffu, suffix >= need);
-          if (ok == 0u) {
-            if (lane == 0) {  // fewer than kp entries in total: keep everything
-              s_cnt[0] = -1;
-              s_cnt[1] = 0;
-              s_cnt[2] = 0;
-            }
-          } else {
-            const int owner = 31 - __clz(ok);
-            if (lane == owner) {
-              int run = suffix - mine;  // entries in the lanes above this one
-              int b = per - 1;
-              for (; b > 0; --b) {
-                if (run + hist[lane * per + b] >= need) break;
-                run += hist[lane * per + b];
-              }
-              s_cnt[0] = lane * per + b;       // boundary bin
-              s_cnt[1] = run;                  // entries in the bins above it (this pass)
-              s_cnt[2] = hist[lane * per + b]; // entries in it
-            }
-          }
-        }
+        if (warp == 0) radix_boundary_bin(hist, nbins, p.kp - above, lane, s_cnt);
         __syncthreads();
         const int bin = s_cnt[0], over = s_cnt[1], inbin = s_cnt[2];
         __syncthreads();
@@ -366,7 +384,33 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     kmin = s_kmin;
     kmax = s_kmax;
     cut = kmax;
-    if (kmin != kmax) {
+    const int hist_ints = (p.sort_n * 12) / 4;  // sel_score / sel_row are not in use yet: room for the histogram
+    if (kmin != kmax && hist_ints >= 2048) {
+      // exact k'-th largest key by radix selection over the pool (12 + 12 + 8 or 11 + 11 + 10 key bits)
+      int* hist = reinterpret_cast<int*>(sel_score);
+      const int b1 = hist_ints >= 4096 ? 12 : 11;
+      int shift = 32 - b1, nbits = b1, above = 0;
+      uint32_t pre = 0u;
+      for (int pass = 0; pass < 3; ++pass) {
+        const int nbins = 1 << nbits;
+        for (int i = tid; i < nbins; i += kMergeThreads) hist[i] = 0;
+        __syncthreads();
+        const int hs = shift + nbits;
+        for (int i = tid; i < m; i += kMergeThreads) {
+          const uint32_t key = items[i].x;
+          if (hs >= 32 || (key >> hs) == (pre >> hs)) atomicAdd(&hist[(key >> shift) & (nbins - 1)], 1);
+        }
+        __syncthreads();
+        if (warp == 0) radix_boundary_bin(hist, nbins, p.kp - above, lane, s_cnt);
+        __syncthreads();
+        pre |= static_cast<uint32_t>(s_cnt[0]) << shift;  // m > kp: a boundary bin always exists
+        above += s_cnt[1];
+        __syncthreads();
+        nbits = pass == 0 ? b1 : 32 - 2 * b1;
+        shift -= nbits;
+      }
+      cut = pre;
+    } else if (kmin != kmax) {
       const int hb = 31 - __clz(kmin ^ kmax);
       cut = (hb == 31) ? 0u : (kmax & ~((2u << hb) - 1u));
       int cur = 0;  // three rotating counters: one barrier per step instead of three
@@ -417,7 +461,7 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   }
   __syncthreads();
   nsel = s_sel;  // == min(m, kp)
-  if (p.stage == 1) {
+  if (p.select_only) {  // three-kernel merge: the re-score and the ranking run on every SM
     for (int j = tid; j < nsel; j += kMergeThreads) p.sel_row_g[static_cast<size_t>(q) * p.sort_n + j] = sel_row[j];
     if (tid == 0) {
       p.sel_n_g[q] = nsel;
@@ -437,12 +481,13 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
       if (lane == 0 && j0 + u < nsel) sel_score[j0 + u] = acc[u];
   }
   __syncthreads();
-  }  // stage != 2
   // rank the re-scored rows by (score desc, row asc): bitonic sort in shared memory (padding
   // entries sort last), then the first k are the answer
   const int k = p.k;
+  unsigned long long* sel_key = reinterpret_cast<unsigned long long*>(sel_score);  // in place
+  for (int j = tid; j < nsel; j += kMergeThreads) sel_key[j] = score_key(sel_score[j]);
   for (int j = nsel + tid; j < p.sort_n; j += kMergeThreads) {
-    sel_score[j] = -CUDART_INF;
+    sel_key[j] = 0ull;  // below every real score
     sel_row[j] = 0xFFFFFFFFu;
   }
   __syncthreads();
@@ -452,11 +497,11 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
         const int lo = 2 * i - (i & (stride - 1));  // element whose `stride` bit is clear
         const int hi = lo + stride;
         const bool descending = (lo & size) == 0;
-        const double sl = sel_score[lo], sh = sel_score[hi];
+        const unsigned long long sl = sel_key[lo], sh = sel_key[hi];
         const unsigned rl = sel_row[lo], rh = sel_row[hi];
-        if (better(sh, rh, sl, rl) == descending) {
-          sel_score[lo] = sh;
-          sel_score[hi] = sl;
+        if (better_key(sh, rh, sl, rl) == descending) {
+          sel_key[lo] = sh;
+          sel_key[hi] = sl;
           sel_row[lo] = rh;
           sel_row[hi] = rl;
         }
@@ -465,12 +510,12 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
     }
   }
   for (int r = tid; r < min(k, nsel); r += kMergeThreads) {
-    const double sc = sel_score[r];
+    const double sc = key_score(sel_key[r]);
     p.out_d[static_cast<size_t>(q) * k + r] = static_cast<float>(sc);
     p.out_i[static_cast<size_t>(q) * k + r] = static_cast<long long>(sel_row[r]) + cv.row_offset;
     if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + r] = sc;
   }
-  if (tid == 0 && nsel >= k) s_kth = sel_score[k - 1];
+  if (tid == 0 && nsel >= k) s_kth = key_score(sel_key[k - 1]);
   for (int r = nsel + tid; r < k; r += kMergeThreads) {  // fewer than k rows: FAISS pads -FLT_MAX / -1
     p.out_d[static_cast<size_t>(q) * k + r] = -FLT_MAX;
     p.out_i[static_cast<size_t>(q) * k + r] = -1;
@@ -502,7 +547,84 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
   }
 }
 
-// Stage 2 of the split merge: exact scores of the rows stage 1 selected, 32 rows per CTA (8 warps x 4
+// ---------------------------------------------------------------------------------------
+// Three-kernel merge for a handful of queries with a large k: merge_rescore_kernel with
+// MergeParams.select_only (returns after writing the selected rows), rescore_rows_kernel, rank_rows_kernel.
+//
+// rank_rows_kernel: ranks the re-scored rows of a query by (score desc, row asc) by COUNTING - eight
+// threads per row each compare it with an eighth of the others (all in shared memory, broadcast reads),
+// 32 rows per CTA, k'/32 CTAs per query - writes the first k in order, the FAISS padding when there are
+// fewer than k, and certifies the answer exactly as merge_rescore_kernel does (the thread that owns the
+// k-th best does it).
+static __global__ void __launch_bounds__(256) rank_rows_kernel(const MergeParams p, const CorpusView cv) {
+  extern __shared__ __align__(16) uint8_t ksm[];
+  const int q = blockIdx.y;
+  const int nsel = p.sel_n_g[q];
+  if (nsel < 0) return;  // zero query / handed to the exact path by the selection kernel
+  if (blockIdx.x != 0 && blockIdx.x * 32 >= nsel) return;  // no row of this CTA (CTA 0 also pads / certifies)
+  unsigned long long* sk = reinterpret_cast<unsigned long long*>(ksm);  // order-preserving score keys
+  unsigned* rw = reinterpret_cast<unsigned*>(sk + p.sort_n);
+  const int tid = threadIdx.x, k = p.k;
+  for (int j = tid; j < nsel; j += 256) {
+    sk[j] = score_key(p.sel_score_g[static_cast<size_t>(q) * p.sort_n + j]);
+    rw[j] = p.sel_row_g[static_cast<size_t>(q) * p.sort_n + j];
+  }
+  __syncthreads();
+  const int i = blockIdx.x * 32 + (tid >> 3), part = tid & 7;
+  const bool have = i < nsel;
+  const unsigned long long ki = have ? sk[i] : 0ull;
+  const double si = key_score(ki);
+  const unsigned ri = have ? rw[i] : 0u;
+  const int chunk = (nsel + 7) >> 3;
+  int rank = 0;
+  if (have) {
+    const int j1 = min(nsel, (part + 1) * chunk);
+#pragma unroll 4
+    for (int j = part * chunk; j < j1; ++j) rank += better_key(sk[j], rw[j], ki, ri) ? 1 : 0;
+  }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+  if (have && part == 0 && rank < k) {
+    p.out_d[static_cast<size_t>(q) * k + rank] = static_cast<float>(si);
+    p.out_i[static_cast<size_t>(q) * k + rank] = static_cast<long long>(ri) + cv.row_offset;
+    if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + rank] = si;
+  }
+  if (blockIdx.x == 0)
+    for (int r = nsel + tid; r < k; r += 256) {  // fewer than k rows: FAISS pads -FLT_MAX / -1
+      p.out_d[static_cast<size_t>(q) * k + r] = -FLT_MAX;
+      p.out_i[static_cast<size_t>(q) * k + r] = -1;
+      if (p.out_d64) p.out_d64[static_cast<size_t>(q) * k + r] = -static_cast<double>(FLT_MAX);
+    }
+  // certificate: by the owner of the k-th best, or by the first thread when there are fewer than k rows
+  const bool owner = nsel >= k ? (have && part == 0 && rank == k - 1) : (blockIdx.x == 0 && tid == 0);
+  if (owner) {
+    const float a_min = p.sel_amin_g[q];
+    bool certified;
+    double theta = 0.0;
+    if (a_min == -CUDART_INF_F) {
+      certified = true;  // nothing was ever dropped: every row of the corpus was re-scored
+    } else {
+      const double unscale = 1.0 / (static_cast<double>(p.qscale[q]) * cv.scan_scale);
+      const double eps = static_cast<double>(cv.max_row_norm) * p.qnorm[q] * cv.rel_err;
+      const double bound = static_cast<double>(a_min) * unscale + eps;  // >= any dropped row's exact score
+      if (nsel >= k) {
+        certified = si > bound;
+        theta = si;
+      } else {
+        certified = false;
+        theta = static_cast<double>(a_min) * unscale - eps;
+      }
+    }
+    if (!certified) {
+      const int slot = atomicAdd(p.flag_count, 1);
+      p.flag_list[slot] = q;
+      p.flag_theta[slot] = theta;
+    }
+  }
+}
+
+// rescore_rows_kernel: exact scores of the selected rows, 32 rows per CTA (8 warps x 4
 // rows in flight), grid = (sort_n / 32, nq) - the gathers of one query are spread over every SM.  Same
 // warp_exact_dots as the one-kernel path: identical bits.
 static __global__ void __launch_bounds__(256) rescore_rows_kernel(const MergeParams p, const CorpusView cv) {
