@@ -17,6 +17,8 @@ import torch
 
 from . import _lib
 
+MAX_K = 2048  # lxg_search returns LXG_EUNSUPPORTED above this (include/lxg.h)
+
 
 def _current_stream_ptr(device: int) -> int:
     return int(torch.cuda.current_stream(device).cuda_stream)
@@ -125,6 +127,9 @@ class GpuIndexFlatIP:
             raise ValueError(f"search expects [nq, {self.d}] float32")
         if k <= 0:
             raise ValueError("k must be positive")
+        if k > MAX_K:
+            raise ValueError(f"k = {k}: this index returns at most {MAX_K} neighbours per query (FAISS has no such limit; "
+                             "the engine's faiss_k defaults to 1000, engine.py:538)")
         self._materialise()
         nq = x.shape[0]
         # results land in page-locked memory (torch's caching host allocator): the library then
@@ -143,6 +148,8 @@ class GpuIndexFlatIP:
             raise ValueError(f"search_torch expects a float32 CUDA tensor [nq, {self.d}]")
         if k <= 0:
             raise ValueError("k must be positive")
+        if k > MAX_K:
+            raise ValueError(f"k = {k}: this index returns at most {MAX_K} neighbours per query")
         x = x.contiguous()
         self._materialise()
         nq = x.shape[0]

@@ -124,6 +124,11 @@ def test_empty_index_and_zero_queries():
     assert ix.ntotal == 10
     D, I = ix.search(np.zeros((0, 64), dtype=np.float32), 3)
     assert D.shape == (0, 3) and I.shape == (0, 3)
+    # the documented limit: a clear ValueError, not a status code from deep inside
+    with pytest.raises(ValueError, match="at most 2048"):
+        ix.search(make_queries(1, 64), 2049)
+    with pytest.raises(ValueError, match="at most 2048"):
+        ix.search_torch(torch.zeros((1, 64), device="cuda"), 4096)
 
 
 def test_zero_norm_query_row():
