@@ -182,6 +182,14 @@ __device__ __forceinline__ void for_each_list_entry(const MergeParams& p, int q,
   }
 }
 
+// Histogram increment for a whole warp (call warp-uniformly): lanes that hit the same bin are
+// combined first.  Score keys of one query share their leading bits, so the first radix pass puts
+// thousands of entries into a handful of bins - one shared-memory atomic per entry would serialise.
+__device__ __forceinline__ void warp_hist_add(int* hist, uint32_t bin, bool pred) {
+  const uint32_t peers = __match_any_sync(0xffffffffu, pred ? bin : 0xFFFFFFFFu);
+  if (pred && static_cast<int>(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], __popc(peers));
+}
+
 // Warp helper of the radix selections below: the highest bin b of hist[0, nbins) with
 // sum(hist[b ..]) >= need.  out[0] = b (-1: the whole histogram holds fewer than `need`), out[1] =
 // entries in the bins above b (or the total when b = -1), out[2] = hist[b].  nbins is a multiple of 32.
@@ -326,7 +334,7 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
         const int hs = shift + nbits;  // bits above the pass's digit must equal the prefix
         for_each_list_entry<kMergeThreads>(p, q, s_len, warp, lane, [&](const uint2& e, bool valid) {
           const uint32_t key = float_to_key(e.x);
-          if (valid && (hs >= 32 || (key >> hs) == (prefix >> hs))) atomicAdd(&hist[(key >> shift) & (nbins - 1)], 1);
+          warp_hist_add(hist, (key >> shift) & (nbins - 1), valid && (hs >= 32 || (key >> hs) == (prefix >> hs)));
         });
         __syncthreads();
         if (warp == 0) radix_boundary_bin(hist, nbins, p.kp - above, lane, s_cnt);
@@ -396,9 +404,9 @@ merge_rescore_kernel(const MergeParams p, const CorpusView cv) {
         for (int i = tid; i < nbins; i += kMergeThreads) hist[i] = 0;
         __syncthreads();
         const int hs = shift + nbits;
-        for (int i = tid; i < m; i += kMergeThreads) {
-          const uint32_t key = items[i].x;
-          if (hs >= 32 || (key >> hs) == (pre >> hs)) atomicAdd(&hist[(key >> shift) & (nbins - 1)], 1);
+        for (int i = tid; (i & ~31) < m; i += kMergeThreads) {  // warp-uniform trip count
+          const uint32_t key = i < m ? items[i].x : 0u;
+          warp_hist_add(hist, (key >> shift) & (nbins - 1), i < m && (hs >= 32 || (key >> hs) == (pre >> hs)));
         }
         __syncthreads();
         if (warp == 0) radix_boundary_bin(hist, nbins, p.kp - above, lane, s_cnt);
