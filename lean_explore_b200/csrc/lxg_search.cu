@@ -31,6 +31,7 @@ static bool g_inited = false;
 constexpr int kMaxDevices = 64;
 static int g_sms[kMaxDevices] = {0};  // SM count of every device lxg_init has brought up (0 = not initialised)
 static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
+static bool g_debug_counts = false;  // LXG_DEBUG_COUNTS=1: candidates per query after pass 1 -> stderr (synchronises)
 static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
 static bool g_asmem_768 = true;      // LXG_SCAN_ASMEM=0: 512 < d <= 768 falls back to 64-row tiles, all of A in tensor memory (A/B)
 static int g_sync_mb = 28;           // LXG_SCAN_SYNC_MB: L2 megabytes the readers' spread may cover (all slices together)
@@ -221,14 +222,14 @@ struct Plan {
   bool pair;      // CTA pairs (cta_group::2) when there are at least two query blocks
   int grid_x;     // query blocks launched (padded to even in pair mode)
   int lists;      // candidate lists per query: one per slice and epilogue group
-  int lvl_r;      // cross-list level: every publishing list publishes its lvl_r-th best (0 = disabled)
-  int lvl_stride, lvl_slots;  // every lvl_stride-th list publishes; slots per query
+  int lvl_r;      // cross-list level: tracker depth, every list publishes its lvl_r best (0 = disabled)
+  int lvl_lg;     // log2 of the tracker ranks per list the level warps read
+  uint32_t lvl_slot, lvl_w;  // per rank class: tracker slot, rows it stands for (4 bits each)
   int max_items;  // pass-2 candidate pool (entries)
 };
 
-// Publishing lists (every stride-th one) that see at least 8*kTrack rows - the others never
-// publish a level (scan_topk.cuh).  List (slice, g) holds columns [g*gc, (g+1)*gc) of every tile of
-// the slice, gc = tile_rows / kGroups.
+// Lists that see at least 8*kTrack rows, i.e. that can fill a tracker (scan_topk.cuh).  List
+// (slice, g) holds columns [g*gc, (g+1)*gc) of every tile of the slice, gc = tile_rows / kGroups.
 int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_per_slice, int stride) {
   const int gc = tile_rows / kGroups;
   int ok = 0;
@@ -266,25 +267,36 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     pl.lists = kGroups * pl.slices;
   };
   slice_up(std::max(1, ix->sms / pl.grid_x));
-  // cross-list level: needs lists * r >= kp with r <= kTrack
-  // with hundreds of lists (one or two query blocks) only every stride-th list publishes, so that a
-  // refresh reads ~32 values per query - as long as that still leaves lists * 8 >= kp
-  pl.lvl_stride = pl.lists > 64 ? (pl.lists + 31) / 32 : 1;
-  int lv = 0;
-  for (;; --pl.lvl_stride) {
-    lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice, pl.lvl_stride);
-    if (pl.lvl_stride == 1 || (lv >= 2 && (pl.kp + lv - 1) / lv <= kTrack)) break;
+  // cross-list level = the kp-th largest of the union of the lists' trackers (scan_topk.cuh): needs
+  // lists * depth >= kp with depth <= kTrack.  The depth is the smallest that gives the union ~2 kp
+  // entries (few lists hold more than twice their share of a query's best kp).  With hundreds of lists
+  // (one or two query blocks) and a deep tracker the level warps read four ranks per list - 1st, 2nd,
+  // 4th, 8th best standing for 1, 1, 2, 4 rows - to keep a query's words within kLvlMaxWords.
+  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice, 1);
+  pl.lvl_r = 0;
+  pl.lvl_lg = 0;
+  pl.lvl_slot = pl.lvl_w = 0;
+  if (lv >= 2 && static_cast<long long>(lv) * kTrack >= pl.kp) {
+    int depth = 1;
+    while (depth < kTrack && static_cast<long long>(lv) * depth < 2LL * pl.kp) depth *= 2;
+    int ncls = depth;
+    while (pl.lists * ncls > kLvlMaxWords) ncls /= 2;
+    pl.lvl_r = depth;
+    for (int c = 0; c < ncls; ++c) {
+      // class c = rank (1-based): every rank when ncls == depth, else depth >> (ncls - 1 - c)
+      const int rank = ncls == depth ? c + 1 : depth >> (ncls - 1 - c);
+      const int prev = c == 0 ? 0 : (ncls == depth ? c : depth >> (ncls - c));
+      pl.lvl_slot |= static_cast<uint32_t>(kTrack - depth + rank - 1) << (4 * c);
+      pl.lvl_w |= static_cast<uint32_t>(rank - prev) << (4 * c);
+    }
+    while ((1 << pl.lvl_lg) < ncls) ++pl.lvl_lg;
   }
-  pl.lvl_slots = (pl.lists + pl.lvl_stride - 1) / pl.lvl_stride;
-  pl.lvl_r = lv >= 2 ? (pl.kp + lv - 1) / lv : 0;
-  if (pl.lvl_r > kTrack) pl.lvl_r = 0;
   if (pl.lvl_r > 0) {
     // lists only grow (a few hundred entries); a list that does fill up is compacted exactly
     pl.cap = std::max(1024, pl.kp + 2 * nt);
     pl.keep_max = pl.kp;
-    // typical survivors: 2-3 k' when every list publishes, ~stride/2 times more when only every
-    // stride-th does (the level then bounds a sample of the corpus); overflow is tightened exactly
-    pl.max_items = std::max(2048, 4 * pl.kp) * (pl.lvl_stride > 1 ? 3 : 1);
+    // typical survivors: a few k' over all lists; overflow is tightened exactly
+    pl.max_items = std::max(2048, 4 * pl.kp);
     // a handful of queries (the 1024-thread merge CTA has an SM's shared memory to itself): room for
     // 12 k' entries - with k' = 1408 (faiss_k = 1000) and ~290 lists publishing their 5th best, 4 k'
     // overflowed and a third of the merge went into tightening the level over global memory
@@ -388,6 +400,8 @@ int lxg_init(int device) {
   g_no_split_merge = ms && ms[0] == '0';
   const char* pm = std::getenv("LXG_SCAN_PERF_MODE");
   g_perf_mode = pm ? std::atoi(pm) : 0;
+  const char* dc = std::getenv("LXG_DEBUG_COUNTS");
+  g_debug_counts = dc && dc[0] == '1';
   g_inited = true;
   return LXG_OK;
 }
@@ -606,7 +620,9 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   // cleared together with the levels right behind them (prep kernel)
   constexpr int kProgWords = 1024;
   const size_t o_flags = take(256 + kProgWords * sizeof(int));
-  const size_t o_lvl = take(lists * sizeof(uint32_t));
+  // cross-list level: [nq] levels, then [nq, lists, kTrack] published trackers
+  const size_t lvl_words = pl.lvl_r > 0 ? (static_cast<size_t>(nq) + 63) / 64 * 64 + lists * kTrack : 0;
+  const size_t o_lvl = take(lvl_words * sizeof(uint32_t));
   // split merge (a handful of queries, large k): selected rows and their exact scores between the stages
   int sort_n = 1;
   while (sort_n < pl.kp) sort_n <<= 1;
@@ -646,8 +662,16 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.keep_max = pl.keep_max;
   sp.lvl = reinterpret_cast<uint32_t*>(sm + o_lvl);
   sp.lvl_r = pl.lvl_r;
-  sp.lvl_stride = pl.lvl_stride;
-  sp.lvl_slots = pl.lvl_slots;
+  sp.trk = sp.lvl + (static_cast<size_t>(nq) + 63) / 64 * 64;
+  sp.lvl_lg = pl.lvl_lg;
+  sp.lvl_slot = pl.lvl_slot;
+  sp.lvl_w = pl.lvl_w;
+  sp.lists = pl.lists;
+  {
+    const char* ls = std::getenv("LXG_LVL_SLEEP");
+    sp.lvl_sleep_ns = ls ? std::atoi(ls) : 0;
+  }
+  sp.lvl_dbg = g_debug_counts ? reinterpret_cast<unsigned long long*>(flag_count + 8) : nullptr;  // cleared by the prep kernel
   sp.perf_mode = g_perf_mode;
   {
     // readers of a slice are kept within ~half an L2 share of each other (see the TMA producer)
@@ -689,7 +713,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
   prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(
       x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize, reinterpret_cast<uint32_t*>(flag_count),
-      64 + kProgWords + (sp.lvl_r > 0 ? static_cast<int>(lists) : 0), reinterpret_cast<uint32_t*>(ex_count), nflag_max);
+      64 + kProgWords + static_cast<int>(lvl_words), reinterpret_cast<uint32_t*>(ex_count), nflag_max);
   LXG_CUDA(cudaGetLastError());
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[1], st));
@@ -708,6 +732,27 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   }
   ++launches;
   if (ev) LXG_CUDA(cudaEventRecord(ev[2], st));
+  if (g_debug_counts) {
+    std::vector<int> hc(lists);
+    std::vector<uint32_t> hl(sp.lvl_r > 0 ? nq : 0);
+    LXG_CUDA(cudaStreamSynchronize(st));
+    LXG_CUDA(cudaMemcpy(hc.data(), sp.cand_count, lists * sizeof(int), cudaMemcpyDeviceToHost));
+    if (!hl.empty()) LXG_CUDA(cudaMemcpy(hl.data(), sp.lvl, nq * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    long long tot = 0;
+    int mx = 0, none = 0;
+    for (int c : hc) {
+      tot += c;
+      mx = std::max(mx, c);
+    }
+    for (uint32_t l : hl) none += l == 0u;
+    unsigned long long dbg[3] = {0, 0, 0};
+    LXG_CUDA(cudaMemcpy(dbg, flag_count + 8, sizeof(dbg), cudaMemcpyDeviceToHost));
+    const double ctas = static_cast<double>(pl.grid_x) * pl.slices * kLvlWarps;
+    std::fprintf(stderr, "[lxg] level warps: %.1f rounds per warp, %.0f clocks per round selecting, %.0f clocks alive\n",
+                 dbg[0] / ctas, dbg[0] ? static_cast<double>(dbg[1]) / dbg[0] : 0.0, dbg[2] / ctas);
+    std::fprintf(stderr, "[lxg] pass 1: nq=%d kp=%d lists=%d depth=%d classes=%d  candidates/query=%.1f  longest list=%d  queries without a level=%d\n",
+                 nq, pl.kp, pl.lists, pl.lvl_r, 1 << pl.lvl_lg, static_cast<double>(tot) / nq, mx, none);
+  }
   ix->stats.slices = pl.slices;
   ix->stats.query_blocks = pl.qblocks;
   ix->stats.kp = pl.kp;
@@ -741,7 +786,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   mp.kp = pl.kp;
   mp.cap = pl.cap;
   mp.lists = pl.lists;
-  mp.lvl_slots = pl.lvl_slots;
+  mp.lvl_slots = 1;
   mp.max_items = pl.max_items;
   mp.sort_n = sort_n;
   mp.select_only = 0;

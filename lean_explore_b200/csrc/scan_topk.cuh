@@ -4,21 +4,24 @@
 // prep_queries_kernel (one warp per query): the fused L2-normalise (FAISS fvec_renorm_L2
 // semantics, engine.py:242), a power-of-two scale and the fp16 conversion of the query block.
 //
-// scan_topk_kernel: one persistent CTA per (corpus slice, block of 128 queries), 10 warps:
+// scan_topk_kernel: one persistent CTA per (corpus slice, block of 128 queries), 12 warps:
 //   * warp 8: TMA producer.  Streams the slice of the fp16 corpus ("scan copy") through a ring
 //     of 128B-swizzled shared-memory stages (N_T rows x 64 dims each) - all ~192 KB of shared
 //     memory is corpus pipeline.
 //   * warp 9: one elected thread issues tcgen05.mma (M=128 queries, N=N_T corpus rows, K=16),
 //     A (the fp16 queries) from TENSOR MEMORY, B from the swizzled stage, fp32 accumulators in
 //     TMEM, double buffered.
-//   * warps 0-7: epilogue, two groups of four.  Group g drains accumulator g (tiles g, g+2, ...):
-//     thread t owns query t of the block: tcgen05.ld 32 scores at a time (lane = query, column
-//     = corpus row), max-tree per 8 columns against the thread's threshold; survivors are
-//     appended to the (slice, group, query) candidate list in global memory (L2 resident).
-//     Thresholds come from a CROSS-LIST LEVEL: every list publishes the r-th best score it has
-//     seen (register tracker); with lists * r >= kp at least kp rows score >= the minimum of the
-//     published values, so nothing below that minimum can be among the query's best kp.
-//     Without a level (too few lists for r <= 8) a list that fills up is compacted by the warp
+//   * warps 0-7: epilogue, two groups of four.  Group g owns half of the columns of every
+//     accumulator tile; thread t owns query t of the block: tcgen05.ld 32 scores at a time (lane =
+//     query, column = corpus row), max-tree per 8 columns against the thread's threshold; survivors
+//     are appended to the (slice, group, query) candidate list in global memory (L2 resident) and
+//     feed a register tracker of the best scores the list has seen, which the thread publishes.
+//   * warps 10-11: LEVEL warps.  Thresholds come from a CROSS-LIST LEVEL: the kp-th largest of the
+//     union of all lists' published trackers (at least kp rows score >= it, so nothing below it can
+//     be among the query's best kp).  The CTAs that scan a query block deal its queries among their
+//     level warps; each selects the level of its queries over and over, off the epilogue's critical
+//     path, and the epilogue threads pick the latest value up from shared memory at every tile.
+//     Without a level (too few lists for trackers of 8) a list that fills up is compacted by its warp
 //     to its best kp entries (exact k-th-largest by bit bisection) and that raises the threshold.
 // Pass 2 (rescore.cuh) merges the lists, re-scores the survivors exactly and certifies that the
 // answer equals the exact top-k.
@@ -26,6 +29,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace lxg {
@@ -40,7 +44,7 @@ namespace lxg {
 constexpr int kGroups = LXG_EPI_GROUPS;   // epilogue warp groups: each owns N_T / kGroups columns of every tile
 constexpr int kEpiWarps = 4 * kGroups;    // four warps (the four TMEM lane quarters) per group
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kScanThreads = kEpiThreads + 64;  // + one TMA warp + one MMA warp
+constexpr int kScanThreads = kEpiThreads + 128;  // + one TMA warp + one MMA warp + two level warps
 constexpr int kKC = 64;            // fp16 elements per 128-byte swizzled row
 constexpr int kStageRing = 196608; // bytes of shared memory used as corpus pipeline (kASm == 0)
 constexpr int kScanSmemMax = 229376;  // A chunks in shared memory + pipeline when kASm > 0
@@ -48,8 +52,10 @@ constexpr int kAChunkBytes = 16384;   // one k-chunk of the query block: 128 row
 constexpr int kStageBytes = 32768; // one pipeline stage: N_T rows x (32768 / (128 N_T)) k-chunks
 constexpr int kQueryBlock = 128;   // queries per CTA == UMMA M
 constexpr int kTrack = 8;          // register tracker: best kTrack scores a list has seen
-constexpr uint32_t kLvlNone = 0u;            // list has not published a level yet
-constexpr uint32_t kLvlSkip = 0xFFFFFFFFu;   // list too short to ever publish one: not counted
+constexpr uint32_t kLvlNone = 0u;            // no level (yet): ordered keys of real scores are never 0
+constexpr uint32_t kLvlSkip = 0xFFFFFFFFu;   // (pass 2) identity of the min over level slots
+constexpr uint32_t kKeyNegInf = 0x007FFFFFu; // float_to_key(-inf): an empty tracker slot
+constexpr int kLvlMaxWords = 1280;           // tracker words per query the level warp selects over (40 per lane)
 
 struct ScanParams {
   const __half* xh;   // [query blocks * 128, dpad] prepared queries (normalised, scaled, fp16, zero padded)
@@ -57,10 +63,15 @@ struct ScanParams {
   int* cand_count;    // [lists, nq]
   float* slice_thr;   // [lists, nq] final threshold of the list: every dropped row scored <= it
   float* dbg_scores;  // optional [nq, n] raw tensor-core scores (tests only), else nullptr
-  uint32_t* lvl;      // [nq, lvl_slots] ordered key of the lvl_r-th best score a publishing list has seen
-  int lvl_r;          // (#publishing lists) * lvl_r >= kp; 0 disables the cross-list level
-  int lvl_stride;     // every lvl_stride-th list publishes (slot list / lvl_stride of lvl_slots per query):
-  int lvl_slots;      // with hundreds of lists (few queries) a refresh reads ~32 values instead of all
+  uint32_t* lvl;      // [nq] cross-list level of every query (ordered key, 0 = none yet), raised by the level warps
+  uint32_t* trk;      // [nq, lists, kTrack] published trackers: ordered keys of the best scores each list has seen
+  int lvl_r;          // tracker depth (1, 2, 4 or 8 real slots); lists * lvl_r >= kp; 0 disables the cross-list level
+  int lvl_lg;         // log2 of the number of tracker ranks ("classes") per list the level warp reads
+  uint32_t lvl_slot;  // class c reads tracker slot (lvl_slot >> 4c) & 15 ...
+  uint32_t lvl_w;     // ... which stands for (lvl_w >> 4c) & 15 rows of the list
+  int lists;          // slices * kGroups
+  int lvl_sleep_ns;
+  unsigned long long* lvl_dbg;  // level-warp diagnostics (LXG_DEBUG_COUNTS), else nullptr
   int nq, dpad, num_kc;
   int n;
   int num_tiles, slices, tiles_per_slice;
@@ -319,31 +330,245 @@ __device__ __forceinline__ void track_insert(float (&t)[kTrack], float v, bool t
   }
 }
 
-// Cross-list level: min over the lists of the published r-th best, for the
-// `nlive` queries q0.. of this warp (query q0 + lane gets its value).  lvl is query-major
-// [nq][lists]: the warp reads one query's levels with coalesced loads, 16 queries in flight.
-__device__ __forceinline__ float warp_refresh_level(const ScanParams& p, int q0, int nlive, int lane) {
-  // kBatch queries' loads are in flight together: a refresh is a chain of dependent L2 round trips
-  // (~0.7 us each), and the tile that follows cannot be released before it returns
-  constexpr int kBatch = 16;
-  const int lists = p.lvl_slots;
-  uint32_t mine = kLvlNone;
-  for (int b = 0; b < nlive; b += kBatch) {  // warp-uniform
-    uint32_t lo[kBatch];
+// ---- cross-list level.  Every list publishes its tracker (kTrack ordered keys, best
+// first behind the sentinels) after each tile that changed it.  If the published values of ALL lists
+// of a query hold at least kp entries >= L - counting a rank-r slot as r rows of its list - then at
+// least kp corpus rows score >= L and no row scoring <= L can be among the query's best kp, whichever
+// slice it lives in.  The largest such L is the kp-th largest of the (weighted) union.  A slot is
+// monotone in time, so a reader that sees a mix of old and new slots of one list only undercounts.
+//
+// The selection runs on a dedicated LEVEL WARP per CTA, off the epilogue's critical path: the CTAs
+// that scan one query block (one per slice) deal the block's queries among themselves, each computes
+// the level of its queries and raises p.lvl[q]; every level warp then copies the block's 128 levels
+// into shared memory, where the epilogue threads pick them up at their next tile.
+//
+// One query: v = lists << lg words; word i is rank class (i & (2^lg - 1)) of list i >> lg.  i = m * 32 +
+// lane, so a lane's class - its tracker slot and the rows it stands for - does not depend on m.
+//
+// Selection = bisection on the ordered keys, from the highest bit in which the query's keys differ
+// down to bit kLvlLowBit (the result is the kp-th largest rounded DOWN - by less than 0.1 % of its
+// value - still a valid level), stopping early once at most ~12 % more than kp entries reach the
+// candidate.  Registers only: the SM's shared
+// memory bandwidth belongs to the tensor cores.  NQ queries run interleaved (the chain of compare /
+// warp-reduce steps is latency, not work).
+constexpr int kLvlWarps = 2;
+constexpr int kLvlLowBit = 13;
+// rec: tracker words of the first query, qstride words between queries.  out[u] = ordered key of a
+// valid level, 0 if there is none (or the query's lists have not all published and need_complete).
+template <int PL, int NQ>
+__device__ __noinline__ void level_select(const uint32_t* __restrict__ rec, size_t qstride, int nqv, int v, int lg,
+                                             int slot_lane, int w_lane, int kp, int lane, bool need_complete,
+                                             uint32_t (&out)[NQ]) {
+  uint32_t key[NQ][PL];
+  uint32_t prefix[NQ];
+  bool done[NQ];
+  int nvalid = 0;
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) lo[u] = kLvlSkip;
-    for (int s = lane; s < lists; s += 32) {
+  for (int m = 0; m < PL; ++m) nvalid += (m * 32 + lane < v) ? 1 : 0;
+  const bool enough = __reduce_add_sync(0xffffffffu, nvalid * w_lane) >= kp;
 #pragma unroll
-      for (int u = 0; u < kBatch; ++u)
-        if (b + u < nlive) lo[u] = min(lo[u], __ldcg(p.lvl + static_cast<size_t>(q0 + b + u) * lists + s));
-    }
+  for (int u = 0; u < NQ; ++u) {
 #pragma unroll
-    for (int u = 0; u < kBatch; ++u) {
-      const uint32_t v = __reduce_min_sync(0xffffffffu, lo[u]);
-      if (lane == b + u) mine = v;
+    for (int m = 0; m < PL; ++m) {
+      const int i = m * 32 + lane;
+      key[u][m] = (u < nqv && i < v) ? __ldcg(rec + u * qstride + ((i >> lg) << 3) + slot_lane) : 0u;
     }
   }
-  return (mine != kLvlNone && mine != kLvlSkip) ? __uint_as_float(key_to_float_bits(mine)) : -CUDART_INF_F;
+  int hbmax = -1;
+#pragma unroll
+  for (int u = 0; u < NQ; ++u) {
+    uint32_t kmin = 0xFFFFFFFFu, kmax = 0u;
+#pragma unroll
+    for (int m = 0; m < PL; ++m) {
+      if (m * 32 + lane < v) {
+        kmin = min(kmin, key[u][m]);
+        kmax = max(kmax, key[u][m]);
+      }
+    }
+    kmin = __reduce_min_sync(0xffffffffu, kmin);
+    kmax = __reduce_max_sync(0xffffffffu, kmax);
+    // kmin == 0: some list has not published yet
+    const bool act = enough && u < nqv && kmax > kKeyNegInf && (kmin != 0u || !need_complete);
+    prefix[u] = act ? kmax : 0u;  // all keys equal: the level is that key
+    done[u] = !act || kmin == kmax;
+    if (!done[u]) {
+      const int hb = 31 - __clz(kmin ^ kmax);
+      prefix[u] = (hb == 31) ? 0u : (kmax & ~((2u << hb) - 1u));
+      hbmax = max(hbmax, hb);
+    }
+  }
+  // above a query's own highest differing bit a step changes nothing: the bit is either part of the
+  // common prefix already (candidate == prefix) or above every key (count 0)
+  for (int bit = hbmax; bit >= kLvlLowBit; --bit) {
+    bool all_done = true;
+#pragma unroll
+    for (int u = 0; u < NQ; ++u) {
+      const uint32_t cnd = prefix[u] | (1u << bit);
+      int mine = 0;
+#pragma unroll
+      for (int m = 0; m < PL; ++m) mine += (key[u][m] >= cnd) ? 1 : 0;
+      const int ge = __reduce_add_sync(0xffffffffu, mine * w_lane);
+      if (!done[u] && ge >= kp) {
+        prefix[u] = cnd;
+        done[u] = ge <= kp + (kp >> 3);
+      }
+      all_done = all_done && done[u];
+    }
+    if (all_done) break;
+  }
+#pragma unroll
+  for (int u = 0; u < NQ; ++u) out[u] = prefix[u] > kKeyNegInf ? prefix[u] : 0u;
+}
+
+// The cheap level of NQ queries (stride qstride words): the minimum over the lists of the tracker
+// slot that holds their r-th best, lists * r >= kp (that many rows reach it).  0 while some list has
+// not published.  All loads are issued before the first reduction: one L2 round trip per call.
+template <int PL, int NQ>
+__device__ __noinline__ void level_min(const uint32_t* __restrict__ rec, size_t qstride, int nqv, int lists, int slot,
+                                          int lane, uint32_t (&out)[NQ]) {
+  uint32_t kmin[NQ];
+#pragma unroll
+  for (int u = 0; u < NQ; ++u) {
+    kmin[u] = 0xFFFFFFFFu;
+#pragma unroll
+    for (int m = 0; m < PL; ++m) {
+      const int i = m * 32 + lane;
+      if (u < nqv && i < lists) kmin[u] = min(kmin[u], __ldcg(rec + u * qstride + (i << 3) + slot));
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < NQ; ++u) {
+    const uint32_t r = __reduce_min_sync(0xffffffffu, kmin[u]);
+    out[u] = (u < nqv && r > kKeyNegInf) ? r : 0u;
+  }
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// A level warp's loop (see above).  which: 0..kLvlWarps-1; thr_sh: the block's 128 levels as floats
+// (-inf = none yet); epi_done counts the epilogue warps that have finished their slice.
+// A round = the selection over the union for every owned query, a few queries per call, then a copy of
+// the block's levels to shared memory.  Until every query of the block has a level - the epilogue warps
+// wait for that before they take anything from their first tile - and whenever the selection could do
+// no better (lists * depth == kp), a round computes the CHEAP level instead / first: the minimum over
+// the lists of their ceil(kp / lists)-th best, one L2 round trip for up to 16 queries.  (Measured on
+// cfg2, Q = 1024: also running the cheap level in every later round costs 0.05 ms of a 0.32 ms scan.)
+struct LevelArgs {
+  unsigned long long* dbg;  // diagnostics: [0] rounds, [1] clocks spent selecting, [2] clocks alive (summed over level warps)
+  uint32_t* lvl;
+  const uint32_t* trk;
+  int lists, lg, kp, nq, depth;
+  uint32_t slot, w;
+  int sleep_ns;  // experiment knob (LXG_LVL_SLEEP): pause between rounds; 0 = default schedule
+};
+__device__ __noinline__ void level_service(const LevelArgs p, int qblock, int slice, int slices, int which, float* thr_sh,
+                                           volatile int* epi_done, int lane) {
+  const int q0 = qblock * kQueryBlock;
+  const int nlive = max(0, min(kQueryBlock, p.nq - q0));
+  const int lg = p.lg;
+  const int cls = lane & ((1 << lg) - 1);
+  const int slot_lane = static_cast<int>((p.slot >> (4 * cls)) & 15u);
+  const int w_lane = static_cast<int>((p.w >> (4 * cls)) & 15u);
+  const int v = p.lists << lg;
+  const int kp = p.kp;
+  // the block's queries are dealt to the level warps of the CTAs that scan it
+  const int owner = slice * kLvlWarps + which, owners = slices * kLvlWarps;
+  const bool owned = owner < nlive;
+  const size_t qwords = static_cast<size_t>(p.lists) * kTrack;
+  // cheap level: rank r = ceil(kp / lists) of every list (lists * r >= kp rows reach the minimum)
+  const int min_rank = (kp + p.lists - 1) / p.lists;
+  const bool have_min = min_rank <= p.depth;
+  const int min_slot = kTrack - p.depth + min_rank - 1;
+  const bool select_useful = p.lists * p.depth > kp;  // else the selection IS the minimum
+  const unsigned long long t0 = global_timer_ns();
+  const long long c0 = clock64();
+  long long csel = 0;
+  int round = 0;
+  bool have_all = false;  // every query of this warp's half of the block has had a level
+
+  auto copy_levels = [&]() {
+    bool all = true;
+#pragma unroll
+    for (int j = 0; j < kQueryBlock / 32 / kLvlWarps; ++j) {
+      const int t = (which * (kQueryBlock / 32 / kLvlWarps) + j) * 32 + lane;
+      if (t < nlive) {
+        const uint32_t key = __ldcg(p.lvl + q0 + t);
+        all = all && key != kLvlNone;
+        if (key != kLvlNone) {
+          const float f = __uint_as_float(key_to_float_bits(key));
+          if (f > thr_sh[t]) thr_sh[t] = f;
+        }
+      }
+    }
+    have_all = have_all || __all_sync(0xffffffffu, all);
+  };
+  auto min_levels = [&](auto pl_tag, auto nq_tag) {
+    constexpr int PL = decltype(pl_tag)::value, NQ = decltype(nq_tag)::value;
+    for (int t = owner; t < nlive; t += owners * NQ) {  // warp-uniform
+      uint32_t key[NQ];
+      level_min<PL, NQ>(p.trk + (q0 + t) * qwords, owners * qwords, min(NQ, (nlive - t + owners - 1) / owners), p.lists,
+                        min_slot, lane, key);
+#pragma unroll
+      for (int u = 0; u < NQ; ++u)
+        if (lane == u && key[u] != 0u) atomicMax(p.lvl + q0 + t + u * owners, key[u]);
+    }
+  };
+  auto select_levels = [&](auto pl_tag, auto nq_tag, bool need_complete) {
+    constexpr int PL = decltype(pl_tag)::value, NQ = decltype(nq_tag)::value;
+    for (int t = owner; t < nlive; t += owners * NQ) {  // warp-uniform
+      uint32_t key[NQ];
+      level_select<PL, NQ>(p.trk + (q0 + t) * qwords, owners * qwords, min(NQ, (nlive - t + owners - 1) / owners), v, lg,
+                           slot_lane, w_lane, kp, lane, need_complete, key);
+#pragma unroll
+      for (int u = 0; u < NQ; ++u)
+        if (lane == u && key[u] != 0u) atomicMax(p.lvl + q0 + t + u * owners, key[u]);
+    }
+  };
+
+  for (;;) {
+    const bool stop = *epi_done >= kEpiWarps;
+    // The first levels wait (bounded) for every list's first tile: a level over a part of the lists
+    // would let the first tiles dump most of their rows.  (The cheap level always needs all lists.)
+    const bool early = !have_all && global_timer_ns() - t0 < 40000ull;
+    const long long cs = clock64();
+    if (owned) {
+      if (have_min && (early || !select_useful)) {
+        if (p.lists <= 64) min_levels(std::integral_constant<int, 2>{}, std::integral_constant<int, 16>{});
+        else min_levels(std::integral_constant<int, 10>{}, std::integral_constant<int, 2>{});
+        copy_levels();
+      }
+      if (select_useful) {
+        if (v <= 160) select_levels(std::integral_constant<int, 5>{}, std::integral_constant<int, 4>{}, early);
+        else if (v <= 320) select_levels(std::integral_constant<int, 10>{}, std::integral_constant<int, 4>{}, early);
+        else if (v <= 640) select_levels(std::integral_constant<int, 20>{}, std::integral_constant<int, 2>{}, early);
+        else select_levels(std::integral_constant<int, kLvlMaxWords / 32>{}, std::integral_constant<int, 1>{}, early);
+      }
+    }
+    csel += clock64() - cs;
+    ++round;
+    copy_levels();
+    have_all = have_all || clock64() - c0 > 150000;  // bounded like the first levels
+    if (stop) break;
+    // Rounds run back to back for the first ~35 us, then an eighth of the scan's age apart.  Early
+    // on the level rises with every tile and its lag is paid in candidates (cfg2, Q = 1024: 0.29 ms
+    // with no pause, 0.30 ms with 20 us pauses, 0.57 ms with 100 us); after thousands of tiles it
+    // hardly moves, and on the long power-limited scans (cfg3 / cfg4) two warps that never rest cost
+    // 3-4 % of the clock.
+    if (have_all) {
+      const long long alive = clock64() - c0;
+      long long pause = p.sleep_ns > 0 ? static_cast<long long>(p.sleep_ns) * 2 : (alive < 65536 ? 400 : alive >> 3);
+      for (; pause > 0 && *epi_done < kEpiWarps; pause -= 4000) __nanosleep(static_cast<unsigned>(min(pause, 4000ll)) >> 1);
+    }
+  }
+  if (p.dbg != nullptr && lane == 0) {
+    atomicAdd(p.dbg, static_cast<unsigned long long>(round));
+    atomicAdd(p.dbg + 1, static_cast<unsigned long long>(csel));
+    atomicAdd(p.dbg + 2, static_cast<unsigned long long>(clock64() - c0));
+  }
 }
 
 __device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
@@ -382,11 +607,6 @@ __device__ __forceinline__ void track_chunk(const uint32_t (&r)[NC], float (&tk)
     for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
     track_insert(tk, fmax3(fmax3(v[0], v[1], v[2]), fmax3(v[3], v[4], v[5]), fmaxf(v[6], v[7])), two_slots);
   }
-}
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
 }
 
 // Cold variant (last, partial tile of the corpus; debug dump): columns >= valid are TMA zero fill.
@@ -441,7 +661,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(kPair ? 256 : 128, N_T);
   constexpr uint32_t kAccArrivals = (kPair ? 2 : 1) * kEpiWarps;  // one arrival per epilogue warp
   constexpr uint32_t kAArrivals = (kPair ? 2 : 1) * kEpiWarps;    // every epilogue warp stores part of A
-  constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
+  constexpr int kTmaWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1, kLvlWarp = kEpiWarps + 2;
 
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kStages];
@@ -450,7 +670,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ __align__(8) uint64_t a_ready_bar;
   __shared__ uint32_t tmem_base_holder;
-  __shared__ float thr_sh[kQueryBlock];  // per query: the latest cross-list level any group fetched
+  __shared__ float thr_sh[kQueryBlock];  // per query: the latest cross-list level (written by the level warp)
+  __shared__ int epi_done;               // epilogue warps that have finished their slice
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -479,6 +700,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     ptx::fence_barrier_init();
   }
   if (threadIdx.x < kQueryBlock) thr_sh[threadIdx.x] = -CUDART_INF_F;
+  if (threadIdx.x == 0) epi_done = 0;
   if (warp == kTmaWarp) {
     if (lane == 0) ptx::prefetch_tensormap(&tmap);
     if constexpr (kPair) {
@@ -641,6 +863,12 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
         }
       }
     }
+  } else if (warp >= kLvlWarp) {
+    // ------------------------------------------------------------- level warps
+    if (p.lvl_r > 0) {
+      const LevelArgs la{p.lvl_dbg, p.lvl, p.trk, p.lists, p.lvl_lg, p.kp, p.nq, p.lvl_r, p.lvl_slot, p.lvl_w, p.lvl_sleep_ns};
+      level_service(la, qblock, slice, static_cast<int>(gridDim.y), warp - kLvlWarp, thr_sh, &epi_done, lane);
+    }
   } else {
     // ------ epilogue warps: group g scans columns [g*kGroupCols, (g+1)*kGroupCols) of every
     // accumulator tile, one query per thread
@@ -706,36 +934,36 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
     const int kp = p.kp, cap = p.cap, keep_max = p.keep_max, n = p.n, lvl_r = p.lvl_r;
     float* dbg_row = (p.dbg_scores != nullptr && live) ? p.dbg_scores + static_cast<size_t>(q) * n : nullptr;
     const bool dbg = p.dbg_scores != nullptr;
-    uint32_t* lvl_mine = nullptr;  // where this list publishes its level (query-major [nq][lists])
-    const int wq0 = qblock * kQueryBlock + (warp & 3) * 32;   // first query of this warp
-    const int wlive = max(0, min(32, p.nq - wq0));            // live queries of this warp
-    if (lvl_r > 0 && live && list_id % p.lvl_stride == 0) {
-      // rows this list will see (only the last tile of the corpus can be partial): a list too short
-      // to feed its tracker kTrack group maxima never publishes a level and is not counted
-      long long rows = static_cast<long long>(my_tiles) * kGroupCols;
-      if (my_tiles > 0 && tile_end == p.num_tiles) {
-        const long long first = static_cast<long long>(p.num_tiles - 1) * N_T + grp * kGroupCols;
-        rows -= kGroupCols - max(0ll, min(static_cast<long long>(kGroupCols), static_cast<long long>(n) - first));
+    // where this list publishes its tracker (query-major [nq][lists][kTrack]: the level warp reads one
+    // query's trackers with coalesced loads)
+    uint4* const trk_mine =
+        (lvl_r > 0 && live) ? reinterpret_cast<uint4*>(p.trk + (static_cast<size_t>(q) * p.lists + list_id) * kTrack) : nullptr;
+    auto publish = [&]() {
+      if (trk_mine != nullptr && tk[kTrack - 1] > published) {
+        published = tk[kTrack - 1];
+        uint32_t w[kTrack];
+#pragma unroll
+        for (int i = 0; i < kTrack; ++i) w[i] = float_to_key(__float_as_uint(tk[i]));
+        __stcg(trk_mine, make_uint4(w[0], w[1], w[2], w[3]));
+        __stcg(trk_mine + 1, make_uint4(w[4], w[5], w[6], w[7]));
       }
-      uint32_t* slot = p.lvl + static_cast<size_t>(q) * p.lvl_slots + list_id / p.lvl_stride;
-      if (rows >= kTrack * 8) lvl_mine = slot; else __stcg(slot, kLvlSkip);
-    }
+    };
+    const volatile float* const vthr = thr_sh;
 
-    int refreshes = 0;
     const uint32_t tfull0 = ptx::opaque(ptx::smem_u32(&tmem_full_bar[0]));
     for (int it = 0; it < my_tiles; ++it) {
       const uint32_t acc = it & 1;
       ptx::mbar_wait_a(tfull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-      if (lvl_r > 0) ls.thr = fmaxf(ls.thr, thr_sh[t]);  // another group may have refreshed it
+      if (lvl_r > 0) ls.thr = fmaxf(ls.thr, vthr[t]);  // the level warp keeps raising it
       const int row0 = (tile_begin + it) * N_T + grp * kGroupCols;  // corpus row of the group's column 0
       const uint32_t tile_addr = tmem_base + lane_base + acc * N_T + grp * kGroupCols;
       if (it == 0 && lvl_r > 0 && lvl_r <= kGroupCols / 8 && !dbg && p.perf_mode == 0 && (tile_begin + 1) * N_T <= n) {
         // ---- first tile: instead of dumping all of it into the list (no threshold exists yet),
-        // pass 1 only feeds the tracker and publishes the list's level; then the warp waits
-        // (bounded: ~20 us, the other CTAs are co-resident and do the same) until every list has
-        // published, and pass 2 re-reads the accumulator - still in tensor memory - against the
-        // first cross-list level.  Lists stay ~4x shorter, which pass 2 of the search reads.
+        // pass 1 only feeds the tracker and publishes it; then the warp waits (bounded: ~50 us, the
+        // other CTAs are co-resident and do the same) until the level warps have turned every list's
+        // first tile into the first cross-list level, and pass 2 re-reads the accumulator - still in
+        // tensor memory - against it.  Lists stay ~4x shorter, which pass 2 of the search reads.
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {
           uint32_t r[kChunkCols];
@@ -743,19 +971,11 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
           ptx::tc_wait_ld();
           track_chunk(r, tk, two_slots);
         }
-        if (lvl_mine != nullptr && tk[kTrack - 1] > published) {
-          published = tk[kTrack - 1];
-          __stcg(lvl_mine, float_to_key(__float_as_uint(published)));
-        }
+        publish();
         const unsigned long long t0 = global_timer_ns();
-        float lv;
-        do {
-          lv = warp_refresh_level(p, wq0, wlive, lane);
-        } while (!__all_sync(0xffffffffu, !live || lv > -CUDART_INF_F) && global_timer_ns() - t0 < 20000ull);
-        if (live && lv > ls.thr) {
-          ls.thr = lv;
-          thr_sh[t] = lv;
-        }
+        while (!__all_sync(0xffffffffu, !live || vthr[t] > -CUDART_INF_F) && global_timer_ns() - t0 < 50000ull)
+          __nanosleep(100);
+        ls.thr = fmaxf(ls.thr, vthr[t]);
 #pragma unroll 1
         for (int c = 0; c < kGroupChunks; ++c) {
           uint32_t r[kChunkCols];
@@ -793,26 +1013,7 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       if (lane == 0) {  // one arrival per warp (in pair mode the odd CTA's arrivals are remote)
         if constexpr (kPair) ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0); else ptx::mbar_arrive(&tmem_empty_bar[acc]);
       }
-      if (lvl_r > 0) {
-        if (lvl_mine != nullptr) {
-          const float lv = tk[kTrack - 1];
-          if (lv > published) {
-            published = lv;
-            __stcg(lvl_mine, float_to_key(__float_as_uint(lv)));
-          }
-        }
-        // the groups take turns refreshing the block's thresholds (shared through thr_sh)
-        const int done = it + 1;
-        if (done <= 4 || (done <= 32 && (done & 3) == 0) || (done & 31) == 0) {
-          if ((refreshes++ % kGroups) == grp) {
-            const float lv = warp_refresh_level(p, wq0, wlive, lane);
-            if (live && lv > ls.thr) {
-              ls.thr = lv;
-              thr_sh[t] = lv;
-            }
-          }
-        }
-      }
+      publish();
       // a tile appends at most kGroupCols entries per list: keep room for the next one
       compact_full_lists(ls, cap - N_T, kp, keep_max, lane);
     }
@@ -822,6 +1023,8 @@ scan_topk_kernel(const __grid_constant__ CUtensorMap tmap, const ScanParams p) {
       p.cand_count[list] = ls.count();
       p.slice_thr[list] = ls.thr;
     }
+    __syncwarp();
+    if (lane == 0) atomicAdd(&epi_done, 1);
   }
 
   ptx::tc_fence_before();

@@ -12,9 +12,10 @@ from lean_explore_b200 import GpuIndexFlatIP  # noqa: E402
 
 dev = torch.device("cuda", 0)
 out = {}
-for name, n, d, dt in (("500k x 384 fp16", 500_000, 384, "float16"), ("400k x 1024 fp32", 400_000, 1024, "float32")):
+for name, n, d, dt in (("500k x 384 fp16", 500_000, 384, "float16"), ("400k x 1024 fp32", 400_000, 1024, "float32"),
+                       ("2M x 768 fp16", 2_000_000, 768, "float16")):
     ix = GpuIndexFlatIP.from_tensor(make_corpus_gpu(n, d, dt, dev, seed=3 if d == 1024 else 0))
-    for q, k in ((1, 50), (8, 50), (64, 50), (256, 50), (1024, 50), (1, 1000), (8, 1000), (64, 1000)):
+    for q, k in ((1, 50), (8, 50), (64, 50), (256, 50), (512, 50), (1024, 50), (4096, 50), (1, 1000), (8, 1000), (64, 1000)):
         xq = [make_queries_gpu(q, d, dev, seed=100 + s) for s in range(4)]
         for i in range(3):
             ix.search_torch(xq[i], k, normalize=True)
