@@ -15,6 +15,7 @@
 
 #include "../../include/lxg.h"
 #include "common.h"
+#include "attention_tc.cuh"
 #include "decoder_kernels.cuh"
 #include "gemm_host.cuh"
 
@@ -36,7 +37,8 @@ struct lxg_decoder {
   size_t stage_cap = 0;                // ints
   bool pack = true;                    // LXG_DECODER_PACK=0: always compute the padded rectangle
   bool pdl = true;                     // LXG_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
-  CUtensorMap map_hn{}, map_ctx{}, map_act{};
+  bool attn_tc = true;                 // LXG_ATTN_TC=0: mma.sync attention for every sequence length (A/B measurements)
+  CUtensorMap map_hn{}, map_ctx{}, map_act{}, map_qkv{};
   std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
   int launches = 0;
   int last_tokens = 0;  // tokens the last forward actually computed (after packing)
@@ -99,12 +101,14 @@ int reserve_ws(lxg_decoder* e, int tokens) {
   LXG_CUDA(cudaMalloc(&e->pos, cap * sizeof(int)));
   // rows beyond the live tokens are read by TMA (never stored): keep them finite
   LXG_CUDA(cudaMemset(e->hn, 0, cap * H * sizeof(__half)));
+  LXG_CUDA(cudaMemset(e->qkv, 0, cap * QKV * sizeof(__half)));
   LXG_CUDA(cudaMemset(e->ctx, 0, cap * C * sizeof(__half)));
   LXG_CUDA(cudaMemset(e->act, 0, cap * F * sizeof(__half)));
   int rc;
   if ((rc = make_map(&e->map_hn, e->hn, static_cast<int>(cap), static_cast<int>(H))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_ctx, e->ctx, static_cast<int>(cap), static_cast<int>(C))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_act, e->act, static_cast<int>(cap), static_cast<int>(F))) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_qkv, e->qkv, static_cast<int>(cap), static_cast<int>(QKV), kTcAttnRows)) != LXG_OK) return rc;
   e->cap_tokens = static_cast<int>(cap);
   return LXG_OK;
 }
@@ -128,8 +132,12 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   int pending = 0;  // slabs waiting to be absorbed by the next RMSNorm / the head kernel
   const int hgroup = tokens >= 2048 ? 4 : 1;  // heads per RoPE warp (cos / sin are evaluated once per warp)
   const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
-  const dim3 attn_grid((s + kCausalRows - 1) / kCausalRows, heads, b);
-  LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_causal_kernel<kHeadDim>), kCausalSmem));
+  // sequences of more than one 64-row tile: tcgen05 attention on 128-row tiles (attention_tc.cuh);
+  // shorter ones (a query) stay on the mma.sync kernel, whose tile they do not even fill
+  const bool attn_tc = e->attn_tc && s > kCausalRows;
+  const dim3 attn_grid(attn_tc ? (s + kTcAttnRows - 1) / kTcAttnRows : (s + kCausalRows - 1) / kCausalRows, heads, b);
+  if (attn_tc) LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_causal_tc_kernel), kTcAttnSmem));
+  else LXG_CUDA(ensure_dyn_smem(reinterpret_cast<const void*>(&attention_causal_kernel<kHeadDim>), kCausalSmem));
   for (int l = 0; l < e->w.layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     // input_layernorm (layer 0: fused with the embed_tokens gather)
@@ -154,8 +162,12 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     LXG_CUDA(lxg_launch(qk_norm_rope_kernel, dim3(rope_blocks), dim3(256), 0, st, pdl, e->qkv, tokens, s, pos_of, heads, kvh, hgroup,
                         reinterpret_cast<const float*>(L.q_norm), reinterpret_cast<const float*>(L.k_norm),
                         reinterpret_cast<const float*>(e->w.inv_freq), eps));
-    LXG_CUDA(lxg_launch(attention_causal_kernel<kHeadDim>, attn_grid, dim3(kCausalRows * 2), kCausalSmem, st, pdl, static_cast<const __half*>(e->qkv),
-                        static_cast<const int*>(e->mask), cu, s, heads, kvh, e->ctx));
+    if (attn_tc)
+      LXG_CUDA(lxg_launch(attention_causal_tc_kernel, attn_grid, dim3(kTcAttnThreads), kTcAttnSmem, st, pdl, e->map_qkv,
+                          static_cast<const int*>(e->mask), cu, s, heads, kvh, e->ctx));
+    else
+      LXG_CUDA(lxg_launch(attention_causal_kernel<kHeadDim>, attn_grid, dim3(kCausalRows * 2), kCausalSmem, st, pdl, static_cast<const __half*>(e->qkv),
+                          static_cast<const int*>(e->mask), cu, s, heads, kvh, e->ctx));
     // o_proj, accumulated onto the residual stream
     gp.n = H;
     gp.k = C;
@@ -412,6 +424,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   e->pack = !(pk && pk[0] == '0');
   const char* pd = std::getenv("LXG_PDL");
   e->pdl = !(pd && pd[0] == '0');
+  const char* at = std::getenv("LXG_ATTN_TC");
+  e->attn_tc = !(at && at[0] == '0');
   *out = e;
   return LXG_OK;
 }

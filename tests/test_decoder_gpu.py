@@ -63,6 +63,8 @@ def _compare_scores(got, want):
 @pytest.mark.parametrize("geom,b,s,side", [
     ("tiny", 5, 19, "left"), ("tiny", 1, 1, "left"), ("tiny", 3, 70, "right"), ("tiny", 2, 300, "left"),
     ("small", 4, 33, "left"), ("small", 7, 129, "left"), ("qwen3-0.6b", 3, 21, "left"), ("qwen3-0.6b", 2, 150, "left"),
+    # several 128-key chunks per query tile (tcgen05 attention: running-maximum rescale of the accumulator)
+    ("tiny", 2, 520, "left"), ("tiny", 3, 260, "right"),
 ])
 def test_embedding_matches_hf_oracle(geom, b, s, side):
     model, cfg, dec = _pair(geom)
