@@ -423,16 +423,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 // single-CTA kernel saturates (~50 % of the tensor peak).  The pair tile reads and writes 8 KB per
 // 128 clocks per SM.
 constexpr int kPairBN = 256;
-constexpr int kPairStageBytes = (kGemmBM + kPairBN / 2) * kGemmBK * 2;  // 32 KB per CTA
-constexpr int kPairStages = 6;
-constexpr int kPairSmem = kPairStages * kPairStageBytes + 1024;
+constexpr int kPairRing = 196608;  // bytes of shared memory used as operand pipeline
+constexpr int kPairSmem = kPairRing + 1024;
+// BN = 128 (`gemm_pair_kernel<EPI, 128>`, W staged as 64-row boxes): for N = 1024 projections over a
+// few thousand rows, where 256 x 256 tiles give every cluster at most ONE tile - no epilogue / main
+// loop overlap at all - and 256 x 128 tiles give most clusters two.  The narrower tile pays ~1.5x
+// the shared-memory traffic per flop (24 KB per 256 tensor clocks and SM, read and written).
 constexpr int kPairEpiWarps = 16;  // 4 per TMEM lane quarter (64 columns each): the epilogue is latency bound, more warps hide it
 constexpr int kPairThreads = (kPairEpiWarps + 2) * 32;
 
-template <int EPI>
+template <int EPI, int BN = kPairBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                  const GemmParams p) {
+  static_assert(BN == 256 || (BN == 128 && EPI != kEpiSwiGLU), "tile widths: 256, or 128 for the plain epilogues");
+  constexpr int kPairStageBytes = (kGemmBM + BN / 2) * kGemmBK * 2;  // 32 KB (24 KB) per CTA and stage
+  constexpr int kPairStages = kPairRing / kPairStageBytes;           // 6 (8)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kPairStages];
   __shared__ __align__(8) uint64_t empty_bar[kPairStages];
@@ -445,10 +451,10 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t rank = ptx::cluster_ctarank();
   const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int tiles_m = (p.m + 2 * kGemmBM - 1) / (2 * kGemmBM);
-  const int tiles = tiles_m * (p.n / kPairBN);
+  const int tiles = tiles_m * (p.n / BN);
   const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
   const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kGemmBM, kPairBN);
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kGemmBM, BN);
   constexpr int kTmaWarp = kPairEpiWarps, kMmaWarp = kPairEpiWarps + 1;
 
   if (warp == kMmaWarp && lane == 0) {
@@ -467,7 +473,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       ptx::prefetch_tensormap(&tmap_a);
       ptx::prefetch_tensormap(&tmap_w);
     }
-    ptx::tmem_alloc_pair(&tmem_base_holder, 2 * kPairBN);
+    ptx::tmem_alloc_pair(&tmem_base_holder, 2 * BN);
     ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
@@ -485,7 +491,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint32_t stage = 0, phase = 0;
     for (int t = cluster; t < tiles; t += nclusters) {
       const int m0 = (t % tiles_m) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
-      const int n0 = (t / tiles_m) * kPairBN + static_cast<int>(rank) * (kPairBN / 2);
+      const int n0 = (t / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
         if (ptx::elect_one()) {
@@ -516,7 +522,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t acc = it & 1;
         ptx::mbar_wait_a(aempty0 + acc * 8, ((it >> 1) & 1) ^ 1u);
         ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kPairBN;
+        const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           ptx::mbar_wait_a(full0 + stage * 8, phase);
           ptx::tc_fence_after();
@@ -540,18 +546,18 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // epilogue: thread = output row of this CTA's half of the tile, warp >> 2 = which 64 columns
+    // epilogue: thread = output row of this CTA's half of the tile, warp >> 2 = which quarter of the columns
     const int quarter = warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t afull0 = ptx::opaque(ptx::smem_u32(&acc_full_bar[0]));
     int it = 0;
     for (int t = cluster; t < tiles; t += nclusters, ++it) {
       const uint32_t acc = it & 1;
-      const int m0 = (t % tiles_m) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM, n0 = (t / tiles_m) * kPairBN;
+      const int m0 = (t % tiles_m) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM, n0 = (t / tiles_m) * BN;
       const int row = m0 + (warp & 3) * 32 + lane;
       ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-      gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kPairBN, quarter * 2, 2, row, n0, p);
+      gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * BN, quarter * (BN / 128), BN / 128, row, n0, p);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(&acc_empty_bar[acc], 0);
@@ -561,7 +567,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::cluster_sync();
   if (warp == kTmaWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc_pair(tmem_base, 2 * kPairBN);
+    ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
   }
 }
 

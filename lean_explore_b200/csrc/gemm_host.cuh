@@ -37,16 +37,37 @@ inline bool gemm_pairs_enabled() {
   return on;
 }
 
+// w64: optional second map of W with 64-row boxes (make_map(..., kPairBN128 / 2)): lets N = 1024-class
+// projections run on 256 x 128 pair tiles when 256 x 256 tiles would not even give every cluster one.
+// LXG_GEMM_NARROW=0 keeps the pair GEMMs on 256 x 256 tiles (A/B measurements)
+inline bool gemm_narrow_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("LXG_GEMM_NARROW");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 template <int EPI>
-inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st, bool pdl = false) {
+inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st, bool pdl = false,
+                               const CUtensorMap* w64 = nullptr) {
   // more than one row tile and N a multiple of 256: 256 x 256 tiles on CTA pairs
   if (gp.m > kGemmBM && gp.n % kPairBN == 0 && gemm_pairs_enabled()) {
+    const int max_clusters = std::max(1, lxg::num_sms() / 2);
+    const int tiles = ((gp.m + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (gp.n / kPairBN);
+    if constexpr (EPI != kEpiSwiGLU) {
+      if (w64 != nullptr && tiles <= max_clusters && 2 * tiles > max_clusters && gemm_narrow_enabled()) {
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_pair_kernel<EPI, 128>), kPairSmem);
+        if (e != cudaSuccess) return e;
+        return lxg_launch(gemm_pair_kernel<EPI, 128>, dim3(2 * std::min(2 * tiles, max_clusters)), dim3(kPairThreads), kPairSmem, st,
+                          pdl, a, *w64, gp);
+      }
+    }
     {
       cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_pair_kernel<EPI>), kPairSmem);
       if (e != cudaSuccess) return e;
     }
-    const int tiles = ((gp.m + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (gp.n / kPairBN);
-    const int clusters = std::min(tiles, std::max(1, lxg::num_sms() / 2));
+    const int clusters = std::min(tiles, max_clusters);
     return lxg_launch(gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(kPairThreads), kPairSmem, st, pdl, a, w, gp);
   }
   {

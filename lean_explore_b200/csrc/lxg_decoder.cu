@@ -40,6 +40,7 @@ struct lxg_decoder {
   bool attn_tc = true;                 // LXG_ATTN_TC=0: mma.sync attention for every sequence length (A/B measurements)
   CUtensorMap map_hn{}, map_ctx{}, map_act{}, map_qkv{};
   std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
+  std::vector<CUtensorMap> map_wo64, map_wdown64;  // 64-row boxes: 256 x 128 pair tiles (gemm_host.cuh)
   int launches = 0;
   int last_tokens = 0;  // tokens the last forward actually computed (after packing)
   struct Graph {
@@ -180,7 +181,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.ksplit = 0;
     } else {
       gp.out = e->resid;
-      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st, pdl));
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st, pdl, &e->map_wo64[l]));
     }
     if (pending > 0)
       LXG_CUDA(lxg_launch(rmsnorm_partial_kernel, dim3(tokens), dim3(256), 0, st, pdl, e->resid, H, reinterpret_cast<const float*>(L.ln2), eps,
@@ -206,7 +207,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.ksplit = 0;
     } else {
       gp.out = e->resid;
-      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st, pdl));
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st, pdl, &e->map_wdown64[l]));
     }
     launches += 8;
   }
@@ -405,6 +406,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   e->map_wo.resize(w->layers);
   e->map_wgu.resize(w->layers);
   e->map_wdown.resize(w->layers);
+  e->map_wo64.resize(w->layers);
+  e->map_wdown64.resize(w->layers);
   for (int l = 0; l < w->layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     const void* ptrs[] = {L.ln1, L.wqkv, L.q_norm, L.k_norm, L.wo, L.ln2, L.wgu, L.wdown};
@@ -415,7 +418,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
       }
     int rc;
     if ((rc = make_map(&e->map_wqkv[l], L.wqkv, QKV, H)) != LXG_OK || (rc = make_map(&e->map_wo[l], L.wo, H, C)) != LXG_OK ||
-        (rc = make_map(&e->map_wgu[l], L.wgu, 2 * F, H)) != LXG_OK || (rc = make_map(&e->map_wdown[l], L.wdown, H, F)) != LXG_OK) {
+        (rc = make_map(&e->map_wgu[l], L.wgu, 2 * F, H)) != LXG_OK || (rc = make_map(&e->map_wdown[l], L.wdown, H, F)) != LXG_OK ||
+        (rc = make_map(&e->map_wo64[l], L.wo, H, C, 64)) != LXG_OK || (rc = make_map(&e->map_wdown64[l], L.wdown, H, F, 64)) != LXG_OK) {
       delete e;
       return rc;
     }
