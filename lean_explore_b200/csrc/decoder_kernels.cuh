@@ -174,6 +174,96 @@ qk_norm_rope_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __
   }
 }
 
+// Bulk variant (hundreds of tokens and more): cos / sin come from a table [position][64] of (cos, sin)
+// pairs built once per workspace by rope_table_kernel - the same sincosf(pos * inv_freq[i]) values -
+// and every access is 16 bytes: 8 lanes cover one head (lane i of the 8 holds features 8i..8i+7 and
+// their rotate_half partners 64+8i..64+8i+7), a warp 4 heads per step, `steps` steps per warp.
+static __global__ void __launch_bounds__(256) rope_table_kernel(float2* __restrict__ tab, int positions,
+                                                                const float* __restrict__ inv_freq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= positions * 64) return;
+  float sn, cs;
+  sincosf(static_cast<float>(i >> 6) * inv_freq[i & 63], &sn, &cs);
+  tab[i] = make_float2(cs, sn);
+}
+
+static __global__ void __launch_bounds__(256)
+qk_norm_rope_bulk_kernel(__half* __restrict__ qkv, int tokens, int seq, const int* __restrict__ pos_of, int heads, int kv_heads, int steps,
+                         const float* __restrict__ q_w, const float* __restrict__ k_w, const float2* __restrict__ tab, float eps) {
+  constexpr int DH = 128;
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
+  const int lane = threadIdx.x & 31, sub = lane >> 3, i8 = (lane & 7) * 8;
+  const int nh = heads + kv_heads;
+  const int groups = (nh + 4 * steps - 1) / (4 * steps);
+  const int wid = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= tokens * groups) return;
+  const int t = wid / groups, h0 = (wid % groups) * 4 * steps;
+  const int pos = pos_of != nullptr ? pos_of[t] : t % seq;
+  float cs[8], sn[8];
+  {
+    const float4* tp = reinterpret_cast<const float4*>(tab + static_cast<size_t>(pos) * 64 + i8);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = __ldg(tp + j);
+      cs[2 * j] = v.x;
+      sn[2 * j] = v.y;
+      cs[2 * j + 1] = v.z;
+      sn[2 * j + 1] = v.w;
+    }
+  }
+  __half* row = qkv + static_cast<size_t>(t) * (heads + 2 * kv_heads) * DH;
+  for (int st = 0; st < steps; ++st) {
+    const int h = h0 + st * 4 + sub;
+    const bool live = h < nh;  // (whole 8-lane groups)
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    __half* p = row + (live ? h : 0) * DH + i8;
+    if (live) {
+      a = *reinterpret_cast<const uint4*>(p);
+      b = *reinterpret_cast<const uint4*>(p + 64);
+    }
+    float lo[8], hi[8];
+    {
+      const __half2* a2 = reinterpret_cast<const __half2*>(&a);
+      const __half2* b2 = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = __half22float2(a2[j]), y = __half22float2(b2[j]);
+        lo[2 * j] = x.x;
+        lo[2 * j + 1] = x.y;
+        hi[2 * j] = y.x;
+        hi[2 * j + 1] = y.y;
+      }
+    }
+    float ss = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ss += lo[j] * lo[j] + hi[j] * hi[j];
+    ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+    ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+    const float rstd = rsqrtf(ss / DH + eps);
+    if (live) {
+      const float* w = (h < heads ? q_w : k_w) + i8;
+      const float4 wl0 = __ldg(reinterpret_cast<const float4*>(w)), wl1 = __ldg(reinterpret_cast<const float4*>(w) + 1);
+      const float4 wh0 = __ldg(reinterpret_cast<const float4*>(w + 64)), wh1 = __ldg(reinterpret_cast<const float4*>(w + 64) + 1);
+      const float wl[8] = {wl0.x, wl0.y, wl0.z, wl0.w, wl1.x, wl1.y, wl1.z, wl1.w};
+      const float wh[8] = {wh0.x, wh0.y, wh0.z, wh0.w, wh1.x, wh1.y, wh1.z, wh1.w};
+      uint4 oa, ob;
+      __half2* oa2 = reinterpret_cast<__half2*>(&oa);
+      __half2* ob2 = reinterpret_cast<__half2*>(&ob);
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float x0 = lo[j] * rstd * wl[j], x1 = lo[j + 1] * rstd * wl[j + 1];
+        const float y0 = hi[j] * rstd * wh[j], y1 = hi[j + 1] * rstd * wh[j + 1];
+        oa2[j >> 1] = __floats2half2_rn(x0 * cs[j] - y0 * sn[j], x1 * cs[j + 1] - y1 * sn[j + 1]);
+        ob2[j >> 1] = __floats2half2_rn(y0 * cs[j] + x0 * sn[j], y1 * cs[j + 1] + x1 * sn[j + 1]);
+      }
+      *reinterpret_cast<uint4*>(p) = oa;
+      *reinterpret_cast<uint4*>(p + 64) = ob;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ causal GQA attention
 // Flash-style: one CTA (4 warps) per (64 query rows, q head, sequence); warp w owns 16 query rows;
 // three CTAs are resident per SM so one CTA's chunk loads overlap the others' MMAs.  Keys and

@@ -270,7 +270,11 @@ __device__ __forceinline__ void gemm_epilogue_row(uint32_t taddr, int c0, int nc
 // tcgen05.mma (SS, M=128 N=128 K=16) into one of TWO TMEM accumulators, warps 0-7 drain the other
 // one (thread = output row, warp >> 2 = column half): the epilogue of tile i (bias, erf-GELU,
 // residual, stores) overlaps the main loop of tile i+1.
-template <int EPI>
+// BN / AROWS: the query path (a few dozen rows: one row tile, weights streamed once) runs narrower
+// output tiles - N = 32 or 64 columns, so that 100+ CTAs share the weight stream instead of N / 128 -
+// and stages only the AROWS = 32 rows of A that exist (the MMA still reads 128 rows of shared
+// memory; what it makes of the unwritten ones lands in accumulator rows nobody stores).
+template <int EPI, int BN = kGemmBN, int AROWS = kGemmBM>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                const GemmParams p) {
@@ -284,12 +288,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int tiles_m = (p.m + kGemmBM - 1) / kGemmBM;
-  const int tiles_mn = tiles_m * (p.n / kGemmBN);
+  static_assert(BN == 128 || BN == 64 || (BN == 32 && EPI != kEpiSwiGLU), "tile widths: 128, 64, or 32 for the plain epilogues");
+  constexpr int kStageTx = (AROWS + BN) * kGemmBK * 2;  // bytes TMA delivers per stage
+  const int tiles_mn = tiles_m * (p.n / BN);
   const int ksplit = p.ksplit > 1 ? p.ksplit : 1;
   const int tiles = tiles_mn * ksplit;  // tile t: k range t / tiles_mn, output tile t % tiles_mn
   const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
   const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
-  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kGemmBM, kGemmBN);
+  constexpr uint32_t kIdesc = ptx::make_idesc_f16(kGemmBM, BN);
   constexpr int kTmaWarp = kGemmEpiWarps, kMmaWarp = kGemmEpiWarps + 1;
 
   if (warp == kMmaWarp && lane == 0) {
@@ -308,7 +314,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       ptx::prefetch_tensormap(&tmap_a);
       ptx::prefetch_tensormap(&tmap_w);
     }
-    ptx::tmem_alloc(&tmem_base_holder, 2 * kGemmBN);
+    ptx::tmem_alloc(&tmem_base_holder, 2 * BN);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -325,13 +331,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     uint32_t stage = 0, phase = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
       const int ks = t / tiles_mn, tt = t % tiles_mn;
-      const int m0 = (tt % tiles_m) * kGemmBM, n0 = (tt / tiles_m) * kGemmBN;
+      const int m0 = (tt % tiles_m) * kGemmBM, n0 = (tt / tiles_m) * BN;
       const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
       for (int kb = kb0; kb < kb1; ++kb) {
         ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t fb = full0 + stage * 8;
-          ptx::mbar_arrive_expect_tx_a(fb, kGemmStageBytes);
+          ptx::mbar_arrive_expect_tx_a(fb, kStageTx);
           const uint32_t dst = ring0 + stage * kGemmStageBytes;
           ptx::tma_load_2d_a(dst, &tmap_a, kb * kGemmBK, m0, fb, ptx::kEvictNormal);
           ptx::tma_load_2d_a(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, fb, ptx::kEvictLast);
@@ -356,7 +362,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const uint32_t acc = it & 1;
       ptx::mbar_wait_a(aempty0 + acc * 8, ((it >> 1) & 1) ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kGemmBN;
+      const uint32_t d_tmem = tmem_base + acc * BN;
       const int ks = t / tiles_mn;
       const int kb0 = ks * num_kb / ksplit, kb1 = (ks + 1) * num_kb / ksplit;
       for (int kb = kb0; kb < kb1; ++kb) {
@@ -381,24 +387,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else {
-    // epilogue: thread = output row of the tile, warp >> 2 = which 64 columns
+    // epilogue: thread = output row of the tile, warp >> 2 = which half of the columns (a SwiGLU
+    // tile of 64 and a tile of 32 are one thread's work: the other half only releases the accumulator)
     const int half = warp >> 2;
+    constexpr bool kOneHalf = BN == 32 || (BN == 64 && EPI == kEpiSwiGLU);
+    constexpr int kChunksPerHalf = kOneHalf ? BN / 32 : BN / 64;
+    const int c0 = kOneHalf ? 0 : half * kChunksPerHalf, nc = (kOneHalf && half == 1) ? 0 : kChunksPerHalf;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t afull0 = ptx::opaque(ptx::smem_u32(&acc_full_bar[0]));
     int it = 0;
     for (int t = blockIdx.x; t < tiles; t += gridDim.x, ++it) {
       const uint32_t acc = it & 1;
       const int ks = t / tiles_mn, tt = t % tiles_mn;
-      const int m0 = (tt % tiles_m) * kGemmBM, n0 = (tt / tiles_m) * kGemmBN;
+      const int m0 = (tt % tiles_m) * kGemmBM, n0 = (tt / tiles_m) * BN;
       const int row = m0 + (warp & 3) * 32 + lane;
       ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
       if constexpr (EPI == kEpiPartial) {
         GemmParams ps = p;  // this k range's slab
         ps.out = reinterpret_cast<float*>(p.out) + static_cast<size_t>(ks) * p.split_stride;
-        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kGemmBN, half * 2, 2, row, n0, ps);
+        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * BN, c0, nc, row, n0, ps);
       } else {
-        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * kGemmBN, half * 2, 2, row, n0, p);
+        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * BN, c0, nc, row, n0, p);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -409,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   __syncthreads();
   if (warp == kTmaWarp) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, 2 * kGemmBN);
+    ptx::tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 

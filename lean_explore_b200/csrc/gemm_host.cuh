@@ -78,4 +78,17 @@ inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const
   return lxg_launch(gemm_tc_kernel<EPI>, dim3(std::min(tiles, std::max(1, lxg::num_sms()))), dim3(kGemmThreads), kGemmSmem, st, pdl, a, w, gp);
 }
 
+// Query path (at most 32 rows): narrow output tiles, A staged as one 32-row box per k-block.
+// a32 = map of A with 32-row boxes, wbn = map of W with BN-row boxes.
+template <int EPI, int BN>
+inline cudaError_t launch_gemm_query(const CUtensorMap& a32, const CUtensorMap& wbn, const GemmParams& gp, cudaStream_t st, bool pdl) {
+  {
+    cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<EPI, BN, 32>), kGemmSmem);
+    if (e != cudaSuccess) return e;
+  }
+  const int tiles = (gp.n / BN) * std::max(1, gp.ksplit);
+  return lxg_launch(gemm_tc_kernel<EPI, BN, 32>, dim3(std::min(tiles, std::max(1, lxg::num_sms()))), dim3(kGemmThreads), kGemmSmem, st, pdl,
+                    a32, wbn, gp);
+}
+
 }  // namespace lxg

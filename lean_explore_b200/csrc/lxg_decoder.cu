@@ -32,6 +32,8 @@ struct lxg_decoder {
   __half *hn = nullptr, *qkv = nullptr, *ctx = nullptr, *act = nullptr;  // normed rows, QKV, context, SwiGLU output
   int *ids = nullptr, *mask = nullptr;
   int *pos = nullptr, *cu = nullptr;   // packed batches: position of every token, sequence offsets [b + 1]
+  float2* rope_tab = nullptr;          // (cos, sin) [positions][64] for the bulk RoPE kernel
+  int rope_positions = 0;
   int cu_cap = 0;
   int* stage = nullptr;                // pinned host staging: packed ids | pos | cu
   size_t stage_cap = 0;                // ints
@@ -39,8 +41,12 @@ struct lxg_decoder {
   bool pdl = true;                     // LXG_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
   bool attn_tc = true;                 // LXG_ATTN_TC=0: mma.sync attention for every sequence length (A/B measurements)
   CUtensorMap map_hn{}, map_ctx{}, map_act{}, map_qkv{};
+  CUtensorMap map_hn32{}, map_ctx32{}, map_act32{};  // 32-row boxes: the query path's GEMMs (gemm_host.cuh)
+  bool rope_bulk = true;                              // LXG_ROPE_BULK=0: per-warp sincosf RoPE kernel for every batch size
+  bool query_gemm = true;                             // LXG_QUERY_GEMM=0: 128 x 128 tiles for every row count
   std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
   std::vector<CUtensorMap> map_wo64, map_wdown64;  // 64-row boxes: 256 x 128 pair tiles (gemm_host.cuh)
+  std::vector<CUtensorMap> map_wqkv32, map_wgu64;  // query path: 32- / 64-column output tiles
   int launches = 0;
   int last_tokens = 0;  // tokens the last forward actually computed (after packing)
   struct Graph {
@@ -59,6 +65,7 @@ namespace {
 
 constexpr int kHeadDim = 128;
 constexpr int kSkinnyRows = 128;    // up to one row tile the o_proj / down_proj GEMMs are split along K ...
+constexpr size_t kRopeTablePositions = 16384;
 constexpr int kSkinnySplits = 16;   // ... into this many ranges (8 output tiles x 16 = 128 CTAs instead of 8)
 
 void drop_graphs(lxg_decoder* e) {
@@ -73,6 +80,9 @@ void free_ws(lxg_decoder* e) {
   e->partial = nullptr;
   cudaFree(e->hn);
   cudaFree(e->qkv);
+  cudaFree(e->rope_tab);
+  e->rope_tab = nullptr;
+  e->rope_positions = 0;
   cudaFree(e->ctx);
   cudaFree(e->act);
   cudaFree(e->ids);
@@ -100,16 +110,27 @@ int reserve_ws(lxg_decoder* e, int tokens) {
   LXG_CUDA(cudaMalloc(&e->ids, cap * sizeof(int)));
   LXG_CUDA(cudaMalloc(&e->mask, cap * sizeof(int)));
   LXG_CUDA(cudaMalloc(&e->pos, cap * sizeof(int)));
+  // no position exceeds the token capacity; beyond kRopeTablePositions the per-warp sincosf kernel serves
+  e->rope_positions = static_cast<int>(std::min<size_t>(cap, kRopeTablePositions));
+  LXG_CUDA(cudaMalloc(&e->rope_tab, static_cast<size_t>(e->rope_positions) * 64 * sizeof(float2)));
+  rope_table_kernel<<<(e->rope_positions * 64 + 255) / 256, 256>>>(e->rope_tab, e->rope_positions,
+                                                                  reinterpret_cast<const float*>(e->w.inv_freq));
+  LXG_CUDA(cudaGetLastError());
   // rows beyond the live tokens are read by TMA (never stored): keep them finite
   LXG_CUDA(cudaMemset(e->hn, 0, cap * H * sizeof(__half)));
   LXG_CUDA(cudaMemset(e->qkv, 0, cap * QKV * sizeof(__half)));
   LXG_CUDA(cudaMemset(e->ctx, 0, cap * C * sizeof(__half)));
   LXG_CUDA(cudaMemset(e->act, 0, cap * F * sizeof(__half)));
+  // the table kernel and the memsets ran on the legacy stream; forwards run on non-blocking ones
+  LXG_CUDA(cudaDeviceSynchronize());
   int rc;
   if ((rc = make_map(&e->map_hn, e->hn, static_cast<int>(cap), static_cast<int>(H))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_ctx, e->ctx, static_cast<int>(cap), static_cast<int>(C))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_act, e->act, static_cast<int>(cap), static_cast<int>(F))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_qkv, e->qkv, static_cast<int>(cap), static_cast<int>(QKV), kTcAttnRows)) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_hn32, e->hn, static_cast<int>(cap), static_cast<int>(H), 32)) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_ctx32, e->ctx, static_cast<int>(cap), static_cast<int>(C), 32)) != LXG_OK) return rc;
+  if ((rc = make_map(&e->map_act32, e->act, static_cast<int>(cap), static_cast<int>(F), 32)) != LXG_OK) return rc;
   e->cap_tokens = static_cast<int>(cap);
   return LXG_OK;
 }
@@ -128,11 +149,17 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   // skinny path (one row tile): o_proj / down_proj have only H / 128 output tiles, so K is split
   // and the partial slabs are added to the residual stream by the kernel that reads it next
   const bool skinny = tokens <= kSkinnyRows;
+  // at most 32 rows (a query): narrow output tiles so that every SM takes part in the weight stream
+  const bool query = e->query_gemm && tokens <= 32;
   const size_t slab = static_cast<size_t>(kSkinnyRows) * H;
   const bool pdl = e->pdl;
   int pending = 0;  // slabs waiting to be absorbed by the next RMSNorm / the head kernel
   const int hgroup = tokens >= 2048 ? 4 : 1;  // heads per RoPE warp (cos / sin are evaluated once per warp)
   const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
+  // bulk batches: table-driven, 16-byte accesses (decoder_kernels.cuh); positions are < s
+  constexpr int kRopeBulkSteps = 2;  // 8 heads per warp
+  const bool rope_bulk = e->rope_bulk && tokens >= 256 && s <= e->rope_positions;
+  const int rope_bulk_blocks = (tokens * ((heads + kvh + 4 * kRopeBulkSteps - 1) / (4 * kRopeBulkSteps)) + 7) / 8;
   // sequences of more than one 64-row tile: tcgen05 attention on 128-row tiles (attention_tc.cuh);
   // shorter ones (a query) stay on the mma.sync kernel, whose tile they do not even fill
   const bool attn_tc = e->attn_tc && s > kCausalRows;
@@ -159,10 +186,16 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     gp.out = e->qkv;
     gp.n = QKV;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st, pdl));
-    LXG_CUDA(lxg_launch(qk_norm_rope_kernel, dim3(rope_blocks), dim3(256), 0, st, pdl, e->qkv, tokens, s, pos_of, heads, kvh, hgroup,
-                        reinterpret_cast<const float*>(L.q_norm), reinterpret_cast<const float*>(L.k_norm),
-                        reinterpret_cast<const float*>(e->w.inv_freq), eps));
+    if (query) LXG_CUDA((launch_gemm_query<kEpiStore, 32>(e->map_hn32, e->map_wqkv32[l], gp, st, pdl)));
+    else LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st, pdl));
+    if (rope_bulk)
+      LXG_CUDA(lxg_launch(qk_norm_rope_bulk_kernel, dim3(rope_bulk_blocks), dim3(256), 0, st, pdl, e->qkv, tokens, s, pos_of, heads, kvh,
+                          kRopeBulkSteps, reinterpret_cast<const float*>(L.q_norm), reinterpret_cast<const float*>(L.k_norm),
+                          static_cast<const float2*>(e->rope_tab), eps));
+    else
+      LXG_CUDA(lxg_launch(qk_norm_rope_kernel, dim3(rope_blocks), dim3(256), 0, st, pdl, e->qkv, tokens, s, pos_of, heads, kvh, hgroup,
+                          reinterpret_cast<const float*>(L.q_norm), reinterpret_cast<const float*>(L.k_norm),
+                          reinterpret_cast<const float*>(e->w.inv_freq), eps));
     if (attn_tc)
       LXG_CUDA(lxg_launch(attention_causal_tc_kernel, attn_grid, dim3(kTcAttnThreads), kTcAttnSmem, st, pdl, e->map_qkv,
                           static_cast<const int*>(e->mask), cu, s, heads, kvh, e->ctx));
@@ -176,7 +209,8 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.out = e->partial;
       gp.ksplit = std::min(kSkinnySplits, C / kGemmBK);
       gp.split_stride = slab;
-      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_ctx, e->map_wo[l], gp, st, pdl));
+      if (query) LXG_CUDA((launch_gemm_query<kEpiPartial, 128>(e->map_ctx32, e->map_wo[l], gp, st, pdl)));
+      else LXG_CUDA(launch_gemm<kEpiPartial>(e->map_ctx, e->map_wo[l], gp, st, pdl));
       pending = gp.ksplit;
       gp.ksplit = 0;
     } else {
@@ -194,7 +228,8 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     gp.out = e->act;
     gp.n = 2 * F;
     gp.k = H;
-    LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st, pdl));
+    if (query) LXG_CUDA((launch_gemm_query<kEpiSwiGLU, 64>(e->map_hn32, e->map_wgu64[l], gp, st, pdl)));
+    else LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st, pdl));
     // down_proj, accumulated onto the residual stream
     gp.n = H;
     gp.k = F;
@@ -202,7 +237,8 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.out = e->partial;
       gp.ksplit = std::min(kSkinnySplits, F / kGemmBK);
       gp.split_stride = slab;
-      LXG_CUDA(launch_gemm<kEpiPartial>(e->map_act, e->map_wdown[l], gp, st, pdl));
+      if (query) LXG_CUDA((launch_gemm_query<kEpiPartial, 128>(e->map_act32, e->map_wdown[l], gp, st, pdl)));
+      else LXG_CUDA(launch_gemm<kEpiPartial>(e->map_act, e->map_wdown[l], gp, st, pdl));
       pending = gp.ksplit;
       gp.ksplit = 0;
     } else {
@@ -408,6 +444,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   e->map_wdown.resize(w->layers);
   e->map_wo64.resize(w->layers);
   e->map_wdown64.resize(w->layers);
+  e->map_wqkv32.resize(w->layers);
+  e->map_wgu64.resize(w->layers);
   for (int l = 0; l < w->layers; ++l) {
     const lxg_qwen3_layer& L = e->layers[l];
     const void* ptrs[] = {L.ln1, L.wqkv, L.q_norm, L.k_norm, L.wo, L.ln2, L.wgu, L.wdown};
@@ -419,7 +457,8 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
     int rc;
     if ((rc = make_map(&e->map_wqkv[l], L.wqkv, QKV, H)) != LXG_OK || (rc = make_map(&e->map_wo[l], L.wo, H, C)) != LXG_OK ||
         (rc = make_map(&e->map_wgu[l], L.wgu, 2 * F, H)) != LXG_OK || (rc = make_map(&e->map_wdown[l], L.wdown, H, F)) != LXG_OK ||
-        (rc = make_map(&e->map_wo64[l], L.wo, H, C, 64)) != LXG_OK || (rc = make_map(&e->map_wdown64[l], L.wdown, H, F, 64)) != LXG_OK) {
+        (rc = make_map(&e->map_wo64[l], L.wo, H, C, 64)) != LXG_OK || (rc = make_map(&e->map_wdown64[l], L.wdown, H, F, 64)) != LXG_OK ||
+        (rc = make_map(&e->map_wqkv32[l], L.wqkv, QKV, H, 32)) != LXG_OK || (rc = make_map(&e->map_wgu64[l], L.wgu, 2 * F, H, 64)) != LXG_OK) {
       delete e;
       return rc;
     }
@@ -428,6 +467,10 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   e->pack = !(pk && pk[0] == '0');
   const char* pd = std::getenv("LXG_PDL");
   e->pdl = !(pd && pd[0] == '0');
+  const char* rb = std::getenv("LXG_ROPE_BULK");
+  e->rope_bulk = !(rb && rb[0] == '0');
+  const char* qg = std::getenv("LXG_QUERY_GEMM");
+  e->query_gemm = !(qg && qg[0] == '0');
   const char* at = std::getenv("LXG_ATTN_TC");
   e->attn_tc = !(at && at[0] == '0');
   *out = e;

@@ -17,7 +17,20 @@ model, cfg = qwen3_random_model()
 dec = Qwen3Decoder(model.state_dict(), hidden=cfg.hidden_size, layers=cfg.num_hidden_layers,
                    heads=cfg.num_attention_heads, kv_heads=cfg.num_key_value_heads, ffn=cfg.intermediate_size,
                    head_dim=cfg.head_dim, rms_eps=cfg.rms_norm_eps, rope_theta=1e6)
-out = {"LXG_ATTN_TC": os.environ.get("LXG_ATTN_TC"), "LXG_DECODER_PACK": os.environ.get("LXG_DECODER_PACK")}
+out = {k: os.environ.get(k) for k in ("LXG_ATTN_TC", "LXG_DECODER_PACK", "LXG_GEMM_NARROW", "LXG_QUERY_GEMM") if os.environ.get(k)}
+for b, s in ((1, 24), (1, 12), (1, 32)):  # the query path: one short text
+    ids, mask = ragged_left_padded_ids(b, s, seed=5)
+    mask[:] = 1
+    for _ in range(5):
+        v = dec.embed_ids(ids, mask)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    n = 200
+    for _ in range(n):
+        v = dec.embed_ids(ids, mask)
+    torch.cuda.synchronize()
+    out[f"embed {b}x{s} ms"] = round((time.perf_counter() - t0) / n * 1e3, 4)
+    out[f"embed {b}x{s} v"] = [round(float(x), 5) for x in v[0, :3]]
 ref = None
 for b, s in ((16, 256), (50, 256), (16, 512), (64, 128)):
     ids, mask = ragged_left_padded_ids(b, s, seed=5)

@@ -65,6 +65,8 @@ def _compare_scores(got, want):
     ("small", 4, 33, "left"), ("small", 7, 129, "left"), ("qwen3-0.6b", 3, 21, "left"), ("qwen3-0.6b", 2, 150, "left"),
     # several 128-key chunks per query tile (tcgen05 attention: running-maximum rescale of the accumulator)
     ("tiny", 2, 520, "left"), ("tiny", 3, 260, "right"),
+    # at most 32 tokens: the query path's narrow-tile GEMMs (32- / 64-column tiles, 32-row A boxes)
+    ("qwen3-0.6b", 1, 24, "left"), ("small", 1, 32, "left"), ("tiny", 2, 16, "left"), ("small", 2, 9, "right"),
 ])
 def test_embedding_matches_hf_oracle(geom, b, s, side):
     model, cfg, dec = _pair(geom)
