@@ -3,9 +3,20 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <string>
 
 namespace lxg {
+// NVTX range around an entry point / phase (header-only NVTX 3: a no-op unless a profiler is attached).
+// nsys / ncu --nvtx show the request path as lxg_search { prep | scan | merge | exact }, lxg_encode,
+// lxg_decoder_embed / lxg_decoder_rerank, lxg_merge_topk.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 // Records `msg` as the calling thread's last error and returns `code`.
 int set_error(int code, const std::string& msg);
 bool is_device_ptr(const void* p);

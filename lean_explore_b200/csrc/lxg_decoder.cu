@@ -266,6 +266,7 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
   }
   if (b == 0) return LXG_OK;
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("lxg_decoder forward (embed / rerank)");
   std::lock_guard<std::mutex> lock(e->mu);
   cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
   const long long tokens_ll = static_cast<long long>(b) * s;

@@ -428,6 +428,7 @@ int lxg_encode(lxg_encoder* e, const int32_t* ids, const int32_t* mask, int32_t 
   if (pool != LXG_POOL_MEAN && pool != LXG_POOL_CLS) return set_error(LXG_EINVAL, "bad pooling mode");
   if (b == 0) return LXG_OK;
   DeviceGuard guard(e->device);
+  NvtxRange nvtx("lxg_encode");
   std::lock_guard<std::mutex> lock(e->mu);
   cudaStream_t caller = reinterpret_cast<cudaStream_t>(stream);
   const long long tokens_ll = static_cast<long long>(b) * s;

@@ -711,6 +711,8 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
     ix->ev_used += 5;
   }
   if (ev) LXG_CUDA(cudaEventRecord(ev[0], st));
+  {
+  NvtxRange nvtx_scan("lxg_search: prep + scan (TMA + tcgen05 + level warps)");
   prep_queries_kernel<<<(nq_pad + 7) / 8, 256, 0, st>>>(
       x, xn, xh, qscale, qnorm, nq, nq_pad, d, dpad, normalize, reinterpret_cast<uint32_t*>(flag_count),
       64 + kProgWords + static_cast<int>(lvl_words), reinterpret_cast<uint32_t*>(ex_count), nflag_max);
@@ -731,6 +733,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
     else LXG_CUDA((launch_scan<64, false>(ix, sp, pl.grid_x, st)));
   }
   ++launches;
+  }
   if (ev) LXG_CUDA(cudaEventRecord(ev[2], st));
   if (g_debug_counts) {
     std::vector<int> hc(lists);
@@ -767,6 +770,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
     return LXG_OK;
   }
 
+  NvtxRange nvtx_merge("lxg_search: merge + exact re-score + certificate");
   MergeParams mp{};
   mp.cand = sp.cand;
   mp.cand_count = sp.cand_count;
@@ -861,6 +865,7 @@ int lxg_search_ex(lxg_index* ix, const float* x, int32_t nq, int32_t k, int norm
   if (nq == 0) return LXG_OK;
   if (!x) return set_error(LXG_EINVAL, "x is NULL");
   DeviceGuard guard(ix->device);
+  NvtxRange nvtx("lxg_search_ex");
   std::lock_guard<std::mutex> lock(ix->mu);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const int d = ix->cv.d;

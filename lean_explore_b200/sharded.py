@@ -117,7 +117,12 @@ class ShardedFlatIP:
             else:
                 gathered = torch.empty((self.world, 2, nq, k), dtype=torch.int64, device=packed.device)
             # (gloo wants the concatenated shape [world * 2, nq, k]; the bytes are the same)
+            nvtx = packed.is_cuda
+            if nvtx:
+                torch.cuda.nvtx.range_push("ShardedFlatIP: all_gather of the per-shard top-k")
             dist.all_gather_into_tensor(gathered.view(self.world * 2, nq, k), packed, group=self.group)  # the single exchange step
+            if nvtx:
+                torch.cuda.nvtx.range_pop()
         if ev:
             ev[2].record()
         out = self._merge(gathered, k)
