@@ -514,26 +514,40 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
-  ptx::pdl_wait();
-  ptx::pdl_launch_dependents();
 
   if (warp == kTmaWarp) {
     // both CTAs load their halves; all bytes are counted on the even CTA's full barrier
     const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
     const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
     const uint32_t ring0 = ptx::opaque(ring_u32);
+    // the first ring-full of WEIGHT tiles goes out before the dependency is awaited (see gemm_tc_kernel)
+    int pre = 0;
+    for (int t = cluster; t < tiles && pre < kPairStages; t += nclusters) {
+      const int n0 = (t / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
+      for (int kb = 0; kb < num_kb && pre < kPairStages; ++kb, ++pre) {
+        if (ptx::elect_one()) {
+          const uint32_t fb = full0 + pre * 8;
+          if (rank == 0) ptx::mbar_arrive_expect_tx_a(fb, 2 * kPairStageBytes);
+          ptx::tma_load_2d_pair_a(ring0 + pre * kPairStageBytes + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, fb, ptx::kEvictLast);
+        }
+        __syncwarp();
+      }
+    }
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     uint32_t stage = 0, phase = 0;
+    int step = 0;
     for (int t = cluster; t < tiles; t += nclusters) {
       const int m0 = (t % tiles_m) * 2 * kGemmBM + static_cast<int>(rank) * kGemmBM;
       const int n0 = (t / tiles_m) * BN + static_cast<int>(rank) * (BN / 2);
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; ++kb, ++step) {
         ptx::mbar_wait_a(empty0 + stage * 8, phase ^ 1u);
         if (ptx::elect_one()) {
           const uint32_t fb = full0 + stage * 8;
-          if (rank == 0) ptx::mbar_arrive_expect_tx_a(fb, 2 * kPairStageBytes);
+          if (rank == 0 && step >= pre) ptx::mbar_arrive_expect_tx_a(fb, 2 * kPairStageBytes);
           const uint32_t dst = ring0 + stage * kPairStageBytes;
           ptx::tma_load_2d_pair_a(dst, &tmap_a, kb * kGemmBK, m0, fb, ptx::kEvictNormal);
-          ptx::tma_load_2d_pair_a(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, fb, ptx::kEvictLast);
+          if (step >= pre) ptx::tma_load_2d_pair_a(dst + kGemmBM * kGemmBK * 2, &tmap_w, kb * kGemmBK, n0, fb, ptx::kEvictLast);
         }
         __syncwarp();
         if (++stage == kPairStages) {
@@ -543,6 +557,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == kMmaWarp) {
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     if (rank == 0) {
       const uint32_t full0 = ptx::opaque(ptx::smem_u32(&full_bar[0]));
       const uint32_t empty0 = ptx::opaque(ptx::smem_u32(&empty_bar[0]));
@@ -580,6 +596,8 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
+    ptx::pdl_wait();
+    ptx::pdl_launch_dependents();
     // epilogue: thread = output row of this CTA's half of the tile, warp >> 2 = which quarter of the columns
     const int quarter = warp >> 2;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
