@@ -373,12 +373,23 @@ def run_workload(key, wl, args, dev, rank, world, peaks, sharded, cpu_baseline, 
     gbs = bytes_alg / (scan_ms / 1e3) / 1e9
     tensor_frac, hbm_frac = tf / peaks["tflops"], gbs / peaks["hbm_gbs"]
     ridge_q = peaks["tflops"] * 1e12 / (peaks["hbm_gbs"] * 1e9) * esize / 2  # flop/byte == 2 Q / esize
+    # Which measured tensor peak applies (task contract: "the burst figure for a kernel timed alone, the
+    # sustained one for a kernel timed inside a long step"): the kernel is timed per launch with CUDA events
+    # inside K back-to-back steps; when that region lasts a quarter of a second or more the chip is at its
+    # power limit for most of it (cfg4: 20 x 20 ms; `clocks` shows the SM clock and sw_power_cap) and the
+    # sustained cuBLAS figure is the ceiling; shorter regions (cfg2: 8 ms, cfg3: 45 ms) run at burst clocks.
+    long_region = ms >= 250.0
+    tpeak = peaks["tflops_sustained"] if long_region else peaks["tflops"]
     if q >= ridge_q:
-        roof = dict(bound="tensor", achieved=round(tf, 2), peak=peaks["tflops"], unit="TFLOP/s", frac=round(tensor_frac, 4))
+        roof = dict(bound="tensor", achieved=round(tf, 2), peak=tpeak, unit="TFLOP/s", frac=round(tf / tpeak, 4),
+                    frac_of_burst_peak=round(tf / peaks["tflops"], 4), frac_of_sustained_peak=round(tf / peaks["tflops_sustained"], 4))
+        psrc = ("sustained (kernel timed per launch inside a %.2f s back-to-back region)" % (ms / 1e3) if long_region
+                else "burst (kernel timed per launch, %.0f ms region)" % ms)
     else:
         roof = dict(bound="hbm", achieved=round(gbs, 1), peak=peaks["hbm_gbs"], unit="GB/s", frac=round(hbm_frac, 4))
+        psrc = "copy bandwidth (kernel timed per launch)"
     roof.update(traffic=None, traffic_source=None, kernel="scan_topk_kernel", ms_per_launch=round(scan_ms, 4),
-                peak_source=peaks["source"] + " burst (kernel timed per launch)",
+                peak_source=peaks["source"] + " " + psrc,
                 other_bound_frac=round(hbm_frac if roof["bound"] == "tensor" else tensor_frac, 4),
                 rows_per_launch=rows_local, algorithmic_bytes=int(bytes_alg), algorithmic_flops=flops,
                 prep_ms_per_launch=round(tm.get("prep_ms", 0.0) / calls, 4),
