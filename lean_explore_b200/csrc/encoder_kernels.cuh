@@ -159,7 +159,16 @@ struct GemmParams {
   int m, n, k;
   int ksplit;              // single-CTA kernel only: K is cut into ksplit ranges, one tile each (0 / 1 = off)
   size_t split_stride;     // kEpiPartial: elements between the partial slabs
+  unsigned long long* trace;  // optional device timeline of gemm_pair_kernel: [CTA][16] %globaltimer stamps (LXG_GEMM_TRACE), else NULL
 };
+
+__device__ __forceinline__ void gemm_trace(const GemmParams& p, int slot) {
+  if (p.trace != nullptr) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    p.trace[static_cast<size_t>(blockIdx.x) * 16 + slot] = t;
+  }
+}
 
 // Epilogue of one thread (= one output row) over `nchunks` 32-column chunks of an accumulator,
 // starting at chunk c0: taddr = TMEM address of the accumulator (lane field set), n0 = first
@@ -465,14 +474,27 @@ constexpr int kPairSmem = kPairRing + 1024;
 // the shared-memory traffic per flop (24 KB per 256 tensor clocks and SM, read and written).
 constexpr int kPairEpiWarps = 16;  // 4 per TMEM lane quarter (64 columns each): the epilogue is latency bound, more warps hide it
 constexpr int kPairThreads = (kPairEpiWarps + 2) * 32;
+// kTmaAcc (kEpiAccF32 only): out += result goes through the TMA engine - every epilogue warp stages its
+// 32 x 32 fp32 block in shared memory (128B-swizzled, 4 KB per warp) and issues ONE
+// cp.reduce.async.bulk.tensor (.add, f32) for it.  The read-modify-write of the fp32 residual stream
+// then happens in the L2, fully coalesced, and no epilogue thread ever waits for a global load: the
+// per-thread version (8 float4 loads of a 4 KB-strided row, add, 8 stores) kept a tile's accumulator
+// busy for 5.2-5.6 us of a 27 us GEMM (device timeline, LXG_GEMM_TRACE).  The staging blocks take 64 KB;
+// the operand ring keeps 5 (BN = 256) / 6 (BN = 128) stages instead of 6 / 8.
+constexpr int kPairAccStage = kPairEpiWarps * 4096;
+constexpr int kPairSmemAcc = 5 * 32768 + kPairAccStage + 1024;
 
-template <int EPI, int BN = kPairBN>
+template <int EPI, int BN = kPairBN, bool kTmaAcc = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kPairThreads, 1)
 gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                 const GemmParams p) {
+                 const CUtensorMap* __restrict__ tmap_out, const GemmParams p) {
+  // (tmap_out lives in device memory and travels as a pointer: a third 128-byte __grid_constant__ map
+  // pushed the parameter block past what the launch path handles cheaply - every pair-GEMM launch of
+  // the build that carried it took ~4.5 us longer, 0.5 ms per reranker forward)
   static_assert(BN == 256 || (BN == 128 && EPI != kEpiSwiGLU), "tile widths: 256, or 128 for the plain epilogues");
+  static_assert(!kTmaAcc || EPI == kEpiAccF32, "the TMA reduce epilogue is the fp32 accumulate one");
   constexpr int kPairStageBytes = (kGemmBM + BN / 2) * kGemmBK * 2;  // 32 KB (24 KB) per CTA and stage
-  constexpr int kPairStages = kPairRing / kPairStageBytes;           // 6 (8)
+  constexpr int kPairStages = (kTmaAcc ? 5 * 32768 : kPairRing) / kPairStageBytes;  // 6 (8); with staging blocks 5 (6)
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[kPairStages];
   __shared__ __align__(8) uint64_t empty_bar[kPairStages];
@@ -482,12 +504,14 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) gemm_trace(p, 0);  // slot 0: CTA start
   const uint32_t rank = ptx::cluster_ctarank();
   const int cluster = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
   const int tiles_m = (p.m + 2 * kGemmBM - 1) / (2 * kGemmBM);
   const int tiles = tiles_m * (p.n / BN);
   const int num_kb = (p.k + kGemmBK - 1) / kGemmBK;
   const uint32_t ring_u32 = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t acc_stage_u32 = ring_u32 + 5 * 32768;  // kTmaAcc: 16 x 4 KB behind the ring (1024-aligned)
   constexpr uint32_t kIdesc = ptx::make_idesc_f16(2 * kGemmBM, BN);
   constexpr int kTmaWarp = kPairEpiWarps, kMmaWarp = kPairEpiWarps + 1;
 
@@ -506,6 +530,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     if (lane == 0) {
       ptx::prefetch_tensormap(&tmap_a);
       ptx::prefetch_tensormap(&tmap_w);
+      if constexpr (kTmaAcc) ptx::prefetch_tensormap(tmap_out);
     }
     ptx::tmem_alloc_pair(&tmem_base_holder, 2 * BN);
     ptx::tmem_relinquish_pair();
@@ -514,6 +539,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   ptx::cluster_sync();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_base_holder;
+  if (threadIdx.x == 0) gemm_trace(p, 1);  // slot 1: prologue done (barriers, TMEM, cluster sync)
 
   if (warp == kTmaWarp) {
     // both CTAs load their halves; all bytes are counted on the even CTA's full barrier
@@ -535,6 +561,7 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     ptx::pdl_wait();
     ptx::pdl_launch_dependents();
+    if (lane == 0) gemm_trace(p, 2);  // slot 2: dependency resolved
     uint32_t stage = 0, phase = 0;
     int step = 0;
     for (int t = cluster; t < tiles; t += nclusters) {
@@ -609,14 +636,56 @@ gemm_pair_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int row = m0 + (warp & 3) * 32 + lane;
       ptx::mbar_wait_a(afull0 + acc * 8, (it >> 1) & 1);
       ptx::tc_fence_after();
-      gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * BN, quarter * (BN / 128), BN / 128, row, n0, p);
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+      if (threadIdx.x == 0 && it < 3) gemm_trace(p, 6 + it);  // slots 6-8: accumulator of tile 0 / 1 / 2 complete
+      if constexpr (kTmaAcc) {
+        const uint32_t stg = acc_stage_u32 + warp * 4096;
+#pragma unroll 1
+        for (int c = 0; c < BN / 128; ++c) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32b_x32(tmem_base + lane_base + acc * BN + (quarter * (BN / 128) + c) * 32, r);
+          ptx::tc_wait_ld();
+          if (c == BN / 128 - 1) {  // the accumulator is in registers: hand it back before the stores
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+          }
+          // the previous reduce of this warp has read the staging block
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          __syncwarp();
+          const bool live = row < p.m;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {  // row `lane` of the block, 16-byte unit j at j ^ (lane & 7) (SWIZZLE_128B)
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + lane * 128 + ((j ^ (lane & 7)) << 4)),
+                         "r"(live ? r[4 * j] : 0u), "r"(live ? r[4 * j + 1] : 0u), "r"(live ? r[4 * j + 2] : 0u), "r"(live ? r[4 * j + 3] : 0u)
+                         : "memory");
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const int col0 = n0 + (quarter * (BN / 128) + c) * 32;
+            asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                             reinterpret_cast<uint64_t>(tmap_out)),
+                         "r"(col0), "r"(m0 + (warp & 3) * 32), "r"(stg)
+                         : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        }
+        if (threadIdx.x == 0 && it < 3) gemm_trace(p, 9 + it);
+      } else {
+        gemm_epilogue_row<EPI>(tmem_base + lane_base + acc * BN, quarter * (BN / 128), BN / 128, row, n0, p);
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (threadIdx.x == 0 && it < 3) gemm_trace(p, 9 + it);  // slots 9-11: warp 0 drained its part of the tile
+        if (lane == 0) ptx::mbar_arrive_cluster(&acc_empty_bar[acc], 0);
+      }
     }
+  }
+  if constexpr (kTmaAcc) {
+    if (warp < kPairEpiWarps && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the reduces have landed
   }
   ptx::tc_fence_before();
   ptx::cluster_sync();
+  if (threadIdx.x == 0) gemm_trace(p, 12);  // slot 12: every warp of the pair is done
   if (warp == kTmaWarp) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_pair(tmem_base, 2 * BN);

@@ -28,6 +28,30 @@ inline int make_map(CUtensorMap* m, const void* base, int rows, int cols, int bo
   return LXG_OK;
 }
 
+// Row-major fp32 [rows, cols] as 32 x 32 boxes, 128-byte swizzle: the destination of the TMA reduce
+// epilogue (gemm_pair_kernel<kEpiAccF32, BN, true>).
+inline int make_map_f32_acc(CUtensorMap* m, void* base, int rows, int cols) {
+  cuuint64_t gdim[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t gstride[1] = {static_cast<cuuint64_t>(cols) * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = lxg::encode_tensor_map(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, gdim, gstride, box, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(LXG_ECUDA, "cuTensorMapEncodeTiled (fp32 accumulate map) failed with CUresult " + std::to_string(r));
+  return LXG_OK;
+}
+
+// LXG_GEMM_TMA_ACC=0: per-thread read-modify-write epilogue for the fp32 accumulate GEMMs (A/B measurements)
+inline bool gemm_tma_acc_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("LXG_GEMM_TMA_ACC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // LXG_GEMM_SINGLE=1 keeps every GEMM on the single-CTA kernel (A/B measurements)
 inline bool gemm_pairs_enabled() {
   static const bool on = [] {
@@ -48,19 +72,36 @@ inline bool gemm_narrow_enabled() {
   return on;
 }
 
+// out_map: optional fp32 map of the output (make_map_f32_acc) IN DEVICE MEMORY: kEpiAccF32 then accumulates
+// through TMA reduces.
 template <int EPI>
 inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const GemmParams& gp, cudaStream_t st, bool pdl = false,
-                               const CUtensorMap* w64 = nullptr) {
+                               const CUtensorMap* w64 = nullptr, const CUtensorMap* out_map = nullptr) {
   // more than one row tile and N a multiple of 256: 256 x 256 tiles on CTA pairs
   if (gp.m > kGemmBM && gp.n % kPairBN == 0 && gemm_pairs_enabled()) {
     const int max_clusters = std::max(1, lxg::num_sms() / 2);
     const int tiles = ((gp.m + 2 * kGemmBM - 1) / (2 * kGemmBM)) * (gp.n / kPairBN);
+    const bool narrow = EPI != kEpiSwiGLU && w64 != nullptr && tiles <= max_clusters && 2 * tiles > max_clusters && gemm_narrow_enabled();
+    if constexpr (EPI == kEpiAccF32) {
+      if (out_map != nullptr && gemm_tma_acc_enabled()) {
+        if (narrow) {
+          cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_pair_kernel<EPI, 128, true>), kPairSmemAcc);
+          if (e != cudaSuccess) return e;
+          return lxg_launch(gemm_pair_kernel<EPI, 128, true>, dim3(2 * std::min(2 * tiles, max_clusters)), dim3(kPairThreads), kPairSmemAcc,
+                            st, pdl, a, *w64, out_map, gp);
+        }
+        cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_pair_kernel<EPI, kPairBN, true>), kPairSmemAcc);
+        if (e != cudaSuccess) return e;
+        return lxg_launch(gemm_pair_kernel<EPI, kPairBN, true>, dim3(2 * std::min(tiles, max_clusters)), dim3(kPairThreads), kPairSmemAcc, st,
+                          pdl, a, w, out_map, gp);
+      }
+    }
     if constexpr (EPI != kEpiSwiGLU) {
-      if (w64 != nullptr && tiles <= max_clusters && 2 * tiles > max_clusters && gemm_narrow_enabled()) {
+      if (narrow) {
         cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_pair_kernel<EPI, 128>), kPairSmem);
         if (e != cudaSuccess) return e;
         return lxg_launch(gemm_pair_kernel<EPI, 128>, dim3(2 * std::min(2 * tiles, max_clusters)), dim3(kPairThreads), kPairSmem, st,
-                          pdl, a, *w64, gp);
+                          pdl, a, *w64, static_cast<const CUtensorMap*>(nullptr), gp);
       }
     }
     {
@@ -68,7 +109,8 @@ inline cudaError_t launch_gemm(const CUtensorMap& a, const CUtensorMap& w, const
       if (e != cudaSuccess) return e;
     }
     const int clusters = std::min(tiles, max_clusters);
-    return lxg_launch(gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(kPairThreads), kPairSmem, st, pdl, a, w, gp);
+    return lxg_launch(gemm_pair_kernel<EPI>, dim3(2 * clusters), dim3(kPairThreads), kPairSmem, st, pdl, a, w,
+                      static_cast<const CUtensorMap*>(nullptr), gp);
   }
   {
     cudaError_t e = ensure_dyn_smem(reinterpret_cast<const void*>(&gemm_tc_kernel<EPI>), kGemmSmem);

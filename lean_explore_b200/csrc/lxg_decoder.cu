@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <string>
@@ -41,7 +42,10 @@ struct lxg_decoder {
   bool pdl = true;                     // LXG_PDL=0: plain stream-ordered launches (no programmatic dependent launch)
   bool attn_tc = true;                 // LXG_ATTN_TC=0: mma.sync attention for every sequence length (A/B measurements)
   CUtensorMap map_hn{}, map_ctx{}, map_act{}, map_qkv{};
+  CUtensorMap* map_resid_dev = nullptr;               // fp32 residual stream as 32 x 32 boxes (device copy of the map): TMA reduce epilogue of o_proj / down_proj
   CUtensorMap map_hn32{}, map_ctx32{}, map_act32{};  // 32-row boxes: the query path's GEMMs (gemm_host.cuh)
+  int trace_layer = -1;                               // LXG_GEMM_TRACE=<layer>: device timeline of that layer's pair GEMMs -> stderr
+  unsigned long long* trace = nullptr;                // [4 GEMMs][296 CTAs][16]
   bool rope_bulk = true;                              // LXG_ROPE_BULK=0: per-warp sincosf RoPE kernel for every batch size
   bool query_gemm = true;                             // LXG_QUERY_GEMM=0: 128 x 128 tiles for every row count
   std::vector<CUtensorMap> map_wqkv, map_wo, map_wgu, map_wdown;
@@ -128,6 +132,12 @@ int reserve_ws(lxg_decoder* e, int tokens) {
   if ((rc = make_map(&e->map_ctx, e->ctx, static_cast<int>(cap), static_cast<int>(C))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_act, e->act, static_cast<int>(cap), static_cast<int>(F))) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_qkv, e->qkv, static_cast<int>(cap), static_cast<int>(QKV), kTcAttnRows)) != LXG_OK) return rc;
+  {
+    CUtensorMap m;
+    if ((rc = make_map_f32_acc(&m, e->resid, static_cast<int>(cap), static_cast<int>(H))) != LXG_OK) return rc;
+    if (!e->map_resid_dev) LXG_CUDA(cudaMalloc(&e->map_resid_dev, sizeof(CUtensorMap)));
+    LXG_CUDA(cudaMemcpy(e->map_resid_dev, &m, sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+  }
   if ((rc = make_map(&e->map_hn32, e->hn, static_cast<int>(cap), static_cast<int>(H), 32)) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_ctx32, e->ctx, static_cast<int>(cap), static_cast<int>(C), 32)) != LXG_OK) return rc;
   if ((rc = make_map(&e->map_act32, e->act, static_cast<int>(cap), static_cast<int>(F), 32)) != LXG_OK) return rc;
@@ -179,6 +189,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
                           reinterpret_cast<const __half*>(e->w.tok_emb), e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn));
     pending = 0;
     GemmParams gp{};
+    unsigned long long* const tr = (l == e->trace_layer && e->trace) ? e->trace : nullptr;
     gp.bias = nullptr;
     gp.residual = nullptr;
     gp.m = tokens;
@@ -186,6 +197,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     gp.out = e->qkv;
     gp.n = QKV;
     gp.k = H;
+    gp.trace = tr;
     if (query) LXG_CUDA((launch_gemm_query<kEpiStore, 32>(e->map_hn32, e->map_wqkv32[l], gp, st, pdl)));
     else LXG_CUDA(launch_gemm<kEpiStore>(e->map_hn, e->map_wqkv[l], gp, st, pdl));
     if (rope_bulk)
@@ -205,6 +217,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     // o_proj, accumulated onto the residual stream
     gp.n = H;
     gp.k = C;
+    gp.trace = tr ? tr + 296 * 16 : nullptr;
     if (skinny) {
       gp.out = e->partial;
       gp.ksplit = std::min(kSkinnySplits, C / kGemmBK);
@@ -215,7 +228,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.ksplit = 0;
     } else {
       gp.out = e->resid;
-      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st, pdl, &e->map_wo64[l]));
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_ctx, e->map_wo[l], gp, st, pdl, &e->map_wo64[l], e->map_resid_dev));
     }
     if (pending > 0)
       LXG_CUDA(lxg_launch(rmsnorm_partial_kernel, dim3(tokens), dim3(256), 0, st, pdl, e->resid, H, reinterpret_cast<const float*>(L.ln2), eps,
@@ -228,11 +241,13 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     gp.out = e->act;
     gp.n = 2 * F;
     gp.k = H;
+    gp.trace = tr ? tr + 2 * 296 * 16 : nullptr;
     if (query) LXG_CUDA((launch_gemm_query<kEpiSwiGLU, 64>(e->map_hn32, e->map_wgu64[l], gp, st, pdl)));
     else LXG_CUDA(launch_gemm<kEpiSwiGLU>(e->map_hn, e->map_wgu[l], gp, st, pdl));
     // down_proj, accumulated onto the residual stream
     gp.n = H;
     gp.k = F;
+    gp.trace = tr ? tr + 3 * 296 * 16 : nullptr;
     if (skinny) {
       gp.out = e->partial;
       gp.ksplit = std::min(kSkinnySplits, F / kGemmBK);
@@ -243,7 +258,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
       gp.ksplit = 0;
     } else {
       gp.out = e->resid;
-      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st, pdl, &e->map_wdown64[l]));
+      LXG_CUDA(launch_gemm<kEpiAccF32>(e->map_act, e->map_wdown[l], gp, st, pdl, &e->map_wdown64[l], e->map_resid_dev));
     }
     launches += 8;
   }
@@ -402,6 +417,34 @@ int run(lxg_decoder* e, const int32_t* ids, const int32_t* mask, int32_t b, int3
     rc = launch_forward(e, b, s, tokens, false, mode, tt, tf, st);
     if (rc != LXG_OK) return rc;
   }
+  if (e->trace) {  // diagnostics: timeline of the traced layer's GEMMs, CTAs 0 / 72 / 146 (even CTA of a pair), us since the CTA started
+    std::vector<unsigned long long> h(4 * 296 * 16);
+    LXG_CUDA(cudaStreamSynchronize(st));
+    LXG_CUDA(cudaMemcpy(h.data(), e->trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    static const char* names[4] = {"qkv", "o_proj", "gate|up", "down"};
+    static const char* slots[13] = {"start", "prologue", "dependency", "-", "-", "-", "acc t0", "acc t1", "acc t2",
+                                    "drain t0", "drain t1", "drain t2", "end"};
+    for (int g = 0; g < 4; ++g) {
+      unsigned long long first = ~0ull, last = 0;
+      for (int c = 0; c < 296; ++c) {
+        const unsigned long long* t = &h[(static_cast<size_t>(g) * 296 + c) * 16];
+        if (t[0]) first = std::min(first, t[0]);
+        last = std::max(last, t[12]);
+      }
+      if (last == 0) continue;
+      std::fprintf(stderr, "[lxg] %s GEMM of layer %d: %.2f us from the first CTA's start to the last CTA's end\n", names[g], e->trace_layer,
+                   (last - first) * 1e-3);
+      for (int c : {0, 72, 146}) {
+        const unsigned long long* t = &h[(static_cast<size_t>(g) * 296 + c) * 16];
+        if (!t[0]) continue;
+        std::fprintf(stderr, "[lxg]   CTA %3d (+%.2f us):", c, (t[0] - first) * 1e-3);
+        for (int k = 1; k < 13; ++k)
+          if (t[k]) std::fprintf(stderr, " %s %.2f", slots[k], (t[k] - t[0]) * 1e-3);
+        std::fprintf(stderr, "\n");
+      }
+    }
+    LXG_CUDA(cudaMemset(e->trace, 0, h.size() * sizeof(unsigned long long)));
+  }
   LXG_CUDA(cudaMemcpyAsync(out, e->out_buf, out_floats * sizeof(float), out_dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
   if (!out_dev) {
     LXG_CUDA(cudaStreamSynchronize(st));
@@ -468,6 +511,15 @@ int lxg_decoder_create(lxg_decoder** out, const lxg_qwen3_weights* w) {
   e->pack = !(pk && pk[0] == '0');
   const char* pd = std::getenv("LXG_PDL");
   e->pdl = !(pd && pd[0] == '0');
+  const char* gt = std::getenv("LXG_GEMM_TRACE");
+  if (gt && gt[0]) {
+    e->trace_layer = std::atoi(gt);
+    e->use_graphs = false;
+    if (cudaMalloc(&e->trace, 4 * 296 * 16 * sizeof(unsigned long long)) == cudaSuccess)
+      cudaMemset(e->trace, 0, 4 * 296 * 16 * sizeof(unsigned long long));
+    else
+      e->trace = nullptr;
+  }
   const char* rb = std::getenv("LXG_ROPE_BULK");
   e->rope_bulk = !(rb && rb[0] == '0');
   const char* qg = std::getenv("LXG_QUERY_GEMM");
@@ -483,6 +535,8 @@ int lxg_decoder_destroy(lxg_decoder* e) {
   DeviceGuard guard(e->device);
   free_ws(e);
   cudaFree(e->out_buf);
+  cudaFree(e->trace);
+  cudaFree(e->map_resid_dev);
   cudaFree(e->cu);
   if (e->stage) cudaFreeHost(e->stage);
   if (e->own) cudaStreamDestroy(e->own);
