@@ -72,6 +72,45 @@ rmsnorm_kernel(float* __restrict__ resid, const int* __restrict__ ids, const __h
   }
 }
 
+// Bulk variant (hidden % 128 == 0, no embedding gather): 16-byte accesses - lane l holds features
+// [4 (32 i + l), +4) of pass i - same arithmetic per element, the sum of squares in a different
+// (fixed) order.  6.8 -> ~5 us per call on 4096 x 1024 (the warp-per-token float2 version moves 3.7 TB/s).
+static __global__ void __launch_bounds__(256)
+rmsnorm_bulk_kernel(const float* __restrict__ resid, int tokens, int hidden, const float* __restrict__ w, float eps,
+                    __half* __restrict__ out) {
+  ptx::pdl_wait();
+  ptx::pdl_launch_dependents();
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (t >= tokens) return;
+  constexpr int kMax = 8;  // hidden <= 1024
+  float4 v[kMax];
+  const int n4 = hidden >> 2;
+  const float4* x4 = reinterpret_cast<const float4*>(resid + static_cast<size_t>(t) * hidden);
+  float ss = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j < n4) {
+      v[i] = x4[j];
+      ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rstd = rsqrtf(ss / hidden + eps);
+  uint2* o2 = reinterpret_cast<uint2*>(out + static_cast<size_t>(t) * hidden);
+#pragma unroll
+  for (int i = 0; i < kMax; ++i) {
+    const int j = i * 32 + lane;
+    if (j < n4) {
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + j);
+      o2[j] = make_uint2(pack_half2(v[i].x * rstd * ww.x, v[i].y * rstd * ww.y), pack_half2(v[i].z * rstd * ww.z, v[i].w * rstd * ww.w));
+    }
+  }
+}
+
 // Skinny path (<= 128 tokens): one CTA per token.  Adds the split-K partial slabs of the preceding
 // o_proj / down_proj to the residual row (slab order, so the sum is reproducible), writes the row
 // back and normalises it.  All slab loads of a thread are independent and in flight together - a

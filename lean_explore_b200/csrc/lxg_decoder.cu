@@ -168,6 +168,7 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
   const int rope_blocks = (tokens * ((heads + kvh + hgroup - 1) / hgroup) + 7) / 8;
   // bulk batches: table-driven, 16-byte accesses (decoder_kernels.cuh); positions are < s
   constexpr int kRopeBulkSteps = 2;  // 8 heads per warp
+  const bool norm_bulk = e->rope_bulk && tokens >= 256 && H % 128 == 0;  // 16-byte RMSNorm kernel (same switch as the bulk RoPE)
   const bool rope_bulk = e->rope_bulk && tokens >= 256 && s <= e->rope_positions;
   const int rope_bulk_blocks = (tokens * ((heads + kvh + 4 * kRopeBulkSteps - 1) / (4 * kRopeBulkSteps)) + 7) / 8;
   // sequences of more than one 64-row tile: tcgen05 attention on 128-row tiles (attention_tc.cuh);
@@ -184,6 +185,9 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     if (pending > 0)
       LXG_CUDA(lxg_launch(rmsnorm_partial_kernel, dim3(tokens), dim3(256), 0, st, pdl, e->resid, H, reinterpret_cast<const float*>(L.ln1), eps,
                           e->hn, static_cast<const float*>(e->partial), pending, slab));
+    else if (norm_bulk && l > 0)
+      LXG_CUDA(lxg_launch(rmsnorm_bulk_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, static_cast<const float*>(e->resid), tokens, H,
+                          reinterpret_cast<const float*>(L.ln1), eps, e->hn));
     else
       LXG_CUDA(lxg_launch(rmsnorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl && l > 0, e->resid, static_cast<const int*>(l == 0 ? e->ids : nullptr),
                           reinterpret_cast<const __half*>(e->w.tok_emb), e->w.vocab, tokens, H, reinterpret_cast<const float*>(L.ln1), eps, e->hn));
@@ -233,6 +237,9 @@ int launch_forward(lxg_decoder* e, int b, int s, int tokens, bool packed, int mo
     if (pending > 0)
       LXG_CUDA(lxg_launch(rmsnorm_partial_kernel, dim3(tokens), dim3(256), 0, st, pdl, e->resid, H, reinterpret_cast<const float*>(L.ln2), eps,
                           e->hn, static_cast<const float*>(e->partial), pending, slab));
+    else if (norm_bulk)
+      LXG_CUDA(lxg_launch(rmsnorm_bulk_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, static_cast<const float*>(e->resid), tokens, H,
+                          reinterpret_cast<const float*>(L.ln2), eps, e->hn));
     else
       LXG_CUDA(lxg_launch(rmsnorm_kernel, dim3(row_blocks), dim3(256), 0, st, pdl, e->resid, static_cast<const int*>(nullptr),
                           static_cast<const __half*>(nullptr), 0, tokens, H, reinterpret_cast<const float*>(L.ln2), eps, e->hn));
