@@ -159,6 +159,27 @@ int lxg_debug_scores(lxg_index* index, const float* x_dev, int32_t nq, int norma
  * LXG_SCAN_PERF_MODE) by lxg_init. */
 int lxg_debug_config(int no_level, int force_single, int perf_mode);
 
+/* How lxg_search would lay out pass 1 for a corpus shape and a batch (pure host arithmetic: needs no
+ * device and no lxg_init; `sms` = streaming multiprocessors of the target GPU, 148 on a B200).  Exposes the
+ * planning rules of DESIGN.md section 4.1 to the CPU test suite: query blocks of 128, corpus slices, two
+ * candidate lists per slice, the tracker depth and the tracker ranks ("classes", each standing for
+ * level_weight rows of a list) the level warps select over, list capacity and the merge pool. */
+typedef struct lxg_plan_info {
+  int32_t kp;               /* candidates certified per query: k plus the margin */
+  int32_t query_blocks;     /* blocks of 128 queries */
+  int32_t slices;           /* corpus slices per query block */
+  int32_t lists;            /* candidate lists per query */
+  int32_t tile_rows;        /* corpus rows per accumulator tile */
+  int32_t pair;             /* 1: CTA pairs (tcgen05 cta_group::2) */
+  int32_t level_depth;      /* tracker depth (0: no cross-list level, per-list compaction only) */
+  int32_t level_classes;    /* tracker ranks read per list */
+  int32_t level_rank[8];    /* 1-based rank of every class */
+  int32_t level_weight[8];  /* rows of the list a class stands for */
+  int32_t list_capacity;    /* entries per candidate list */
+  int32_t merge_pool;       /* shared-memory pool of pass 2 (entries) */
+} lxg_plan_info;
+int lxg_debug_plan(int64_t n, int32_t d, int dtype, int32_t sms, int32_t nq, int32_t k, lxg_plan_info* out);
+
 /* ---- sentence encoder (BERT-class) --------------------------------------------------
  * Replaces SentenceTransformer.encode inside EmbeddingClient.embed
  * (src/lean_explore/util/embedding_client.py:88-101): transformer forward -> pooling ->

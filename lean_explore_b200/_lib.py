@@ -39,6 +39,15 @@ class SearchStats(ctypes.Structure):
     ]
 
 
+class PlanInfo(ctypes.Structure):
+    """lxg_plan_info: the pass-1 layout lxg_debug_plan reports (include/lxg.h)."""
+    _fields_ = [
+        ("kp", c_int32), ("query_blocks", c_int32), ("slices", c_int32), ("lists", c_int32), ("tile_rows", c_int32),
+        ("pair", c_int32), ("level_depth", c_int32), ("level_classes", c_int32), ("level_rank", c_int32 * 8),
+        ("level_weight", c_int32 * 8), ("list_capacity", c_int32), ("merge_pool", c_int32),
+    ]
+
+
 class Timing(ctypes.Structure):
     _fields_ = [("calls", c_int32), ("scan_ms", c_float), ("merge_ms", c_float), ("exact_ms", c_float),
                 ("prep_ms", c_float)]
@@ -95,6 +104,7 @@ SIGNATURES = {
     "lxg_debug_scores": (c_int, [c_void_p, c_void_p, c_int32, c_int, c_void_p, c_void_p,
                                  POINTER(c_float), c_void_p]),
     "lxg_debug_config": (c_int, [c_int, c_int, c_int]),
+    "lxg_debug_plan": (c_int, [c_int64, c_int32, c_int, c_int32, c_int32, c_int32, POINTER(PlanInfo)]),
     "lxg_encoder_create": (c_int, [POINTER(c_void_p), POINTER(BertWeights)]),
     "lxg_encoder_destroy": (c_int, [c_void_p]),
     "lxg_encoder_last_launches": (c_int, [c_void_p]),

@@ -250,12 +250,35 @@ int lists_with_level(int n, int tile_rows, int num_tiles, int slices, int tiles_
   return ok;
 }
 
-Plan make_plan(const lxg_index* ix, int nq, int k) {
+// What a plan depends on (a handle's shape, or the arguments of lxg_debug_plan).
+struct PlanInput {
+  int tile_rows;
+  float rel_err;
+  int d;
+  long long n;
+  int sms;
+};
+// Tile rows and error bound of a corpus shape - shared by lxg_index_create and lxg_debug_plan.
+int tile_rows_for(int num_kc) {
+  const int a_smem = num_kc <= 8 ? 0 : (num_kc > 12 ? 8 : (g_asmem_768 ? 4 : 0));
+  return (num_kc <= 8 || a_smem > 0) ? 128 : 64;
+}
+float rel_err_for(int d, int dtype) {
+  // |tensor-core score - exact score| <= rel_err * ||row|| * ||query||  (DESIGN.md, certificate)
+  const float u16 = 1.0f / 2048.0f;  // fp16 round-to-nearest unit
+  float rel = u16 * 1.001f;          // query fp32 -> fp16
+  if (dtype == LXG_F32) rel += u16 * 1.001f;  // corpus fp32 -> fp16 scan copy
+  rel += 1.0f / 65536.0f;                     // fp32 accumulation inside the tensor core
+  rel += std::sqrt(static_cast<float>(d)) * (1.0f / 8388608.0f);  // fp16 subnormal flush of tiny elements
+  return rel;
+}
+
+Plan make_plan(const PlanInput& in, int nq, int k) {
   Plan pl;
-  const int nt = ix->tile_rows;
-  pl.kp = candidates_per_slice(k, ix->cv.rel_err, ix->cv.d, ix->cv.n);
+  const int nt = in.tile_rows;
+  pl.kp = candidates_per_slice(k, in.rel_err, in.d, in.n);
   pl.qblocks = (nq + kQueryBlock - 1) / kQueryBlock;
-  pl.num_tiles = static_cast<int>((ix->cv.n + nt - 1) / nt);
+  pl.num_tiles = static_cast<int>((in.n + nt - 1) / nt);
   pl.pair = pl.qblocks >= 2 && !g_force_single;
   pl.grid_x = pl.pair ? (pl.qblocks + 1) / 2 * 2 : pl.qblocks;
   auto slice_up = [&](int s) {
@@ -266,13 +289,13 @@ Plan make_plan(const lxg_index* ix, int nq, int k) {
     pl.slices = std::max(1, (pl.num_tiles + pl.tiles_per_slice - 1) / std::max(1, pl.tiles_per_slice));
     pl.lists = kGroups * pl.slices;
   };
-  slice_up(std::max(1, ix->sms / pl.grid_x));
+  slice_up(std::max(1, in.sms / pl.grid_x));
   // cross-list level = the kp-th largest of the union of the lists' trackers (scan_topk.cuh): needs
   // lists * depth >= kp with depth <= kTrack.  The depth is the smallest that gives the union ~2 kp
   // entries (few lists hold more than twice their share of a query's best kp).  With hundreds of lists
   // (one or two query blocks) and a deep tracker the level warps read four ranks per list - 1st, 2nd,
   // 4th, 8th best standing for 1, 1, 2, 4 rows - to keep a query's words within kLvlMaxWords.
-  const int lv = g_no_level ? 0 : lists_with_level(ix->cv.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice, 1);
+  const int lv = g_no_level ? 0 : lists_with_level(in.n, nt, pl.num_tiles, pl.slices, pl.tiles_per_slice, 1);
   pl.lvl_r = 0;
   pl.lvl_lg = 0;
   pl.lvl_slot = pl.lvl_w = 0;
@@ -417,6 +440,29 @@ int lxg_debug_config(int no_level, int force_single, int perf_mode) {
   return LXG_OK;
 }
 
+int lxg_debug_plan(int64_t n, int32_t d, int dtype, int32_t sms, int32_t nq, int32_t k, lxg_plan_info* out) {
+  if (!out || n < 0 || d <= 0 || d > 1024 || sms <= 0 || nq <= 0 || k <= 0 || (dtype != LXG_F32 && dtype != LXG_F16))
+    return set_error(LXG_EINVAL, "bad argument");
+  const int num_kc = (d + kKC - 1) / kKC;
+  const Plan pl = make_plan(PlanInput{tile_rows_for(num_kc), rel_err_for(d, dtype), d, static_cast<long long>(n), sms}, nq, k);
+  *out = lxg_plan_info{};
+  out->kp = pl.kp;
+  out->query_blocks = pl.qblocks;
+  out->slices = pl.slices;
+  out->lists = pl.lists;
+  out->tile_rows = tile_rows_for(num_kc);
+  out->pair = pl.pair ? 1 : 0;
+  out->level_depth = pl.lvl_r;
+  out->level_classes = pl.lvl_r > 0 ? 1 << pl.lvl_lg : 0;
+  for (int c = 0; c < out->level_classes; ++c) {
+    out->level_rank[c] = static_cast<int32_t>((pl.lvl_slot >> (4 * c)) & 15u) - (kTrack - pl.lvl_r) + 1;
+    out->level_weight[c] = static_cast<int32_t>((pl.lvl_w >> (4 * c)) & 15u);
+  }
+  out->list_capacity = pl.cap;
+  out->merge_pool = pl.max_items;
+  return LXG_OK;
+}
+
 int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t d, int dtype,
                      int64_t row_offset) {
   if (!out) return set_error(LXG_EINVAL, "out is NULL");
@@ -457,7 +503,7 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
   // against 2.62 ms for the 64-row-tile variant that keeps all of A in tensor memory, which
   // LXG_SCAN_ASMEM=0 still selects), 8 chunks for d <= 1024
   ix->a_smem_chunks = ix->num_kc <= 8 ? 0 : (ix->num_kc > 12 ? 8 : (g_asmem_768 ? 4 : 0));
-  ix->tile_rows = (ix->num_kc <= 8 || ix->a_smem_chunks > 0) ? 128 : 64;
+  ix->tile_rows = tile_rows_for(ix->num_kc);
   const float sqrt_d = std::sqrt(static_cast<float>(d));
   const bool alias = dtype == LXG_F16 && d % 8 == 0 && (reinterpret_cast<uintptr_t>(corpus_dev) % 16 == 0);
   if (n > 0) {
@@ -523,13 +569,7 @@ int lxg_index_create(lxg_index** out, const void* corpus_dev, int64_t n, int32_t
       return rc;
     }
   }
-  // |tensor-core score - exact score| <= rel_err * ||row|| * ||query||  (DESIGN.md, certificate)
-  const float u16 = 1.0f / 2048.0f;  // fp16 round-to-nearest unit
-  float rel = u16 * 1.001f;          // query fp32 -> fp16
-  if (dtype == LXG_F32) rel += u16 * 1.001f;  // corpus fp32 -> fp16 scan copy
-  rel += 1.0f / 65536.0f;                     // fp32 accumulation inside the tensor core
-  rel += sqrt_d * (1.0f / 8388608.0f);        // fp16 subnormal flush of tiny elements
-  ix->cv.rel_err = rel;
+  ix->cv.rel_err = rel_err_for(d, dtype);
   *out = ix;
   return LXG_OK;
 }
@@ -597,7 +637,7 @@ namespace {
 int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, float* D, long long* I,
                   double* D64, float* dbg_scores, float* dbg_qscale, cudaStream_t st, bool read_flags) {
   const int d = ix->cv.d;
-  const Plan pl = make_plan(ix, nq, k);
+  const Plan pl = make_plan(PlanInput{ix->tile_rows, ix->cv.rel_err, ix->cv.d, ix->cv.n, ix->sms}, nq, k);
   const size_t lists = static_cast<size_t>(pl.lists) * nq;
   const int nq_pad = pl.grid_x * kQueryBlock;
   const int dpad = ix->num_kc * kKC;

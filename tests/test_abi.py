@@ -102,3 +102,51 @@ def test_header_is_plain_c(tmp_path):
     out = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
                           "-I", str(HEADER.parent), str(src)], capture_output=True, text=True)
     assert out.returncode == 0, out.stderr
+
+
+def _plan(n, d, dtype, nq, k, sms=148):
+    from lean_explore_b200 import _lib
+
+    info = _lib.PlanInfo()
+    lib = _lib.load()  # loading needs no GPU; lxg_debug_plan is pure host arithmetic
+    assert lib.lxg_debug_plan(n, d, dtype, sms, nq, k, info) == 0
+    return info
+
+
+def test_pass1_plan_invariants_on_the_cpu():
+    """The planning rules of DESIGN.md 4.1 (lxg_debug_plan runs make_plan without a device): query blocks,
+    slices, the cross-list level's tracker depth / classes, list capacity - over the bench configs, the engine's
+    request shape and a sweep of odd sizes."""
+    F32, F16 = 0, 1
+    cases = [(500_000, 384, F16, q, 50) for q in (1, 8, 64, 256, 512, 1024, 4096)]
+    cases += [(2_000_000, 768, F16, 1024, 50), (16_000_000, 768, F16, 1024, 50), (50_000, 384, F32, 1000, 10),
+              (400_000, 1024, F32, 1, 1000), (400_000, 1024, F32, 64, 1000), (400_000, 1024, F32, 1024, 50)]
+    cases += [(n, d, F16, q, k) for n in (1, 100, 5_000, 77_777) for d in (64, 100, 1024) for q in (1, 129, 3000) for k in (1, 50, 2048)]
+    for n, d, dt, q, k in cases:
+        p = _plan(n, d, dt, q, k)
+        assert p.kp >= k and p.kp % 32 == 0, (n, d, q, k)
+        assert p.query_blocks == (q + 127) // 128
+        assert 1 <= p.slices <= 148 and p.lists == 2 * p.slices
+        grid_x = (p.query_blocks + 1) // 2 * 2 if p.pair else p.query_blocks
+        assert p.pair == (1 if p.query_blocks >= 2 else 0)
+        assert grid_x * p.slices <= 148 or p.slices == 1  # one co-resident CTA per SM
+        assert p.tile_rows == 128
+        if p.level_depth:
+            assert p.level_depth in (1, 2, 4, 8) and p.level_classes in (1, 2, 4, 8) and p.level_classes <= p.level_depth
+            ranks, weights = list(p.level_rank[: p.level_classes]), list(p.level_weight[: p.level_classes])
+            assert ranks == sorted(set(ranks)) and ranks[-1] == p.level_depth and all(1 <= r <= 8 for r in ranks)
+            assert sum(weights) == p.level_depth  # every row of a tracker is counted exactly once
+            assert weights == [r - (ranks[i - 1] if i else 0) for i, r in enumerate(ranks)]
+            assert p.lists * p.level_classes <= 1280  # words a level warp selects over
+            assert p.lists * p.level_depth >= p.kp  # the union can hold kp entries
+            assert p.list_capacity >= 1024 and p.merge_pool >= 4 * p.kp
+        else:
+            assert p.list_capacity >= p.kp + 2 * p.tile_rows  # per-list compaction: room for a tile between two compactions
+    # the shapes DESIGN.md quotes
+    p = _plan(500_000, 384, F16, 1024, 50)
+    assert (p.kp, p.slices, p.lists, p.pair, p.level_depth, p.level_classes) == (64, 18, 36, 1, 4, 4)
+    p = _plan(500_000, 384, F16, 1, 1000)
+    assert (p.kp, p.level_depth, p.level_classes) == (1280, 8, 4) and list(p.level_rank[:4]) == [1, 2, 4, 8] and list(p.level_weight[:4]) == [1, 1, 2, 4]
+    p = _plan(500_000, 384, F16, 4096, 50)
+    assert (p.lists, p.level_depth, p.level_classes) == (8, 8, 8)  # union == kp: the cheap level is the level
+    assert _plan(400_000, 1024, F32, 1, 1000).kp == 1408
