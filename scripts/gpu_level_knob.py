@@ -1,4 +1,4 @@
-"""Scan time and pass-1 candidates at a few batch sizes for one setting of the level-warp knobs (env)."""
+"""Scan time at a few batch sizes (cfg2 corpus) for one setting of LXG_LVL_SLEEP, the pause between level-warp rounds."""
 import json
 import os
 import sys
@@ -26,4 +26,4 @@ for q in (1, 64, 1024, 4096):
     tm = ix.get_timing()
     ix.set_timing(False)
     out[q] = round(tm["scan_ms"] / 20, 4)
-print(os.environ.get("LXG_LVL_SLEEP"), os.environ.get("LXG_LVL_FLAGS"), json.dumps(out))
+print(os.environ.get("LXG_LVL_SLEEP"), json.dumps(out))
