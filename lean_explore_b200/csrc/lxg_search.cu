@@ -31,6 +31,7 @@ static bool g_inited = false;
 constexpr int kMaxDevices = 64;
 static int g_sms[kMaxDevices] = {0};  // SM count of every device lxg_init has brought up (0 = not initialised)
 static bool g_no_level = false;      // LXG_SCAN_NOLEVEL=1: no cross-slice level (A/B measurements)
+static int g_lvl_sleep_ns = 0;        // LXG_LVL_SLEEP=<ns>: pause between level-warp rounds (experiments; 0 = the built-in schedule)
 static bool g_debug_counts = false;  // LXG_DEBUG_COUNTS=1: candidates per query after pass 1 -> stderr (synchronises)
 static int g_perf_mode = 0;          // LXG_SCAN_PERF_MODE: pipeline measurements with a crippled epilogue (wrong results)
 static bool g_asmem_768 = true;      // LXG_SCAN_ASMEM=0: 512 < d <= 768 falls back to 64-row tiles, all of A in tensor memory (A/B)
@@ -423,6 +424,8 @@ int lxg_init(int device) {
   g_no_split_merge = ms && ms[0] == '0';
   const char* pm = std::getenv("LXG_SCAN_PERF_MODE");
   g_perf_mode = pm ? std::atoi(pm) : 0;
+  const char* ls = std::getenv("LXG_LVL_SLEEP");
+  g_lvl_sleep_ns = ls ? std::atoi(ls) : 0;
   const char* dc = std::getenv("LXG_DEBUG_COUNTS");
   g_debug_counts = dc && dc[0] == '1';
   g_inited = true;
@@ -707,10 +710,7 @@ int search_device(lxg_index* ix, const float* x, int nq, int k, int normalize, f
   sp.lvl_slot = pl.lvl_slot;
   sp.lvl_w = pl.lvl_w;
   sp.lists = pl.lists;
-  {
-    const char* ls = std::getenv("LXG_LVL_SLEEP");
-    sp.lvl_sleep_ns = ls ? std::atoi(ls) : 0;
-  }
+  sp.lvl_sleep_ns = g_lvl_sleep_ns;
   sp.lvl_dbg = g_debug_counts ? reinterpret_cast<unsigned long long*>(flag_count + 8) : nullptr;  // cleared by the prep kernel
   sp.perf_mode = g_perf_mode;
   {
