@@ -236,3 +236,33 @@ def test_reranker_client_duck_type():
     assert np.abs(np.asarray(r2.scores) - np.asarray(r.scores)).max() < TOL_SCORE
     assert asyncio.run(client.rerank("q", [])).scores == []
     dec.tokenizer = None
+
+
+def test_tma_reduce_epilogue_is_bit_identical_to_the_per_thread_one(tmp_path):
+    """o_proj / down_proj accumulate onto the fp32 residual stream either through one
+    cp.reduce.async.bulk.tensor per 32 x 32 block (default) or by the row's thread (LXG_GEMM_TMA_ACC=0).
+    Every output element is the same single fp32 addition either way, so the two builds of the forward must
+    agree bit for bit.  The switch is read once per process: two child processes."""
+    import os
+    import subprocess
+    import sys
+
+    script = tmp_path / "run.py"
+    script.write_text(
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {str(Path(__file__).resolve().parents[1])!r})\n"
+        "from oracle import qwen3_decoder as qd\n"
+        "from lean_explore_b200.decoder import Qwen3Decoder\n"
+        "model, cfg = qd.make_model('small', seed=0)\n"
+        "dec = Qwen3Decoder(model.state_dict(), hidden=cfg.hidden_size, layers=cfg.num_hidden_layers, heads=cfg.num_attention_heads,\n"
+        "                   kv_heads=cfg.num_key_value_heads, ffn=cfg.intermediate_size, head_dim=cfg.head_dim, rms_eps=cfg.rms_norm_eps, rope_theta=1e6)\n"
+        "ids, mask = qd.make_inputs(7, 129, seed=7, side='left')\n"
+        "np.save(sys.argv[1], dec.embed_ids(ids, mask))\n")
+    outs = []
+    for flag in ("1", "0"):
+        out = tmp_path / f"emb_{flag}.npy"
+        env = dict(os.environ, LXG_GEMM_TMA_ACC=flag)
+        subprocess.run([sys.executable, str(script), str(out)], check=True, env=env, timeout=300)
+        outs.append(np.load(out))
+    assert outs[0].shape == (7, outs[0].shape[1]) and np.isfinite(outs[0]).all()
+    assert np.array_equal(outs[0], outs[1])
