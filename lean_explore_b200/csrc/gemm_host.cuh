@@ -61,17 +61,19 @@ inline bool gemm_pairs_enabled() {
   return on;
 }
 
-// w64: optional second map of W with 64-row boxes (make_map(..., kPairBN128 / 2)): lets N = 1024-class
-// projections run on 256 x 128 pair tiles when 256 x 256 tiles would not even give every cluster one.
-// LXG_GEMM_NARROW=0 keeps the pair GEMMs on 256 x 256 tiles (A/B measurements)
+// LXG_GEMM_NARROW=1 runs N = 1024-class projections whose 256 x 256 tiles would not even give every cluster
+// one tile on 256 x 128 tiles (w64 maps).  Off by default since the fp32 accumulate epilogue went to the TMA
+// engine: the narrow tiles bought overlap of a slow epilogue with the next main loop (29.9 -> 29.4 us per GEMM);
+// with the fast epilogue one 256 x 256 tile per cluster wins (rerank 16 x 256: 3.57 vs 3.77 ms).
 inline bool gemm_narrow_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("LXG_GEMM_NARROW");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
 
+// w64: optional second map of W with 64-row boxes (make_map(..., 64)) for the narrow tiles above.
 // out_map: optional fp32 map of the output (make_map_f32_acc) IN DEVICE MEMORY: kEpiAccF32 then accumulates
 // through TMA reduces.
 template <int EPI>
